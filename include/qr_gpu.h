@@ -1,0 +1,122 @@
+/* qr_gpu.h -- C ABI of the B200-native batched locomotion-control engine (libqr_gpu.so).
+ *
+ * Drop-in boundary for the convex-MPC hot path of TopHillRobotics/quadruped-robot.  Each entry point
+ * names the reference interface it replaces (paths relative to /root/reference/quadruped/).
+ * Plain pointers and sizes only; no C++/torch types.  All batched arrays are "problem rows":
+ * element [i][k] of an array with row length K lives at base[i*K + k] (one robot instance per row),
+ * which is what one CTA per problem reads with coalesced loads.
+ *
+ * Return value of every function: 0 on success, a negative QR_E* code on an API error (bad argument,
+ * CUDA failure).  Numerical outcomes are reported per instance in status_out:
+ *   0 converged and verified optimal (KKT conditions hold on the identified active set)
+ *   1 interior-point iterate returned (active-set verification did not settle / iteration cap)
+ *   2 infeasible or inconsistent bounds (f_max < 0)
+ *   3 non-finite input or breakdown
+ * (The reference swallows solver failures: qr_mpc_interface.cpp:436-442 ignores qpOASES' return code.)
+ */
+#ifndef QR_GPU_H
+#define QR_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QR_OK 0
+#define QR_EINVAL (-22)
+#define QR_ECUDA (-5)
+#define QR_ENOMEM (-12)
+
+#define QR_MAX_HORIZON 16 /* K_MAX_GAIT_SEGMENTS, controllers/mpc/qr_mpc_interface.h:33 */
+
+/* Replaces Quadruped::ProblemConfig + the inertia/mass SetupProblem stores in MPCRobotState
+ * (include/quadruped/controllers/mpc/qr_mpc_interface.h:107-144; SetupProblem :157,
+ * src/controllers/mpc/qr_mpc_interface.cpp:160-175).  Values are the float32 the reference keeps. */
+typedef struct {
+    int32_t horizon;  /* 1..QR_MAX_HORIZON */
+    float dt;         /* dtMPC */
+    float mu;         /* frictionCoeff (0.45 in qr_mpc_stance_leg_controller.cpp:90) */
+    float f_max;      /* totalMass * 9.81 */
+    float mass;
+    float inertia[3]; /* body-frame diagonal */
+    float weights[12];/* rpy, xyz, omega, v */
+    float alpha;      /* 4e-6 */
+} qr_mpc_params;
+
+/* Solver knobs; pass NULL for the defaults written next to each field. */
+typedef struct {
+    int32_t max_ipm_iter;     /* 40    interior-point iteration cap                              */
+    int32_t max_polish_rounds;/* 12    active-set verification / correction rounds               */
+    double ipm_tol;           /* 1e-5  scaled stationarity and complementarity-gap tolerance     */
+    double act_kappa;         /* 1e3   constraint i is guessed active when s_i < kappa*lambda_i   */
+    double feas_tol;          /* 1e-9  admissible constraint violation after the polish [N]      */
+    double mult_tol;          /* 1e-11 admissible negative multiplier after the polish           */
+} qr_qp_options;
+
+/* Device selection / workspace creation.  Must be called once per process (per GPU) before any
+ * solve.  device < 0 keeps the current CUDA device. */
+int qr_gpu_init(int device);
+void qr_gpu_shutdown(void);
+const char* qr_gpu_last_error(void);
+
+/* Number of SMs and max CTAs the fused kernel keeps resident per SM for this horizon (bench/roofline). */
+int qr_gpu_mpc_occupancy(int horizon, int* sm_count, int* ctas_per_sm, int* threads_per_cta,
+                         int* smem_bytes);
+
+/* qr_gpu_mpc_solve_batch -- replaces SolveMPCKernel + GetMPCSolution
+ * (qr_mpc_interface.h:200,215; qr_mpc_interface.cpp:334-356, 359-443, 446-451) for `batch`
+ * independent robot instances: state -> SRB model -> discretisation -> condensed QP -> solve.
+ *
+ *   p, v, w, rpy   [batch][3]   base position, world velocity, world angular velocity, roll-pitch-yaw
+ *   quat           [batch][4]   (w,x,y,z)
+ *   r_feet         [batch][12]  foot - CoM, world aligned, r_feet[3*leg+axis]  (Eigen 3x4 column-major)
+ *   traj           [batch][12h] reference trajectory (state_trajectory)
+ *   gait           [batch][4h]  contact table, row-major h x 4 floats (mpcTable.data())
+ *   mu_i, fmax_i   [batch] or NULL  per-instance friction / force limit (NULL: P->mu, P->f_max)
+ *   grf_out        [batch][12]  step-0 ground reaction forces, world frame (GetMPCSolution(0..11))
+ *   u_out          [batch][12h] or NULL  full solution vector
+ *   status_out     [batch] or NULL
+ *   iters_out      [batch][2] or NULL    {interior-point iterations, polish rounds}
+ * All pointers are DEVICE pointers; the call is asynchronous on `cuda_stream` (a cudaStream_t). */
+int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_options* opt, int batch,
+                           const float* p, const float* v, const float* quat, const float* w,
+                           const float* r_feet, const float* rpy, const float* traj,
+                           const float* gait, const float* mu_i, const float* fmax_i,
+                           float* grf_out, float* u_out, int32_t* status_out, int32_t* iters_out,
+                           void* cuda_stream);
+
+/* Same call with HOST buffers (what a reference-side caller holds): inputs are copied host->device,
+ * the fused kernel runs, results are copied device->host, and the call returns after the stream has
+ * drained.  Pageable or pinned memory both work; pinned avoids a staging copy. */
+int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_options* opt, int batch,
+                                const float* p, const float* v, const float* quat, const float* w,
+                                const float* r_feet, const float* rpy, const float* traj,
+                                const float* gait, const float* mu_i, const float* fmax_i,
+                                float* grf_out, float* u_out, int32_t* status_out,
+                                int32_t* iters_out);
+
+/* qr_gpu_mpc_condense_batch -- replaces ComputeContinuousTimeStateSpaceMatrices + ConvertToDiscreteQP
+ * + the H/g/U_b build of SolveMPC (qr_mpc_interface.cpp:296-331, 257-293, 359-412): float32 QP data
+ * with the reference's operation order.  H_out [batch][n*n] row-major, g_out [batch][n],
+ * ub_out [batch][20h] (n = 12h).  Device pointers, asynchronous on the stream. */
+int qr_gpu_mpc_condense_batch(const qr_mpc_params* P, int batch, const float* p, const float* v,
+                              const float* quat, const float* w, const float* r_feet,
+                              const float* rpy, const float* traj, const float* gait,
+                              const float* fmax_i, float* H_out, float* g_out, float* ub_out,
+                              void* cuda_stream);
+
+/* qr_gpu_qp_solve_batch -- replaces the qpOASES call of SolveMPC (qr_mpc_interface.cpp:414-438) on
+ * caller-supplied QP data: min 1/2 x'Hx + g'x  s.t. the friction-pyramid rows of ResizeQPMats
+ * (:230-240) with 0 <= A x <= ub.  H [batch][n*n] float32 row-major (symmetrised as (H+H')/2),
+ * g [batch][n], ub [batch][20h] (only entries 5k+4 are read), mu_i [batch] or NULL (then `mu`).
+ * x_out [batch][n].  Device pointers, asynchronous on the stream. */
+int qr_gpu_qp_solve_batch(int horizon, float mu, const qr_qp_options* opt, int batch,
+                          const float* H, const float* g, const float* ub, const float* mu_i,
+                          float* x_out, double* x_out_f64, int32_t* status_out, int32_t* iters_out,
+                          void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QR_GPU_H */

@@ -1,0 +1,243 @@
+"""ctypes binding of the CPU oracle (oracle/libqr_oracle.so) + an extended-precision KKT polish.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  Nothing under quadruped-robot_b200/ imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+RET_MAX_NWSR_REACHED = 64  # qpOASES MessageHandling.hpp
+
+
+class MpcParams(C.Structure):
+    _fields_ = [("horizon", C.c_int), ("dt", C.c_float), ("mu", C.c_float), ("f_max", C.c_float),
+                ("mass", C.c_float), ("inertia", C.c_float * 3), ("weights", C.c_float * 12),
+                ("alpha", C.c_float)]
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle (and oracle/_ref when /root/reference is present)."""
+    so = os.path.join(_HERE, "libqr_oracle.so")
+    have_ref = os.path.isdir("/root/reference/quadruped/extern/qpOASES/src")
+    if force or not os.path.exists(so) or have_ref:
+        if have_ref:
+            subprocess.run(["make", "-s", "-j8", "-C", _HERE, "all", "refmpc"], check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        elif not os.path.exists(so):
+            raise RuntimeError("oracle/libqr_oracle.so missing and /root/reference not available to build it")
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libqr_oracle.so")
+        if not os.path.exists(so):
+            build()
+        _LIB = C.CDLL(so)
+        _LIB.qro_mpc_time_batch.restype = C.c_double
+    return _LIB
+
+
+def params_of(robot, horizon: int, dt: float, mu: float | None = None, f_max: float | None = None) -> MpcParams:
+    P = MpcParams()
+    P.horizon = horizon
+    P.dt = dt
+    P.mu = robot.mu if mu is None else mu
+    P.f_max = robot.f_max if f_max is None else f_max
+    P.mass = robot.mass
+    P.inertia[:] = robot.inertia
+    P.weights[:] = robot.weights
+    P.alpha = robot.alpha
+    return P
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def mpc_build(P: MpcParams, batch: dict, i: int, want_ab: bool = False):
+    """Float32 (H, g, ub) of problem i of a synth batch."""
+    h = P.horizon
+    n, m = 12 * h, 20 * h
+    H = np.empty((n, n), np.float32)
+    g = np.empty(n, np.float32)
+    ub = np.empty(m, np.float32)
+    Aqp = np.empty((13 * h, 13), np.float32) if want_ab else None
+    Bqp = np.empty((13 * h, n), np.float32) if want_ab else None
+    rows = [np.ascontiguousarray(batch[k][i]) for k in ("p", "v", "quat", "w", "r_feet", "rpy", "traj", "gait")]
+    rc = lib().qro_mpc_build(C.byref(P), *[_fp(r) for r in rows], _fp(H), _fp(g), _fp(ub),
+                             _fp(Aqp) if want_ab else None, _fp(Bqp) if want_ab else None)
+    assert rc == 0
+    return (H, g, ub, Aqp, Bqp) if want_ab else (H, g, ub)
+
+
+def mpc_qpoases(h: int, mu: float, H, g, ub, nWSR: int = 100000):
+    """The reference's qpOASES call on float32 QP data.  Returns x, info(rval, nWSR), kkt, cstat."""
+    n, m = 12 * h, 20 * h
+    x = np.empty(n)
+    info = np.zeros(2, np.int32)
+    kkt = np.zeros(3)
+    cstat = np.zeros(m, np.int32)
+    H = np.ascontiguousarray(H, np.float32)
+    g = np.ascontiguousarray(g, np.float32)
+    ub = np.ascontiguousarray(ub, np.float32)
+    lib().qro_mpc_qpoases(h, C.c_float(mu), _fp(H), _fp(g), _fp(ub), nWSR, _dp(x), _ip(info), _dp(kkt), _ip(cstat))
+    return x, info, kkt, cstat
+
+
+def qpoases_dense(H, g, A, lbA, ubA, nWSR: int = 100000):
+    n, m = H.shape[0], A.shape[0]
+    H, g, A = (np.ascontiguousarray(a, np.float64) for a in (H, g, A))
+    lbA, ubA = (np.ascontiguousarray(a, np.float64) for a in (lbA, ubA))
+    x = np.empty(n)
+    info = np.zeros(2, np.int32)
+    kkt = np.zeros(3)
+    cstat = np.zeros(m, np.int32)
+    lib().qro_qpoases_dense(n, m, _dp(H), _dp(g), _dp(A), _dp(lbA), _dp(ubA), nWSR, _dp(x), _ip(info), _dp(kkt), _ip(cstat))
+    return x, info, kkt, cstat
+
+
+def mpc_solve(P: MpcParams, batch: dict, i: int, nWSR: int = 100000):
+    n = 12 * P.horizon
+    x = np.empty(n)
+    info = np.zeros(2, np.int32)
+    rows = [np.ascontiguousarray(batch[k][i]) for k in ("p", "v", "quat", "w", "r_feet", "rpy", "traj", "gait")]
+    lib().qro_mpc_solve(C.byref(P), *[_fp(r) for r in rows], nWSR, _dp(x), _ip(info))
+    return x, info
+
+
+def mpc_time_batch(P: MpcParams, batch: dict, lo: int, hi: int, nWSR: int = 100, want_x: bool = False):
+    """Times SolveMPC-equivalents for problems [lo, hi) in this process.  Returns (seconds, lat, capped, x)."""
+    cnt = hi - lo
+    n = 12 * P.horizon
+    lat = np.empty(cnt)
+    capped = C.c_int(0)
+    x = np.empty((cnt, n)) if want_x else None
+    arrs = [np.ascontiguousarray(batch[k][lo:hi]) for k in ("p", "v", "quat", "w", "r_feet", "rpy", "traj", "gait")]
+    sec = lib().qro_mpc_time_batch(C.byref(P), cnt, *[_fp(a) for a in arrs], nWSR,
+                                   _dp(x) if want_x else None, _dp(lat), C.byref(capped))
+    return sec, lat, capped.value, x
+
+
+def contact_table(h, n_horizon_l, progress, duty, early=None, contacts=None):
+    progress = np.ascontiguousarray(progress, np.float32)
+    duty = np.ascontiguousarray(duty, np.float32)
+    out = np.empty((h, 4), np.float32)
+    e = None if early is None else np.ascontiguousarray(early, np.int32)
+    c = None if contacts is None else np.ascontiguousarray(contacts, np.int32)
+    lib().qro_mpc_contact_table(h, n_horizon_l, _fp(progress), _fp(duty), None if e is None else _ip(e),
+                                None if c is None else _ip(c), _fp(out))
+    return out
+
+
+def reference_traj(h, dt, init, pos_xy):
+    init = np.ascontiguousarray(init, np.float32)
+    pos_xy = np.ascontiguousarray(pos_xy, np.float32)
+    out = np.empty(12 * h, np.float32)
+    lib().qro_mpc_reference_traj(h, C.c_float(dt), _fp(init), _fp(pos_xy), _fp(out))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Exact optimum of the reference's QP by an extended-precision active-set solve ("polish").
+# ---------------------------------------------------------------------------------------------
+
+def constraint_rows(h: int, mu: float):
+    """Dense friction matrix (20h x 12h) as ResizeQPMats builds it (qr_mpc_interface.cpp:230-240)."""
+    n, m = 12 * h, 20 * h
+    A = np.zeros((m, n))
+    mu_ = float(np.float32(1.0) / np.float32(mu))
+    blk = np.array([[mu_, 0, 1], [-mu_, 0, 1], [0, mu_, 1], [0, -mu_, 1], [0, 0, 1]], float)
+    for k in range(4 * h):
+        A[5 * k:5 * k + 5, 3 * k:3 * k + 3] = blk
+    return A
+
+
+def exact_qp(H, g, A, lb, ub, x_hint=None, tol_act=1e-7, max_iter=200):
+    """Exact minimiser of 1/2 x'Hs x + g'x s.t. lb <= A x <= ub with Hs = (H+H')/2, in longdouble.
+
+    Primal active-set iteration started from a guess of the active set taken from x_hint (any
+    near-optimal point, e.g. the qpOASES solution); terminates when the KKT conditions hold in
+    extended precision.  Returns (x, active_lower, active_upper, iters).  For the small dense
+    problems used in tests only.
+    """
+    LD = np.longdouble
+    Hs = ((np.asarray(H, LD) + np.asarray(H, LD).T) / 2)
+    g = np.asarray(g, LD)
+    A = np.asarray(A, LD)
+    lb = np.asarray(lb, LD)
+    ub = np.asarray(ub, LD)
+    n, m = Hs.shape[0], A.shape[0]
+    if x_hint is None:
+        x_hint = np.zeros(n)
+    ax = A @ np.asarray(x_hint, LD)
+    scale = max(1.0, float(np.abs(ax).max()))
+    act_lo = ax - lb <= tol_act * scale
+    act_up = ub - ax <= tol_act * scale
+
+    def solve_eq(rows, rhs):
+        # min 1/2 x'Hx + g'x s.t. A_r x = rhs  via null-space free KKT solve with rank handling (QR)
+        Ar = A[rows]
+        k = Ar.shape[0]
+        if k == 0:
+            x = np.linalg.solve(Hs.astype(float), -g.astype(float)).astype(LD)
+            for _ in range(3):
+                x = x - np.linalg.solve(Hs.astype(float), (Hs @ x + g).astype(float)).astype(LD)
+            return x, np.zeros(0, LD)
+        K = np.zeros((n + k, n + k), LD)
+        K[:n, :n] = Hs
+        K[:n, n:] = -Ar.T
+        K[n:, :n] = Ar
+        r = np.concatenate([-g, rhs])
+        Kd = K.astype(float)
+        sol = np.linalg.lstsq(Kd, r.astype(float), rcond=1e-13)[0].astype(LD)
+        for _ in range(6):
+            res = r - K @ sol
+            sol = sol + np.linalg.lstsq(Kd, res.astype(float), rcond=1e-13)[0].astype(LD)
+        return sol[:n], sol[n:]
+
+    for it in range(max_iter):
+        rows = np.nonzero(act_lo | act_up)[0]
+        rhs = np.where(act_up[rows], ub[rows], lb[rows])
+        x, lam = solve_eq(rows, rhs)
+        ax = A @ x
+        # multipliers: gradient = A_r' lam ; need lam >= 0 on lower-active, <= 0 on upper-active
+        sign = np.where(act_up[rows] & ~act_lo[rows], -1.0, 1.0)
+        eq = act_up[rows] & act_lo[rows]
+        bad_mult = np.where(~eq & (sign * lam < -1e-12 * max(1.0, float(np.abs(lam).max()) if lam.size else 1.0)))[0]
+        viol_lo = lb - ax
+        viol_up = ax - ub
+        viol = np.maximum(viol_lo, viol_up)
+        viol[rows] = -1
+        worst = int(np.argmax(viol))
+        if viol[worst] > 1e-11 * scale:
+            if viol_lo[worst] >= viol_up[worst]:
+                act_lo[worst] = True
+            else:
+                act_up[worst] = True
+            continue
+        if bad_mult.size:
+            j = bad_mult[np.argmin((sign * lam)[bad_mult])]
+            r_ = rows[j]
+            act_lo[r_] = False
+            act_up[r_] = False
+            continue
+        return x, act_lo, act_up, it
+    raise RuntimeError("exact_qp did not terminate")

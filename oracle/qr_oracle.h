@@ -1,0 +1,96 @@
+/* qr_oracle.h -- C interface of the CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * this library.  The product library (libqr_gpu.so) never links or calls anything declared here.
+ *
+ * The oracle is an Eigen-free float32 restatement of the reference's convex-MPC build
+ *   quadruped/src/controllers/mpc/qr_mpc_interface.cpp:160-451
+ *   quadruped/src/controllers/mpc/qr_mpc_stance_leg_controller.cpp:282-303, 345-376, 396-409
+ * that hands the QP to the reference's own vendored qpOASES 3.2.0 (oracle/_ref/libqpOASES.a, compiled
+ * from /root/reference/quadruped/extern/qpOASES/src) exactly as SolveMPC does (:428-438).
+ *
+ * Pinning status: the reference repository holds NO test, golden vector or fixture for this path
+ * (SURVEY.md section 4 / 8c).  The restatement is pinned instead against the reference's own
+ * qr_mpc_interface.cpp compiled unmodified against oracle/mini_eigen (oracle/_ref/libqr_mpc_ref.so)
+ * -- see oracle/README.md.  Eigen's own summation order is not reproducible here (Eigen is not
+ * installed), so bit-level agreement with a true Eigen build is UNPINNED; all float32 products in
+ * the oracle are plain sequential sums without FMA contraction.
+ */
+#ifndef QR_ORACLE_H
+#define QR_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Mirrors Quadruped::ProblemConfig (+ the body inertia SetupProblem stores in MPCRobotState),
+ * include/quadruped/controllers/mpc/qr_mpc_interface.h:107-144.  The narrowing double->float of
+ * dt / frictionCoeff / fMax / totalMass that SetupProblem performs (:163-168) is the caller's job. */
+typedef struct {
+    int   horizon;
+    float dt;
+    float mu;        /* frictionCoeff */
+    float f_max;
+    float mass;
+    float inertia[3];
+    float weights[12];
+    float alpha;
+} qro_mpc_params;
+
+/* Float32 QP data exactly as SolveMPC builds them (qr_mpc_interface.cpp:359-425).
+ *   p,v,w,rpy : 3 floats each;  quat = (w,x,y,z);  r_feet[3*leg+axis] (column-major 3x4, foot - CoM,
+ *   world aligned);  traj[12*h];  gait[4*h] row-major h x 4.
+ * Outputs (caller-allocated): H[n*n] row-major, g[n], ub[m]  with n = 12h, m = 20h.
+ * Optional outputs (may be NULL): Aqp[13h*13], Bqp[13h*12h] row-major.                           */
+int qro_mpc_build(const qro_mpc_params* P, const float* p, const float* v, const float* quat,
+                  const float* w, const float* r_feet, const float* rpy, const float* traj,
+                  const float* gait, float* H, float* g, float* ub, float* Aqp, float* Bqp);
+
+/* The reference's qpOASES call (qr_mpc_interface.cpp:414-438) on float32 data widened to double.
+ * nWSR = 100 reproduces the stock cap; a large value gives the converged oracle.
+ *   x[n]            primal solution (getPrimalSolution)
+ *   info[0]         qpOASES return value of init()
+ *   info[1]         working-set recalculations used
+ *   kkt[3]          stationarity / feasibility / complementarity (SolutionAnalysis::getKktViolation)
+ *   cstat[m]        constraint status (-1 lower active, 0 inactive, +1 upper active); may be NULL   */
+int qro_mpc_qpoases(int horizon, float mu, const float* H, const float* g, const float* ub,
+                    int nWSR, double* x, int* info, double* kkt, int* cstat);
+
+/* Same solver on double data supplied by the caller (used to study H symmetrisation etc.). */
+int qro_qpoases_dense(int n, int m, const double* H, const double* g, const double* A,
+                      const double* lbA, const double* ubA, int nWSR, double* x, int* info,
+                      double* kkt, int* cstat);
+
+/* SolveMPCKernel + GetMPCSolution in one call: build + qpOASES; x[12h] out. */
+int qro_mpc_solve(const qro_mpc_params* P, const float* p, const float* v, const float* quat,
+                  const float* w, const float* r_feet, const float* rpy, const float* traj,
+                  const float* gait, int nWSR, double* x, int* info);
+
+/* Contact table, qr_mpc_stance_leg_controller.cpp:282-303.  progress[4], duty[4] float32;
+ * early_contact[4] / contacts[4] are 0/1 flags (contacts may be NULL: row 0 is then left as computed).
+ * table[h*4] row-major float 0/1. */
+void qro_mpc_contact_table(int horizon, int num_horizon_l, const float* progress, const float* duty,
+                           const int* early_contact, const int* contacts, float* table);
+
+/* Reference trajectory, qr_mpc_stance_leg_controller.cpp:345-376.
+ * init[12] = {rpyComp0, rpyComp1, yawDes, xDes, yDes, bodyHeight, 0,0,yawRate, vxW, vyW, 0};
+ * pos_xy[2] = actual base x,y used to clip the start to +-0.1 m.  traj[12*h] out. */
+void qro_mpc_reference_traj(int horizon, float dt_mpc, const float* init, const float* pos_xy,
+                            float* traj);
+
+/* Post-processing, qr_mpc_stance_leg_controller.cpp:402-409: f_ff(leg) = -R_base^T f_world(leg).
+ * R_base[9] row-major (base->world).  f_world[12] = solution entries 0..11; f_ff[12] out (3*leg+axis). */
+void qro_mpc_grf_to_leg_force(const float* R_base, const double* x, float* f_world, float* f_ff);
+
+/* Wall-clock a batch of `count` independent SolveMPC calls (cold QProblem each) in this process.
+ * Inputs are SoA-free: arrays of `count` consecutive problems.  Returns seconds; per-problem
+ * seconds in lat[count] (may be NULL); number of RET_MAX_NWSR_REACHED in *capped. */
+double qro_mpc_time_batch(const qro_mpc_params* P, int count, const float* p, const float* v,
+                          const float* quat, const float* w, const float* r_feet, const float* rpy,
+                          const float* traj, const float* gait, int nWSR, double* x_all,
+                          double* lat, int* capped);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

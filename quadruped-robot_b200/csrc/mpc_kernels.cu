@@ -1,0 +1,342 @@
+// mpc_kernels.cu -- CUDA kernels (sm_100a) and the extern "C" layer of libqr_gpu.so (include/qr_gpu.h).
+//
+// One CTA ("team") per MPC instance, persistent over the batch: grid = resident CTAs of the device,
+// each CTA walks the batch with a stride.  Shared memory holds the matrix under factorisation and
+// all solver vectors; the symmetric Hessian of the current instance sits in a per-CTA slice of a
+// global scratch buffer that never leaves L2.  There is no CPU fallback in this library: every entry
+// point fails with QR_ECUDA when no device is usable.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "mpc_problem.h"
+
+#ifndef QR_NT
+#define QR_NT 128
+#endif
+
+namespace {
+
+__global__ void __launch_bounds__(QR_NT) qr_mpc_fused_kernel(const QrMpcArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NT = QR_NT;
+    double* Hs = A.scratch + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap);
+    for (int prob = blockIdx.x; prob < A.batch; prob += gridDim.x)
+        qr_mpc_solve_problem<NT>(A, prob, smem, Hs);
+}
+
+__global__ void __launch_bounds__(QR_NT) qr_mpc_condense_kernel(const QrMpcArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NT = QR_NT;
+    for (int prob = blockIdx.x; prob < A.batch; prob += gridDim.x)
+        qr_mpc_condense_problem<NT>(A, prob, smem);
+}
+
+__global__ void __launch_bounds__(QR_NT) qr_qp_solve_kernel(const QrMpcArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NT = QR_NT;
+    double* Hs = A.scratch + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap);
+    for (int prob = blockIdx.x; prob < A.batch; prob += gridDim.x)
+        qr_qp_solve_problem<NT>(A, prob, smem, Hs);
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side context
+// ------------------------------------------------------------------------------------------
+struct Ctx {
+    bool ready = false;
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    double* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // staging buffers of the *_host entry point
+    unsigned char* stage = nullptr;
+    size_t stage_bytes = 0;
+    cudaStream_t stream = nullptr;
+    char err[256] = {0};
+};
+Ctx g_ctx;
+std::mutex g_mu;
+
+int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+    if (e != cudaSuccess) snprintf(g_ctx.err, sizeof(g_ctx.err), "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(g_ctx.err, sizeof(g_ctx.err), "%s", what);
+    return code;
+}
+
+qr_qp_options default_options() {
+    qr_qp_options o;
+    o.max_ipm_iter = 40;
+    o.max_polish_rounds = 12;
+    o.ipm_tol = 1e-5;
+    o.act_kappa = 1e3;
+    o.feas_tol = 1e-9;
+    o.mult_tol = 1e-11;
+    return o;
+}
+
+template <typename Kern>
+int launch_geometry(Kern kern, int horizon, int batch, int* grid, size_t* smem, int* per_sm) {
+    const int nfcap = 4 * horizon;
+    const size_t bytes = qr_mpc_smem_bytes(nfcap, horizon);
+    if (bytes > g_ctx.smem_optin) return fail(QR_EINVAL, "horizon needs more shared memory than one CTA may use");
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(QR_ECUDA, "cudaFuncSetAttribute", e);
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, QR_NT, bytes);
+    if (e != cudaSuccess) return fail(QR_ECUDA, "cudaOccupancyMaxActiveBlocksPerMultiprocessor", e);
+    if (occ < 1) occ = 1;
+    int g = g_ctx.sm_count * occ;
+    if (g > batch) g = batch;
+    if (g < 1) g = 1;
+    *grid = g;
+    *smem = bytes;
+    if (per_sm) *per_sm = occ;
+    return QR_OK;
+}
+
+int ensure_scratch(int grid, int nfcap) {
+    const size_t need = (size_t)grid * 9 * ((nfcap * (nfcap + 1)) / 2) * sizeof(double);
+    if (need <= g_ctx.scratch_bytes) return QR_OK;
+    if (g_ctx.scratch) cudaFree(g_ctx.scratch);
+    g_ctx.scratch = nullptr;
+    g_ctx.scratch_bytes = 0;
+    cudaError_t e = cudaMalloc(&g_ctx.scratch, need);
+    if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMalloc(scratch)", e);
+    g_ctx.scratch_bytes = need;
+    return QR_OK;
+}
+
+int check_params(const qr_mpc_params* P, int batch) {
+    if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
+    if (!P || batch < 0) return fail(QR_EINVAL, "null params or negative batch");
+    if (P->horizon < 1 || P->horizon > QR_MAX_HORIZON) return fail(QR_EINVAL, "horizon out of range");
+    if (!(P->dt > 0.f) || !(P->mass > 0.f) || !(P->mu > 0.f)) return fail(QR_EINVAL, "dt, mass and mu must be positive");
+    return QR_OK;
+}
+
+}  // namespace
+
+extern "C" const char* qr_gpu_last_error(void) { return g_ctx.err; }
+
+extern "C" int qr_gpu_init(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return fail(QR_ECUDA, "no CUDA device", e);
+    if (device >= 0) {
+        e = cudaSetDevice(device);
+        if (e != cudaSuccess) return fail(QR_ECUDA, "cudaSetDevice", e);
+    }
+    e = cudaGetDevice(&g_ctx.device);
+    if (e != cudaSuccess) return fail(QR_ECUDA, "cudaGetDevice", e);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, g_ctx.device);
+    if (e != cudaSuccess) return fail(QR_ECUDA, "cudaGetDeviceProperties", e);
+    if (prop.major < 10) return fail(QR_ECUDA, "libqr_gpu.so is built for sm_100a only");
+    g_ctx.sm_count = prop.multiProcessorCount;
+    g_ctx.smem_optin = prop.sharedMemPerBlockOptin;
+    if (!g_ctx.stream) {
+        e = cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return fail(QR_ECUDA, "cudaStreamCreate", e);
+    }
+    g_ctx.ready = true;
+    g_ctx.err[0] = 0;
+    return QR_OK;
+}
+
+extern "C" void qr_gpu_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx.scratch) cudaFree(g_ctx.scratch);
+    if (g_ctx.stage) cudaFree(g_ctx.stage);
+    if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
+    g_ctx = Ctx();
+}
+
+extern "C" int qr_gpu_mpc_occupancy(int horizon, int* sm_count, int* ctas_per_sm, int* threads_per_cta,
+                                    int* smem_bytes) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
+    if (horizon < 1 || horizon > QR_MAX_HORIZON) return fail(QR_EINVAL, "horizon out of range");
+    int grid = 0, occ = 0;
+    size_t smem = 0;
+    int rc = launch_geometry(qr_mpc_fused_kernel, horizon, 1 << 30, &grid, &smem, &occ);
+    if (rc) return rc;
+    if (sm_count) *sm_count = g_ctx.sm_count;
+    if (ctas_per_sm) *ctas_per_sm = occ;
+    if (threads_per_cta) *threads_per_cta = QR_NT;
+    if (smem_bytes) *smem_bytes = (int)smem;
+    return QR_OK;
+}
+
+extern "C" int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_options* opt, int batch,
+                                      const float* p, const float* v, const float* quat,
+                                      const float* w, const float* r_feet, const float* rpy,
+                                      const float* traj, const float* gait, const float* mu_i,
+                                      const float* fmax_i, float* grf_out, float* u_out,
+                                      int32_t* status_out, int32_t* iters_out, void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = check_params(P, batch);
+    if (rc) return rc;
+    if (batch == 0) return QR_OK;
+    if (!p || !v || !quat || !w || !r_feet || !rpy || !traj || !gait || !grf_out)
+        return fail(QR_EINVAL, "null input/output pointer");
+    int grid = 0;
+    size_t smem = 0;
+    rc = launch_geometry(qr_mpc_fused_kernel, P->horizon, batch, &grid, &smem, nullptr);
+    if (rc) return rc;
+    rc = ensure_scratch(grid, 4 * P->horizon);
+    if (rc) return rc;
+    QrMpcArgs A;
+    memset(&A, 0, sizeof(A));
+    A.P = *P;
+    A.opt = opt ? *opt : default_options();
+    A.batch = batch;
+    A.nfcap = 4 * P->horizon;
+    A.p = p; A.v = v; A.quat = quat; A.w = w; A.r_feet = r_feet; A.rpy = rpy; A.traj = traj; A.gait = gait;
+    A.mu_i = mu_i; A.fmax_i = fmax_i;
+    A.grf_out = grf_out; A.u_out = u_out; A.status_out = status_out; A.iters_out = iters_out;
+    A.scratch = g_ctx.scratch;
+    qr_mpc_fused_kernel<<<grid, QR_NT, smem, (cudaStream_t)cuda_stream>>>(A);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_fused_kernel", e);
+    return QR_OK;
+}
+
+extern "C" int qr_gpu_mpc_condense_batch(const qr_mpc_params* P, int batch, const float* p,
+                                         const float* v, const float* quat, const float* w,
+                                         const float* r_feet, const float* rpy, const float* traj,
+                                         const float* gait, const float* fmax_i, float* H_out,
+                                         float* g_out, float* ub_out, void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = check_params(P, batch);
+    if (rc) return rc;
+    if (batch == 0) return QR_OK;
+    if (!p || !v || !quat || !w || !r_feet || !rpy || !traj || !gait || !H_out || !g_out || !ub_out)
+        return fail(QR_EINVAL, "null input/output pointer");
+    int grid = 0;
+    size_t smem = 0;
+    rc = launch_geometry(qr_mpc_condense_kernel, P->horizon, batch, &grid, &smem, nullptr);
+    if (rc) return rc;
+    QrMpcArgs A;
+    memset(&A, 0, sizeof(A));
+    A.P = *P;
+    A.opt = default_options();
+    A.batch = batch;
+    A.nfcap = 4 * P->horizon;
+    A.p = p; A.v = v; A.quat = quat; A.w = w; A.r_feet = r_feet; A.rpy = rpy; A.traj = traj; A.gait = gait;
+    A.fmax_i = fmax_i;
+    A.H_out = H_out; A.g_out = g_out; A.ub_out = ub_out;
+    qr_mpc_condense_kernel<<<grid, QR_NT, smem, (cudaStream_t)cuda_stream>>>(A);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_condense_kernel", e);
+    return QR_OK;
+}
+
+extern "C" int qr_gpu_qp_solve_batch(int horizon, float mu, const qr_qp_options* opt, int batch,
+                                     const float* H, const float* g, const float* ub,
+                                     const float* mu_i, float* x_out, double* x_out_f64,
+                                     int32_t* status_out, int32_t* iters_out, void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    qr_mpc_params P;
+    memset(&P, 0, sizeof(P));
+    P.horizon = horizon; P.mu = mu; P.dt = 1.f; P.mass = 1.f;
+    int rc = check_params(&P, batch);
+    if (rc) return rc;
+    if (batch == 0) return QR_OK;
+    if (!H || !g || !ub || (!x_out && !x_out_f64)) return fail(QR_EINVAL, "null input/output pointer");
+    int grid = 0;
+    size_t smem = 0;
+    rc = launch_geometry(qr_qp_solve_kernel, horizon, batch, &grid, &smem, nullptr);
+    if (rc) return rc;
+    rc = ensure_scratch(grid, 4 * horizon);
+    if (rc) return rc;
+    QrMpcArgs A;
+    memset(&A, 0, sizeof(A));
+    A.P = P;
+    A.opt = opt ? *opt : default_options();
+    A.batch = batch;
+    A.nfcap = 4 * horizon;
+    A.mu_i = mu_i;
+    A.H_in = H; A.g_in = g; A.ub_in = ub;
+    A.x_out = x_out; A.x_out_f64 = x_out_f64; A.status_out = status_out; A.iters_out = iters_out;
+    A.scratch = g_ctx.scratch;
+    qr_qp_solve_kernel<<<grid, QR_NT, smem, (cudaStream_t)cuda_stream>>>(A);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_qp_solve_kernel", e);
+    return QR_OK;
+}
+
+extern "C" int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_options* opt, int batch,
+                                           const float* p, const float* v, const float* quat,
+                                           const float* w, const float* r_feet, const float* rpy,
+                                           const float* traj, const float* gait, const float* mu_i,
+                                           const float* fmax_i, float* grf_out, float* u_out,
+                                           int32_t* status_out, int32_t* iters_out) {
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        int rc = check_params(P, batch);
+        if (rc) return rc;
+    }
+    if (batch == 0) return QR_OK;
+    if (!p || !v || !quat || !w || !r_feet || !rpy || !traj || !gait || !grf_out)
+        return fail(QR_EINVAL, "null input/output pointer");
+    const int h = P->horizon;
+    const size_t B = (size_t)batch;
+    // device staging layout (floats unless noted)
+    const size_t n_in = B * (3 + 3 + 4 + 3 + 12 + 3 + 12 * h + 4 * h + 2);
+    const size_t n_out = B * (12 + (u_out ? 12 * h : 0));
+    const size_t bytes = (n_in + n_out) * sizeof(float) + B * 3 * sizeof(int32_t) + 256;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (bytes > g_ctx.stage_bytes) {
+            if (g_ctx.stage) cudaFree(g_ctx.stage);
+            g_ctx.stage = nullptr;
+            g_ctx.stage_bytes = 0;
+            cudaError_t e = cudaMalloc(&g_ctx.stage, bytes);
+            if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMalloc(stage)", e);
+            g_ctx.stage_bytes = bytes;
+        }
+    }
+    cudaStream_t st = g_ctx.stream;
+    float* d = reinterpret_cast<float*>(g_ctx.stage);
+    cudaError_t e = cudaSuccess;
+    auto up = [&](const float* src, size_t cnt) -> float* {
+        float* dst = d;
+        d += cnt;
+        if (src && e == cudaSuccess) e = cudaMemcpyAsync(dst, src, cnt * sizeof(float), cudaMemcpyHostToDevice, st);
+        return src ? dst : nullptr;
+    };
+    float* dp = up(p, B * 3);
+    float* dv = up(v, B * 3);
+    float* dq = up(quat, B * 4);
+    float* dw = up(w, B * 3);
+    float* dr = up(r_feet, B * 12);
+    float* drpy = up(rpy, B * 3);
+    float* dtraj = up(traj, B * 12 * h);
+    float* dgait = up(gait, B * 4 * h);
+    float* dmu = up(mu_i, B);
+    float* dfm = up(fmax_i, B);
+    if (!mu_i) d += B;
+    if (!fmax_i) d += B;
+    if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpyAsync H2D", e);
+    float* dgrf = d; d += B * 12;
+    float* du = nullptr;
+    if (u_out) { du = d; d += B * 12 * h; }
+    int32_t* dstat = reinterpret_cast<int32_t*>(d);
+    int32_t* dit = dstat + B;
+    int rc = qr_gpu_mpc_solve_batch(P, opt, batch, dp, dv, dq, dw, dr, drpy, dtraj, dgait, dmu, dfm, dgrf, du,
+                                    dstat, dit, st);
+    if (rc) return rc;
+    e = cudaMemcpyAsync(grf_out, dgrf, B * 12 * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && u_out) e = cudaMemcpyAsync(u_out, du, B * 12 * h * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && status_out) e = cudaMemcpyAsync(status_out, dstat, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && iters_out) e = cudaMemcpyAsync(iters_out, dit, 2 * B * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpyAsync D2H", e);
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(QR_ECUDA, "cudaStreamSynchronize", e);
+    return QR_OK;
+}

@@ -1,0 +1,275 @@
+// mpc_problem.h -- one MPC instance end to end on one thread team: stage inputs, condense (float32,
+// reference operation order), eliminate swing foot-steps, solve (float64), scatter the forces.
+// Shared by the CUDA kernels (mpc_kernels.cu) and by the host emulation used in CPU-only tests.
+#pragma once
+
+#include "mpc_condense.h"
+#include "qp_solver.h"
+
+// Arguments common to all kernels (passed by value).
+struct QrMpcArgs {
+    qr_mpc_params P;
+    qr_qp_options opt;
+    int batch;
+    int nfcap;               // capacity (stance foot-steps) the workspace was carved for
+    const float *p, *v, *quat, *w, *r_feet, *rpy, *traj, *gait, *mu_i, *fmax_i;
+    float* grf_out;          // [batch][12]
+    float* u_out;            // [batch][12h] or null
+    int32_t* status_out;     // [batch] or null
+    int32_t* iters_out;      // [batch][2] or null
+    double* scratch;         // [teams][9*ntri(nfcap)] symmetric Hessian blocks
+    // condense-only outputs
+    float *H_out, *g_out, *ub_out;
+    // qp-only inputs / outputs
+    const float *H_in, *g_in, *ub_in;
+    float* x_out;
+    double* x_out_f64;
+};
+
+QR_DEV int qr_ntri(int nf) { return (nf * (nf + 1)) / 2; }
+
+// Shared-memory footprint in bytes for a workspace able to hold nfcap stance foot-steps.
+QR_HD size_t qr_mpc_smem_bytes(int nfcap, int horizon) {
+    size_t dbl = (size_t)9 * ((nfcap * (nfcap + 1)) / 2) + (size_t)83 * nfcap + 8;
+    size_t bytes = dbl * sizeof(double);
+    bytes += sizeof(QrCondenseTables);
+    bytes += (size_t)(16 * horizon + 32) * sizeof(float);    // staged traj + gait + state rows
+    bytes += (size_t)(3 * nfcap + 2 * 4 * horizon + 8) * sizeof(int);
+    return (bytes + 15) & ~(size_t)15;
+}
+
+struct QrMpcSmem {
+    QrQpWork W;
+    QrCondenseTables* T;
+    float* traj;   // [12h]
+    float* gait;   // [4h]
+    float* state;  // [32]: p v quat w r_feet rpy
+    int* fs;       // [4h] stance list: fs[s] = foot-step id 4*i + leg
+    int* slot;     // [4h] inverse map (or -1)
+    int* misc;     // [8]
+};
+
+QR_DEV void qr_mpc_carve(QrMpcSmem& S, unsigned char* base, int nfcap, int horizon) {
+    double* d = reinterpret_cast<double*>(base);
+    QrQpWork& W = S.W;
+    const int n = 3 * nfcap, m = 5 * nfcap;
+    W.K = d; d += 9 * qr_ntri(nfcap);
+    W.Dinv = d; d += 9 * nfcap;
+    W.Zs = d; d += 9 * nfcap;
+    W.ps = d; d += n;
+    W.g = d; d += n;  W.x = d; d += n;  W.xn = d; d += n; W.q = d; d += n; W.wv = d; d += n;
+    W.yv = d; d += n; W.dxa = d; d += n; W.dx = d; d += n; W.rd = d; d += n;
+    W.s = d; d += m; W.lam = d; d += m; W.dsa = d; d += m; W.dla = d; d += m; W.rc = d; d += m; W.dl = d; d += m;
+    W.ubz = d; d += nfcap;
+    W.red = d; d += 4 * nfcap;
+    d += 8;
+    S.T = reinterpret_cast<QrCondenseTables*>(d);
+    float* f = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(d) + sizeof(QrCondenseTables));
+    S.traj = f; f += 12 * horizon;
+    S.gait = f; f += 4 * horizon;
+    S.state = f; f += 32;
+    int* ip = reinterpret_cast<int*>(f);
+    W.act = ip; ip += nfcap;
+    W.flag = ip; ip += nfcap;
+    W.vert = ip; ip += nfcap;
+    S.fs = ip; ip += 4 * horizon;
+    S.slot = ip; ip += 4 * horizon;
+    S.misc = ip;
+}
+
+// Stage this problem's rows and build the stance list.  After return (and its trailing barrier):
+// S.state/traj/gait hold the inputs, S.fs/slot the stance map, W.nf, W.ubz, W.mu_ are set, and
+// S.misc[0] = per-instance status so far (0 ok, 2 negative bound, 3 non-finite input).
+template <int NT>
+QR_DEV void qr_mpc_stage(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
+    const int h = A.P.horizon;
+    QR_FOR(i, 12 * h) S.traj[i] = A.traj[(size_t)prob * 12 * h + i];
+    QR_FOR(i, 4 * h) S.gait[i] = A.gait[(size_t)prob * 4 * h + i];
+    QR_FOR(i, 28) {
+        float val;
+        if (i < 3) val = A.p[(size_t)prob * 3 + i];
+        else if (i < 6) val = A.v[(size_t)prob * 3 + i - 3];
+        else if (i < 10) val = A.quat[(size_t)prob * 4 + i - 6];
+        else if (i < 13) val = A.w[(size_t)prob * 3 + i - 10];
+        else if (i < 25) val = A.r_feet[(size_t)prob * 12 + i - 13];
+        else val = A.rpy[(size_t)prob * 3 + i - 25];
+        S.state[i] = val;
+    }
+    QR_SYNC();
+    QR_THREADS(t) {
+        if (t == 0) {
+            const float fmax = A.fmax_i ? A.fmax_i[prob] : A.P.f_max;
+            const float mu = A.mu_i ? A.mu_i[prob] : A.P.mu;
+            S.W.mu_ = (double)QR_FDIV(1.f, mu);          // mu_ = 1.f / frictionCoeff (qr_mpc_interface.cpp:230)
+            int nf = 0, st = 0;
+            for (int k = 0; k < 4 * h; ++k) {
+                const float ub = QR_FMUL(S.gait[k], fmax);   // U_b(5k+4) = gait * fMax (:387)
+                if (ub > 0.f && nf < A.nfcap) {
+                    S.fs[nf] = k; S.slot[k] = nf; S.W.ubz[nf] = (double)ub; ++nf;
+                } else {
+                    S.slot[k] = -1;
+                    if (ub < 0.f) st = 2;
+                    if (!(ub == ub)) st = 3;
+                    if (ub > 0.f) st = 3;  // capacity exceeded (cannot happen when nfcap == 4h)
+                }
+            }
+            for (int i = 0; i < 28; ++i) if (!(fabsf(S.state[i]) < 3.0e38f)) st = 3;
+            if (!(mu > 0.f)) st = 3;
+            S.misc[0] = st;
+            S.misc[1] = nf;
+        }
+    }
+    QR_SYNC();
+    S.W.nf = S.misc[1];
+}
+
+// Condense into the solver workspace: symmetric Hessian blocks of the stance variables -> Hs
+// (global scratch), g -> W.g.  H_sym = (H + H')/2 evaluated in float64 from the two float32 entries.
+template <int NT>
+QR_DEV void qr_mpc_condense_to_work(const QrMpcArgs& A, QrMpcSmem& S, double* Hs) {
+    const int h = A.P.horizon;
+    QrCondenseTables& T = *S.T;
+    QR_THREADS(t) {
+        if (t == 0) qr_condense_model(A.P, S.state, S.state + 3, S.state + 6, S.state + 10, S.state + 13, S.state + 25, T);
+    }
+    QR_SYNC();
+    qr_condense_tables<NT>(A.P, S.traj, T);
+    QR_SYNC();
+    const int nf = S.W.nf;
+    QR_FOR(idx, 9 * qr_ntri(nf)) {
+        const int b = idx / 9, e = idx - 9 * b;
+        int Sb, Tb;
+        qr_tri_decode(b, Sb, Tb);
+        const int ks = S.fs[Sb], kt = S.fs[Tb];
+        const int r = e / 3, c = e - 3 * r;
+        const float hst = qr_condense_h_entry(T, h, ks >> 2, ks & 3, r, kt >> 2, kt & 3, c);
+        const float hts = qr_condense_h_entry(T, h, kt >> 2, kt & 3, c, ks >> 2, ks & 3, r);
+        Hs[idx] = 0.5 * ((double)hst + (double)hts);
+    }
+    QR_FOR(i, 3 * nf) {
+        const int k = S.fs[i / 3];
+        S.W.g[i] = (double)qr_condense_g_entry(T, h, k >> 2, k & 3, i % 3);
+    }
+    QR_SYNC();
+}
+
+// Scatter the stance solution into the 12h force vector (swing foot-steps are exactly zero).
+template <int NT>
+QR_DEV void qr_mpc_scatter(const QrMpcArgs& A, int prob, QrMpcSmem& S, const double* x, int status,
+                           int ipm_iters, int polish_rounds) {
+    const int h = A.P.horizon;
+    QR_FOR(i, 12 * h) {
+        const int k = i / 3, sl = S.slot[k];
+        const float val = (sl >= 0 && status != 2 && status != 3) ? (float)x[3 * sl + (i - 3 * k)] : 0.f;
+        if (A.u_out) A.u_out[(size_t)prob * 12 * h + i] = val;
+        if (i < 12 && A.grf_out) A.grf_out[(size_t)prob * 12 + i] = val;
+        if (A.x_out) A.x_out[(size_t)prob * 12 * h + i] = val;
+        if (A.x_out_f64) A.x_out_f64[(size_t)prob * 12 * h + i] = (sl >= 0 && status != 2 && status != 3) ? x[3 * sl + (i - 3 * k)] : 0.0;
+    }
+    QR_THREADS(t) {
+        if (t == 0) {
+            if (A.status_out) A.status_out[prob] = status;
+            if (A.iters_out) { A.iters_out[2 * prob] = ipm_iters; A.iters_out[2 * prob + 1] = polish_rounds; }
+        }
+    }
+}
+
+// The fused path: SolveMPCKernel + GetMPCSolution for one instance.
+template <int NT>
+QR_DEV void qr_mpc_solve_problem(const QrMpcArgs& A, int prob, unsigned char* smem, double* Hs) {
+    QrMpcSmem S;
+    qr_mpc_carve(S, smem, A.nfcap, A.P.horizon);
+    qr_mpc_stage<NT>(A, prob, S);
+    int status = S.misc[0];
+    int it = 0, rounds = 0;
+    const double* x = S.W.xn;
+    if (status == 0) {
+        S.W.Hs = Hs;
+        qr_mpc_condense_to_work<NT>(A, S, Hs);
+        status = qr_qp_solve<NT>(S.W, A.opt, &it, &rounds, &x);
+        // breakdown guard: a non-finite result is reported, never returned as a force
+        QR_FOR(i, 3 * S.W.nf) S.W.red[i] = (fabs(x[i]) < 1e300) ? 0.0 : 1.0;
+        QR_SYNC();
+        if (S.W.nf > 0 && qr_red_max<NT>(S.W.red, 3 * S.W.nf) != 0.0) status = 3;
+        QR_SYNC();
+    }
+    qr_mpc_scatter<NT>(A, prob, S, x, status, it, rounds);
+    QR_SYNC();
+}
+
+// Condense only: float32 H (n x n), g (n), ub (20h) exactly as SolveMPC hands them to qpOASES.
+template <int NT>
+QR_DEV void qr_mpc_condense_problem(const QrMpcArgs& A, int prob, unsigned char* smem) {
+    QrMpcSmem S;
+    qr_mpc_carve(S, smem, A.nfcap, A.P.horizon);
+    qr_mpc_stage<NT>(A, prob, S);
+    const int h = A.P.horizon, n = 12 * h;
+    QrCondenseTables& T = *S.T;
+    QR_THREADS(t) {
+        if (t == 0) qr_condense_model(A.P, S.state, S.state + 3, S.state + 6, S.state + 10, S.state + 13, S.state + 25, T);
+    }
+    QR_SYNC();
+    qr_condense_tables<NT>(A.P, S.traj, T);
+    QR_SYNC();
+    float* H = A.H_out + (size_t)prob * n * n;
+    QR_FOR(idx, n * n) {
+        const int r = idx / n, c = idx - r * n;
+        H[idx] = qr_condense_h_entry(T, h, r / 12, (r % 12) / 3, r % 3, c / 12, (c % 12) / 3, c % 3);
+    }
+    QR_FOR(i, n) A.g_out[(size_t)prob * n + i] = qr_condense_g_entry(T, h, i / 12, (i % 12) / 3, i % 3);
+    const float fmax = A.fmax_i ? A.fmax_i[prob] : A.P.f_max;
+    QR_FOR(k, 4 * h) {
+        float* ub = A.ub_out + (size_t)prob * 20 * h + 5 * k;
+        ub[0] = ub[1] = ub[2] = ub[3] = 5e10f;            // BIG_NUMBER prefill (ResizeQPMats :219-229)
+        ub[4] = QR_FMUL(S.gait[k], fmax);
+    }
+    QR_SYNC();
+}
+
+// QP only: caller-supplied float32 H, g, ub (the qpOASES call's inputs).
+template <int NT>
+QR_DEV void qr_qp_solve_problem(const QrMpcArgs& A, int prob, unsigned char* smem, double* Hs) {
+    QrMpcSmem S;
+    qr_mpc_carve(S, smem, A.nfcap, A.P.horizon);
+    const int h = A.P.horizon, n = 12 * h;
+    const float* H = A.H_in + (size_t)prob * n * n;
+    const float* g = A.g_in + (size_t)prob * n;
+    const float* ub = A.ub_in + (size_t)prob * 20 * h;
+    QR_THREADS(t) {
+        if (t == 0) {
+            const float mu = A.mu_i ? A.mu_i[prob] : A.P.mu;
+            S.W.mu_ = (double)QR_FDIV(1.f, mu);
+            int nf = 0, st = 0;
+            for (int k = 0; k < 4 * h; ++k) {
+                const float u = ub[5 * k + 4];
+                if (u > 0.f && nf < A.nfcap) { S.fs[nf] = k; S.slot[k] = nf; S.W.ubz[nf] = (double)u; ++nf; }
+                else { S.slot[k] = -1; if (u < 0.f) st = 2; if (!(u == u)) st = 3; }
+            }
+            S.misc[0] = st; S.misc[1] = nf;
+        }
+    }
+    QR_SYNC();
+    S.W.nf = S.misc[1];
+    S.W.Hs = Hs;
+    int status = S.misc[0], it = 0, rounds = 0;
+    const double* x = S.W.xn;
+    if (status == 0) {
+        const int nf = S.W.nf;
+        QR_FOR(idx, 9 * qr_ntri(nf)) {
+            const int b = idx / 9, e = idx - 9 * b;
+            int Sb, Tb;
+            qr_tri_decode(b, Sb, Tb);
+            const int ri = 3 * S.fs[Sb] + e / 3, ci = 3 * S.fs[Tb] + e % 3;
+            Hs[idx] = 0.5 * ((double)H[(size_t)ri * n + ci] + (double)H[(size_t)ci * n + ri]);
+        }
+        QR_FOR(i, 3 * nf) S.W.g[i] = (double)g[3 * S.fs[i / 3] + i % 3];
+        QR_SYNC();
+        status = qr_qp_solve<NT>(S.W, A.opt, &it, &rounds, &x);
+        QR_FOR(i, 3 * nf) S.W.red[i] = (fabs(x[i]) < 1e300) ? 0.0 : 1.0;
+        QR_SYNC();
+        if (nf > 0 && qr_red_max<NT>(S.W.red, 3 * nf) != 0.0) status = 3;
+        QR_SYNC();
+    }
+    qr_mpc_scatter<NT>(A, prob, S, x, status, it, rounds);
+    QR_SYNC();
+}

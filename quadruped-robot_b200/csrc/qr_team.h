@@ -1,0 +1,54 @@
+// qr_team.h -- "one thread team per problem" programming layer.
+//
+// Every solver routine in csrc/ is written as a sequence of PHASES separated by team barriers.
+// Inside a phase a thread touches only its own loop indices; data crosses threads only through
+// the workspace (shared memory on the GPU) and only across a barrier.  Compiled by nvcc for sm_100a
+// a phase is a strided loop over threadIdx.x and QR_SYNC() is a CTA (or warp) barrier.  Compiled by
+// g++ (tests/emul, test infrastructure only) the same source runs the phases one after another with
+// a plain loop over the thread index, which lets the control flow and the arithmetic be checked on
+// a machine without a GPU.  There is no CPU product path: libqr_gpu.so contains only the nvcc build.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define QR_DEV __device__ __forceinline__
+#define QR_DEV_NOINLINE __device__ __noinline__
+#define QR_HD __host__ __device__ inline
+#else
+#define QR_DEV inline
+#define QR_DEV_NOINLINE inline
+#define QR_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+// ---- device ------------------------------------------------------------------------------
+#define QR_ON_DEVICE 1
+template <int NT>
+__device__ __forceinline__ void qr_team_sync() {
+    if (NT <= 32) __syncwarp(); else __syncthreads();
+}
+#define QR_FOR(i, n) for (int i = threadIdx.x; i < (n); i += NT)
+#define QR_THREADS(t) for (int t = threadIdx.x, _qr_once = 1; _qr_once; _qr_once = 0)
+#define QR_SYNC() qr_team_sync<NT>()
+// float32 arithmetic that must not be contracted into FMAs (bit-exact condensing)
+#define QR_FMUL(a, b) __fmul_rn((a), (b))
+#define QR_FADD(a, b) __fadd_rn((a), (b))
+#define QR_FSUB(a, b) __fsub_rn((a), (b))
+#define QR_FDIV(a, b) __fdiv_rn((a), (b))
+#else
+// ---- host emulation (tests only) ---------------------------------------------------------
+#define QR_FOR(i, n) for (int i = 0; i < (n); ++i)
+#define QR_THREADS(t) for (int t = 0; t < NT; ++t)
+#define QR_SYNC() ((void)0)
+#define QR_FMUL(a, b) ((a) * (b))
+#define QR_FADD(a, b) ((a) + (b))
+#define QR_FSUB(a, b) ((a) - (b))
+#define QR_FDIV(a, b) ((a) / (b))
+#endif
+
+QR_DEV double qr_min(double a, double b) { return a < b ? a : b; }
+QR_DEV double qr_max(double a, double b) { return a > b ? a : b; }
+QR_DEV int qr_imin(int a, int b) { return a < b ? a : b; }
+QR_DEV int qr_imax(int a, int b) { return a > b ? a : b; }

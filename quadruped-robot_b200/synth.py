@@ -1,0 +1,147 @@
+"""Seeded synthetic MPC workloads and the host-side contact-table /
+reference-trajectory builders.
+
+Everything is float32 and laid out as one contiguous row per robot instance ("problem rows"):
+    p[B,3] v[B,3] quat[B,4] w[B,3] r_feet[B,12] rpy[B,3] traj[B,12h] gait[B,4h] mu[B] f_max[B]
+which is the layout `qr_gpu_mpc_solve_batch` consumes (one CTA per problem reads its rows
+with coalesced loads).
+
+contact_table / reference_traj restate
+    quadruped/src/controllers/mpc/qr_mpc_stance_leg_controller.cpp:282-303 and :345-376
+in float32 so that masks are bit-exact with the reference's x86-64 build (no FMA contraction).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .robots import GAITS, ROBOTS, RobotMPC
+
+F32 = np.float32
+
+
+def num_horizon_l(gait: dict) -> int:
+    """numHorizonL = max(2, int(fullCyclePeriod / 0.4)), qr_mpc_stance_leg_controller.cpp:50."""
+    full_cycle = F32(gait["stance_duration"]) / F32(gait["duty"])
+    return max(2, int(float(full_cycle) / 0.4))
+
+
+def contact_table(horizon: int, n_horizon_l: int, progress: np.ndarray, duty: np.ndarray,
+                  early_contact: np.ndarray | None = None,
+                  contacts: np.ndarray | None = None) -> np.ndarray:
+    """mpcTable [B, h, 4] float32 of 0/1 (qr_mpc_stance_leg_controller.cpp:282-303).
+
+    progress, duty: [B,4] float32.  early_contact / contacts: [B,4] bool or None.
+    """
+    progress = np.asarray(progress, F32)
+    duty = np.asarray(duty, F32)
+    B = progress.shape[0]
+    d_phase = F32(1.0 / (n_horizon_l * horizon))  # double division, narrowed
+    table = np.empty((B, horizon, 4), F32)
+    for i in range(horizon):
+        ph = progress + F32(i) * d_phase  # float32 multiply, float32 add (two roundings)
+        # `while (ph > 1.0) ph -= 1.0` -- at most a few wraps for progress in [0,1]
+        for _ in range(4):
+            over = ph > F32(1.0)
+            if not over.any():
+                break
+            ph = np.where(over, ph - F32(1.0), ph).astype(F32)
+        st = ph < duty
+        if early_contact is not None:
+            st = st | np.asarray(early_contact, bool)
+        table[:, i, :] = st
+    if contacts is not None:
+        table[:, 0, :] = np.asarray(contacts, bool)
+    return table
+
+
+def reference_traj(horizon: int, dt_mpc: float, init: np.ndarray, pos_xy: np.ndarray) -> np.ndarray:
+    """trajAll [B, 12h] float32 (qr_mpc_stance_leg_controller.cpp:345-376)."""
+    init = np.array(init, F32, copy=True)
+    pos_xy = np.asarray(pos_xy, F32)
+    dt = F32(dt_mpc)
+    for a in range(2):
+        lo = pos_xy[:, a] - F32(0.1)
+        hi = pos_xy[:, a] + F32(0.1)
+        init[:, 3 + a] = np.minimum(np.maximum(init[:, 3 + a], lo), hi)
+    B = init.shape[0]
+    traj = np.empty((B, horizon, 12), F32)
+    traj[:, :, :] = init[:, None, :]
+    yaw_rate, vx, vy = init[:, 8], init[:, 9], init[:, 10]
+    for i in range(1, horizon):
+        traj[:, i, 2] = traj[:, i - 1, 2] + dt * yaw_rate
+        traj[:, i, 3] = traj[:, i - 1, 3] + dt * vx
+        traj[:, i, 4] = traj[:, i - 1, 4] + dt * vy
+    return traj.reshape(B, 12 * horizon)
+
+
+def _rot_zyx(rpy: np.ndarray) -> np.ndarray:
+    """R = Rz(yaw) Ry(pitch) Rx(roll), float64 [B,3,3]."""
+    r, p, y = rpy[:, 0], rpy[:, 1], rpy[:, 2]
+    cr, sr, cp, sp, cy, sy = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(y), np.sin(y)
+    R = np.empty((rpy.shape[0], 3, 3))
+    R[:, 0, 0] = cy * cp; R[:, 0, 1] = cy * sp * sr - sy * cr; R[:, 0, 2] = cy * sp * cr + sy * sr
+    R[:, 1, 0] = sy * cp; R[:, 1, 1] = sy * sp * sr + cy * cr; R[:, 1, 2] = sy * sp * cr - cy * sr
+    R[:, 2, 0] = -sp;     R[:, 2, 1] = cp * sr;                R[:, 2, 2] = cp * cr
+    return R
+
+
+def _quat_from_rpy(rpy: np.ndarray) -> np.ndarray:
+    """(w,x,y,z) of Rz Ry Rx, float64 [B,4]."""
+    hr, hp, hy = rpy[:, 0] / 2, rpy[:, 1] / 2, rpy[:, 2] / 2
+    cr, sr, cp, sp, cy, sy = np.cos(hr), np.sin(hr), np.cos(hp), np.sin(hp), np.cos(hy), np.sin(hy)
+    q = np.stack([cy * cp * cr + sy * sp * sr,
+                  cy * cp * sr - sy * sp * cr,
+                  cy * sp * cr + sy * cp * sr,
+                  sy * cp * cr - cy * sp * sr], axis=1)
+    return q
+
+
+def make_mpc_batch(robot: str | RobotMPC = "a1", horizon: int = 10, dt: float = 0.03,
+                   batch: int = 1024, seed: int = 0, gait: str = "trot",
+                   mu_sweep: bool = False) -> dict:
+    """Randomised states per SURVEY.md section 8d.  gait = trot | walk | gallop | stand | mixed."""
+    rb = ROBOTS[robot] if isinstance(robot, str) else robot
+    rng = np.random.default_rng(seed)
+    B, h = batch, horizon
+    U = rng.uniform
+    rpy = np.stack([U(-0.1, 0.1, B), U(-0.1, 0.1, B), U(-np.pi, np.pi, B)], axis=1)
+    p = np.stack([U(-1, 1, B), U(-1, 1, B), rb.body_height + U(-0.02, 0.02, B)], axis=1)
+    w = U(-0.5, 0.5, (B, 3))
+    v = np.stack([U(-0.5, 1.0, B), U(-0.3, 0.3, B), U(-0.1, 0.1, B)], axis=1)
+    R = _rot_zyx(rpy)
+    quat = _quat_from_rpy(rpy)
+    hips = np.array(rb.hip_positions, float)  # [4,3]
+    feet_base = hips[None, :, :] + np.array([0, 0, -rb.body_height]) + U(-0.05, 0.05, (B, 4, 3))
+    feet_base = feet_base - np.array(rb.com_offset)
+    r_feet = np.einsum("bij,blj->bli", R, feet_base)  # world-aligned lever arms [B,4,3]
+    cmd = np.stack([U(-0.5, 1.0, B), U(-0.3, 0.3, B), U(-0.5, 0.5, B)], axis=1)  # vx, vy, yawRate
+    v_des_w = np.einsum("bij,bj->bi", R, np.stack([cmd[:, 0], cmd[:, 1], np.zeros(B)], axis=1))
+    init = np.zeros((B, 12))
+    init[:, 2] = rpy[:, 2]
+    init[:, 3:5] = p[:, :2] + U(-0.15, 0.15, (B, 2))  # desired xy, clipped to +-0.1 of actual
+    init[:, 5] = rb.body_height
+    init[:, 8] = cmd[:, 2]
+    init[:, 9:11] = v_des_w[:, :2]
+    traj = reference_traj(h, dt, init.astype(F32), p[:, :2].astype(F32))
+
+    names = ["trot", "walk", "gallop"] if gait == "mixed" else [gait]
+    pick = rng.integers(0, len(names), B)
+    phase0 = U(0, 1, B)
+    table = np.empty((B, h, 4), F32)
+    for gi, gname in enumerate(names):
+        sel = np.nonzero(pick == gi)[0]
+        if sel.size == 0:
+            continue
+        gt = GAITS[gname]
+        progress = np.mod(phase0[sel, None] + np.array(gt["offsets"])[None, :], 1.0).astype(F32)
+        duty = np.full((sel.size, 4), gt["duty"], F32)
+        table[sel] = contact_table(h, num_horizon_l(gt), progress, duty)
+    mu = U(0.2, 1.0, B) if mu_sweep else np.full(B, rb.mu)
+    out = dict(
+        p=p, v=v, quat=quat, w=w, r_feet=r_feet.reshape(B, 12), rpy=rpy, traj=traj,
+        gait=table.reshape(B, 4 * h), mu=mu, f_max=np.full(B, rb.f_max))
+    out = {k: np.ascontiguousarray(a, dtype=F32) for k, a in out.items()}
+    out["robot"] = rb
+    out["horizon"] = h
+    out["dt"] = dt
+    return out
