@@ -170,74 +170,52 @@ def constraint_rows(h: int, mu: float):
     return A
 
 
-def exact_qp(H, g, A, lb, ub, x_hint=None, tol_act=1e-7, max_iter=200):
-    """Exact minimiser of 1/2 x'Hs x + g'x s.t. lb <= A x <= ub with Hs = (H+H')/2, in longdouble.
+def polish_from_working_set(H, g, A, lb, ub, cstat, refine: int = 8):
+    """x* = exact minimiser of the reference's QP on qpOASES' own final working set.
 
-    Primal active-set iteration started from a guess of the active set taken from x_hint (any
-    near-optimal point, e.g. the qpOASES solution); terminates when the KKT conditions hold in
-    extended precision.  Returns (x, active_lower, active_upper, iters).  For the small dense
-    problems used in tests only.
+    The quadratic form x'Hx of the (slightly asymmetric, float32-built) H is that of Hs = (H+H')/2.
+    Builds K = [[Hs, -Aa'],[Aa, 0]] from the active rows (cstat != 0; qpOASES keeps them linearly
+    independent), solves in float64 and refines the residual in numpy.longdouble.
+    Returns (x, multipliers of the active rows).
     """
     LD = np.longdouble
-    Hs = ((np.asarray(H, LD) + np.asarray(H, LD).T) / 2)
-    g = np.asarray(g, LD)
-    A = np.asarray(A, LD)
-    lb = np.asarray(lb, LD)
-    ub = np.asarray(ub, LD)
-    n, m = Hs.shape[0], A.shape[0]
-    if x_hint is None:
-        x_hint = np.zeros(n)
-    ax = A @ np.asarray(x_hint, LD)
+    Hs = (np.asarray(H, LD) + np.asarray(H, LD).T) / 2
+    rows = np.nonzero(cstat)[0]
+    Ar = np.asarray(A, LD)[rows]
+    rhs = np.where(np.asarray(cstat)[rows] > 0, np.asarray(ub, LD)[rows], np.asarray(lb, LD)[rows])
+    n, k = Hs.shape[0], len(rows)
+    K = np.zeros((n + k, n + k), LD)
+    K[:n, :n] = Hs
+    K[:n, n:] = -Ar.T
+    K[n:, :n] = Ar
+    r = np.concatenate([-np.asarray(g, LD), rhs])
+    Kd = K.astype(float)
+    sol = np.linalg.lstsq(Kd, r.astype(float), rcond=1e-14)[0].astype(LD)
+    for _ in range(refine):
+        sol = sol + np.linalg.lstsq(Kd, (r - K @ sol).astype(float), rcond=1e-14)[0].astype(LD)
+    return sol[:n].astype(float), sol[n:].astype(float)
+
+
+def kkt_certificate(H, g, A, lb, ub, x, act_tol: float = 1e-7):
+    """Independent optimality check of a candidate x for min 1/2 x'Hs x + g'x, lb <= Ax <= ub.
+
+    Returns (stationarity, feasibility) where stationarity = min over multipliers of the right sign
+    on the rows active at x of ||Hs x + g - A_act' y||_inf (non-negative least squares), and
+    feasibility = the largest bound violation.  For a strictly convex QP both ~0 proves optimality:
+    ||x - x*|| <= stationarity / lambda_min(Hs).
+    """
+    from scipy.optimize import nnls
+    Hs = (np.asarray(H, float) + np.asarray(H, float).T) / 2
+    x = np.asarray(x, float)
+    ax = A @ x
+    feas = float(max(0.0, (lb - ax).max(), (ax - ub).max()))
     scale = max(1.0, float(np.abs(ax).max()))
-    act_lo = ax - lb <= tol_act * scale
-    act_up = ub - ax <= tol_act * scale
-
-    def solve_eq(rows, rhs):
-        # min 1/2 x'Hx + g'x s.t. A_r x = rhs  via null-space free KKT solve with rank handling (QR)
-        Ar = A[rows]
-        k = Ar.shape[0]
-        if k == 0:
-            x = np.linalg.solve(Hs.astype(float), -g.astype(float)).astype(LD)
-            for _ in range(3):
-                x = x - np.linalg.solve(Hs.astype(float), (Hs @ x + g).astype(float)).astype(LD)
-            return x, np.zeros(0, LD)
-        K = np.zeros((n + k, n + k), LD)
-        K[:n, :n] = Hs
-        K[:n, n:] = -Ar.T
-        K[n:, :n] = Ar
-        r = np.concatenate([-g, rhs])
-        Kd = K.astype(float)
-        sol = np.linalg.lstsq(Kd, r.astype(float), rcond=1e-13)[0].astype(LD)
-        for _ in range(6):
-            res = r - K @ sol
-            sol = sol + np.linalg.lstsq(Kd, res.astype(float), rcond=1e-13)[0].astype(LD)
-        return sol[:n], sol[n:]
-
-    for it in range(max_iter):
-        rows = np.nonzero(act_lo | act_up)[0]
-        rhs = np.where(act_up[rows], ub[rows], lb[rows])
-        x, lam = solve_eq(rows, rhs)
-        ax = A @ x
-        # multipliers: gradient = A_r' lam ; need lam >= 0 on lower-active, <= 0 on upper-active
-        sign = np.where(act_up[rows] & ~act_lo[rows], -1.0, 1.0)
-        eq = act_up[rows] & act_lo[rows]
-        bad_mult = np.where(~eq & (sign * lam < -1e-12 * max(1.0, float(np.abs(lam).max()) if lam.size else 1.0)))[0]
-        viol_lo = lb - ax
-        viol_up = ax - ub
-        viol = np.maximum(viol_lo, viol_up)
-        viol[rows] = -1
-        worst = int(np.argmax(viol))
-        if viol[worst] > 1e-11 * scale:
-            if viol_lo[worst] >= viol_up[worst]:
-                act_lo[worst] = True
-            else:
-                act_up[worst] = True
-            continue
-        if bad_mult.size:
-            j = bad_mult[np.argmin((sign * lam)[bad_mult])]
-            r_ = rows[j]
-            act_lo[r_] = False
-            act_up[r_] = False
-            continue
-        return x, act_lo, act_up, it
-    raise RuntimeError("exact_qp did not terminate")
+    lo = np.nonzero(ax - lb <= act_tol * scale)[0]
+    up = np.nonzero(ub - ax <= act_tol * scale)[0]
+    grad = Hs @ x + g
+    # grad = sum_lo y_i a_i - sum_up z_i a_i with y, z >= 0
+    M = np.concatenate([A[lo].T, -A[up].T], axis=1)
+    if M.shape[1] == 0:
+        return float(np.abs(grad).max()), feas
+    y, _ = nnls(M, grad, maxiter=50 * M.shape[1])
+    return float(np.abs(M @ y - grad).max()), feas

@@ -1,0 +1,137 @@
+"""ctypes binding of libqr_gpu.so (include/qr_gpu.h) -- the host-side mirror of the reference's
+MPC interface (SetupProblem / SolveMPCKernel / GetMPCSolution) for batches.
+
+There is no fallback: if the library is missing or no B200 is visible, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_LIB = None
+
+
+class MpcParams(C.Structure):
+    """qr_mpc_params (include/qr_gpu.h)."""
+    _fields_ = [("horizon", C.c_int32), ("dt", C.c_float), ("mu", C.c_float), ("f_max", C.c_float),
+                ("mass", C.c_float), ("inertia", C.c_float * 3), ("weights", C.c_float * 12),
+                ("alpha", C.c_float)]
+
+
+class QpOptions(C.Structure):
+    """qr_qp_options (include/qr_gpu.h)."""
+    _fields_ = [("max_ipm_iter", C.c_int32), ("max_polish_rounds", C.c_int32), ("ipm_tol", C.c_double),
+                ("act_kappa", C.c_double), ("feas_tol", C.c_double), ("mult_tol", C.c_double)]
+
+
+def default_options() -> QpOptions:
+    return QpOptions(40, 12, 1e-5, 1e3, 1e-9, 1e-11)
+
+
+EXPORTS = ["qr_gpu_init", "qr_gpu_shutdown", "qr_gpu_last_error", "qr_gpu_mpc_occupancy",
+           "qr_gpu_mpc_solve_batch", "qr_gpu_mpc_solve_batch_host", "qr_gpu_mpc_condense_batch",
+           "qr_gpu_qp_solve_batch"]
+
+
+def lib():
+    """Load libqr_gpu.so (must have been built by build.build(); never built implicitly on import)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_build.LIB):
+            raise RuntimeError(f"{_build.LIB} is missing: run __graft_entry__.build() first")
+        _LIB = C.CDLL(_build.LIB)
+        _LIB.qr_gpu_last_error.restype = C.c_char_p
+    return _LIB
+
+
+class QrGpuError(RuntimeError):
+    pass
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise QrGpuError(f"{what} failed with {rc}: {lib().qr_gpu_last_error().decode()}")
+
+
+def init(device: int = -1):
+    _check(lib().qr_gpu_init(device), "qr_gpu_init")
+
+
+def params_of(robot, horizon: int, dt: float, mu: float | None = None, f_max: float | None = None) -> MpcParams:
+    """SetupProblem(dt, horizon, mu, fMax, mass, inertia, weights, alpha) -> qr_mpc_params."""
+    P = MpcParams()
+    P.horizon = horizon
+    P.dt = dt
+    P.mu = robot.mu if mu is None else mu
+    P.f_max = robot.f_max if f_max is None else f_max
+    P.mass = robot.mass
+    P.inertia[:] = robot.inertia
+    P.weights[:] = robot.weights
+    P.alpha = robot.alpha
+    return P
+
+
+def _vp(x):
+    """void* of a numpy array (host) or anything with data_ptr() (torch CUDA tensor); None -> NULL."""
+    if x is None:
+        return None
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr())
+    return C.c_void_p(x.ctypes.data)
+
+
+_KEYS = ("p", "v", "quat", "w", "r_feet", "rpy", "traj", "gait")
+
+
+def mpc_solve_batch_host(P: MpcParams, batch: dict, opt: QpOptions | None = None, per_instance_mu=False,
+                         want_u=False, want_info=True):
+    """Host buffers in, host buffers out (numpy).  Returns dict(grf, u, status, iters)."""
+    B = batch["p"].shape[0]
+    h = P.horizon
+    grf = np.empty((B, 12), np.float32)
+    u = np.empty((B, 12 * h), np.float32) if want_u else None
+    status = np.empty(B, np.int32) if want_info else None
+    iters = np.empty((B, 2), np.int32) if want_info else None
+    rc = lib().qr_gpu_mpc_solve_batch_host(
+        C.byref(P), C.byref(opt) if opt is not None else None, B, *[_vp(batch[k]) for k in _KEYS],
+        _vp(batch["mu"]) if per_instance_mu else None, None, _vp(grf), _vp(u), _vp(status), _vp(iters))
+    _check(rc, "qr_gpu_mpc_solve_batch_host")
+    return dict(grf=grf, u=u, status=status, iters=iters)
+
+
+def mpc_solve_batch_device(P: MpcParams, dev: dict, out: dict, stream_ptr: int, opt: QpOptions | None = None,
+                           per_instance_mu=False):
+    """Device tensors in `dev` (torch), outputs in `out` (grf, optional u/status/iters); asynchronous."""
+    B = dev["p"].shape[0]
+    rc = lib().qr_gpu_mpc_solve_batch(
+        C.byref(P), C.byref(opt) if opt is not None else None, B, *[_vp(dev[k]) for k in _KEYS],
+        _vp(dev["mu"]) if per_instance_mu else None, None, _vp(out["grf"]), _vp(out.get("u")),
+        _vp(out.get("status")), _vp(out.get("iters")), C.c_void_p(stream_ptr))
+    _check(rc, "qr_gpu_mpc_solve_batch")
+
+
+def mpc_condense_batch_device(P: MpcParams, dev: dict, H, g, ub, stream_ptr: int):
+    B = dev["p"].shape[0]
+    rc = lib().qr_gpu_mpc_condense_batch(C.byref(P), B, *[_vp(dev[k]) for k in _KEYS], None,
+                                         _vp(H), _vp(g), _vp(ub), C.c_void_p(stream_ptr))
+    _check(rc, "qr_gpu_mpc_condense_batch")
+
+
+def qp_solve_batch_device(horizon: int, mu: float, H, g, ub, x32, x64, status, iters, stream_ptr: int,
+                          opt: QpOptions | None = None, mu_i=None):
+    B = H.shape[0]
+    rc = lib().qr_gpu_qp_solve_batch(horizon, C.c_float(mu), C.byref(opt) if opt is not None else None, B,
+                                     _vp(H), _vp(g), _vp(ub), _vp(mu_i), _vp(x32), _vp(x64), _vp(status),
+                                     _vp(iters), C.c_void_p(stream_ptr))
+    _check(rc, "qr_gpu_qp_solve_batch")
+
+
+def occupancy(horizon: int):
+    sm, per, thr, smem = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    _check(lib().qr_gpu_mpc_occupancy(horizon, C.byref(sm), C.byref(per), C.byref(thr), C.byref(smem)),
+           "qr_gpu_mpc_occupancy")
+    return dict(sm_count=sm.value, ctas_per_sm=per.value, threads_per_cta=thr.value, smem_bytes=smem.value)

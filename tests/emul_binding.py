@@ -1,0 +1,75 @@
+"""Builds and binds tests/emul/libqr_emul.so -- the device sources compiled for the host (tests only)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "emul", "emul.cpp")
+_SO = os.path.join(_HERE, "emul", "libqr_emul.so")
+_CSRC = os.path.join(_HERE, "..", "quadruped-robot_b200", "csrc")
+_KEYS = ("p", "v", "quat", "w", "r_feet", "rpy", "traj", "gait")
+
+
+def _stale():
+    if not os.path.exists(_SO):
+        return True
+    t = os.path.getmtime(_SO)
+    deps = [_SRC] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+class Emul:
+    def __init__(self, lib):
+        self.lib = lib
+
+    @staticmethod
+    def _fp(a):
+        return None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+
+    def condense(self, P, batch):
+        B, h = batch["p"].shape[0], P.horizon
+        n = 12 * h
+        H = np.zeros((B, n, n), np.float32)
+        g = np.zeros((B, n), np.float32)
+        ub = np.zeros((B, 20 * h), np.float32)
+        self.lib.qr_emul_mpc_condense_batch(C.byref(P), B, *[self._fp(batch[k]) for k in _KEYS], None,
+                                            self._fp(H), self._fp(g), self._fp(ub))
+        return H, g, ub
+
+    def solve(self, P, batch, opt=None, per_instance_mu=False):
+        B, h = batch["p"].shape[0], P.horizon
+        n = 12 * h
+        grf = np.zeros((B, 12), np.float32)
+        u = np.zeros((B, n), np.float32)
+        u64 = np.zeros((B, n))
+        st = np.zeros(B, np.int32)
+        it = np.zeros((B, 2), np.int32)
+        self.lib.qr_emul_mpc_solve_batch(
+            C.byref(P), C.byref(opt) if opt is not None else None, B, *[self._fp(batch[k]) for k in _KEYS],
+            self._fp(batch["mu"]) if per_instance_mu else None, None, self._fp(grf), self._fp(u),
+            u64.ctypes.data_as(C.POINTER(C.c_double)), st.ctypes.data_as(C.POINTER(C.c_int)),
+            it.ctypes.data_as(C.POINTER(C.c_int)))
+        return dict(grf=grf, u=u, u64=u64, status=st, iters=it)
+
+    def qp_solve(self, h, mu, H, g, ub, opt=None):
+        B, n = H.shape[0], 12 * h
+        x64 = np.zeros((B, n))
+        st = np.zeros(B, np.int32)
+        it = np.zeros((B, 2), np.int32)
+        H = np.ascontiguousarray(H, np.float32)
+        g = np.ascontiguousarray(g, np.float32)
+        ub = np.ascontiguousarray(ub, np.float32)
+        self.lib.qr_emul_qp_solve_batch(h, C.c_float(mu), C.byref(opt) if opt is not None else None, B,
+                                        self._fp(H), self._fp(g), self._fp(ub), None, None,
+                                        x64.ctypes.data_as(C.POINTER(C.c_double)),
+                                        st.ctypes.data_as(C.POINTER(C.c_int)), it.ctypes.data_as(C.POINTER(C.c_int)))
+        return dict(x64=x64, status=st, iters=it)
+
+
+def load():
+    if _stale():
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", "-shared", "-o", _SO, _SRC],
+                       check=True)
+    return Emul(C.CDLL(_SO))

@@ -1,0 +1,173 @@
+"""GPU parity tests (run on a B200 with `pytest -m gpu`): every call goes through the C ABI of
+libqr_gpu.so.  Small cases are compared with the oracle / golden fixtures; BASELINE.json's full
+batch size is checked through size-independent properties."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import parity
+
+pytestmark = pytest.mark.gpu
+KEYS = ("p", "v", "quat", "w", "r_feet", "rpy", "traj", "gait", "mu")
+
+
+def to_dev(b):
+    import torch
+    return {k: torch.from_numpy(np.ascontiguousarray(b[k])).cuda() for k in KEYS}
+
+
+def gpu_solve(gpu, P, b, per_instance_mu=False, opt=None):
+    import torch
+    dev = to_dev(b)
+    B, h = b["p"].shape[0], P.horizon
+    out = dict(grf=torch.empty((B, 12), device="cuda"), u=torch.empty((B, 12 * h), device="cuda"),
+               status=torch.empty(B, dtype=torch.int32, device="cuda"),
+               iters=torch.empty((B, 2), dtype=torch.int32, device="cuda"))
+    gpu.mpc_solve_batch_device(P, dev, out, torch.cuda.current_stream().cuda_stream, opt=opt,
+                               per_instance_mu=per_instance_mu)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+@pytest.mark.parametrize("path", parity.golden_files(), ids=os.path.basename)
+def test_condense_bit_exact_vs_golden(path, gpu, pkg):
+    import torch
+    z, b, h, dt, mu_sweep = parity.load_golden(path, pkg)
+    P = gpu.params_of(b["robot"], h, dt)
+    B, n = b["p"].shape[0], 12 * h
+    H = torch.empty((B, n, n), device="cuda")
+    g = torch.empty((B, n), device="cuda")
+    ub = torch.empty((B, 20 * h), device="cuda")
+    gpu.mpc_condense_batch_device(P, to_dev(b), H, g, ub, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    H, g, ub = H.cpu().numpy(), g.cpu().numpy(), ub.cpu().numpy()
+    assert np.array_equal(H[0], z["H0"])
+    for i in range(B):
+        assert np.array_equal(g[i], z["g"][i]) and np.array_equal(ub[i], z["ub"][i])
+        # normalise -0.0 before hashing
+        assert hashlib.sha256((H[i] + 0.0).tobytes()).hexdigest() == str(z["H_sha256"][i])
+
+
+@pytest.mark.parametrize("path", parity.golden_files(), ids=os.path.basename)
+def test_fused_solve_vs_golden(path, gpu, pkg):
+    z, b, h, dt, mu_sweep = parity.load_golden(path, pkg)
+    P = gpu.params_of(b["robot"], h, dt)
+    r = gpu_solve(gpu, P, b, per_instance_mu=mu_sweep)
+    assert (r["status"] == 0).all(), r["status"]
+    for i in range(b["p"].shape[0]):
+        parity.assert_elementwise(r["u"][i], z["x_star"][i], f"{os.path.basename(path)}[{i}]")
+        parity.assert_vs_qpoases(r["u"][i], z["x_conv"][i], z["x_star"][i])
+        assert (r["u"][i][parity.swing_mask(b["gait"][i], h)] == 0).all()
+        assert np.array_equal(r["grf"][i], r["u"][i][:12])
+
+
+@pytest.mark.parametrize("path", parity.golden_files()[:2], ids=os.path.basename)
+def test_host_buffer_entry_point(path, gpu, pkg):
+    """qr_gpu_mpc_solve_batch_host (what a reference-side caller binds) gives the same answer."""
+    z, b, h, dt, mu_sweep = parity.load_golden(path, pkg)
+    P = gpu.params_of(b["robot"], h, dt)
+    r = gpu.mpc_solve_batch_host(P, b, per_instance_mu=mu_sweep, want_u=True)
+    d = gpu_solve(gpu, P, b, per_instance_mu=mu_sweep)
+    assert np.array_equal(r["u"], d["u"]) and np.array_equal(r["grf"], d["grf"])
+    assert np.array_equal(r["status"], d["status"])
+    for i in range(b["p"].shape[0]):
+        parity.assert_elementwise(r["u"][i], z["x_star"][i])
+
+
+def test_qp_solver_on_identical_data(gpu, oracle, pkg):
+    """P1: solver parity on the byte-identical (H, g, ub) the oracle hands to qpOASES."""
+    import torch
+    h, dt, B = 10, 0.03, 16
+    b = pkg.synth.make_mpc_batch("a1", h, dt, B, seed=31, gait="mixed")
+    P = oracle.params_of(b["robot"], h, dt)
+    built = [oracle.mpc_build(P, b, i) for i in range(B)]
+    H = torch.from_numpy(np.stack([x[0] for x in built])).cuda()
+    g = torch.from_numpy(np.stack([x[1] for x in built])).cuda()
+    ub = torch.from_numpy(np.stack([x[2] for x in built])).cuda()
+    x64 = torch.empty((B, 12 * h), dtype=torch.float64, device="cuda")
+    st = torch.empty(B, dtype=torch.int32, device="cuda")
+    it = torch.empty((B, 2), dtype=torch.int32, device="cuda")
+    gpu.qp_solve_batch_device(h, P.mu, H, g, ub, None, x64, st, it, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    x64, st = x64.cpu().numpy(), st.cpu().numpy()
+    assert (st == 0).all()
+    A = oracle.constraint_rows(h, P.mu)
+    for i in range(B):
+        Hi, gi, ubi = built[i]
+        xq, info, kkt, cstat = oracle.mpc_qpoases(h, P.mu, Hi, gi, ubi, 100000)
+        xs, _ = oracle.polish_from_working_set(Hi, gi, A, np.zeros(20 * h), ubi.astype(float), cstat)
+        parity.assert_elementwise(x64[i], xs, f"qp[{i}]")
+        parity.assert_vs_qpoases(x64[i], xq, xs)
+        assert np.abs(x64[i] - xs).max() <= np.abs(xq - xs).max() + 1e-9
+
+
+def test_gpu_matches_host_emulation(gpu, emul, pkg):
+    """The CUDA build and the host build of the same sources agree (FMA contraction aside)."""
+    h, dt, B = 10, 0.03, 192
+    b = pkg.synth.make_mpc_batch("aliengo", h, dt, B, seed=32, gait="mixed", mu_sweep=True)
+    P = gpu.params_of(b["robot"], h, dt)
+    r = gpu_solve(gpu, P, b, per_instance_mu=True)
+    e = emul.solve(P, b, per_instance_mu=True)
+    assert (r["status"] == 0).all() and (e["status"] == 0).all()
+    assert np.abs(r["u"] - e["u64"]).max() < 2e-5
+    assert np.array_equal(r["u"] == 0, e["u"] == 0)
+
+
+def test_full_size_properties(gpu, oracle, pkg):
+    """BASELINE.json's batch (65536 A1 trot instances): status, exact swing zeros, friction-pyramid
+    feasibility, determinism, permutation invariance, and an independent KKT certificate on a sample."""
+    h, dt, B = 10, 0.03, 65536
+    b = pkg.synth.make_mpc_batch("a1", h, dt, B, seed=3, gait="trot")
+    P = gpu.params_of(b["robot"], h, dt)
+    r = gpu_solve(gpu, P, b)
+    assert (r["status"] == 0).all(), np.bincount(r["status"])
+    u = r["u"].reshape(B, 4 * h, 3)
+    table = b["gait"].reshape(B, 4 * h)
+    assert (u[table == 0] == 0).all()
+    mu_ = float(np.float32(1.0) / np.float32(P.mu))
+    fz = u[..., 2]
+    assert (fz >= -1e-4).all() and (fz <= P.f_max * (1 + 1e-6) + 1e-4).all()
+    assert (np.abs(u[..., 0]) * mu_ <= fz + 1e-3).all() and (np.abs(u[..., 1]) * mu_ <= fz + 1e-3).all()
+    # determinism
+    r2 = gpu_solve(gpu, P, b)
+    assert np.array_equal(r["u"], r2["u"])
+    # permutation invariance on a slice
+    perm = np.random.default_rng(1).permutation(4096)
+    bp = {k: (np.ascontiguousarray(v[:4096][perm]) if isinstance(v, np.ndarray) else v) for k, v in b.items()}
+    rp = gpu_solve(gpu, P, bp)
+    assert np.array_equal(rp["u"], r["u"][:4096][perm])
+    # independent optimality certificate on a sample (oracle-built QP, NNLS multipliers)
+    Po = oracle.params_of(b["robot"], h, dt)
+    A = oracle.constraint_rows(h, Po.mu)
+    for i in np.random.default_rng(2).choice(B, 24, replace=False):
+        H, g, ub = oracle.mpc_build(Po, b, int(i))
+        stat, feas = oracle.kkt_certificate(H, g, A, np.zeros(20 * h), ub.astype(float), r["u"][i].astype(float))
+        # float32 output rounding (<= 8e-6 N) times ||H|| bounds the visible stationarity residual
+        assert stat < 5e-7 and feas < 1e-4, (i, stat, feas)
+    # iteration statistics stay in the expected band
+    assert r["iters"][:, 0].max() <= 40 and r["iters"][:, 1].max() <= 12
+
+
+def test_edge_cases(gpu, pkg):
+    h, dt = 5, 0.06
+    b = pkg.synth.make_mpc_batch("lite3", h, dt, 4, seed=33)
+    b["p"][0, 0] = np.nan
+    b["gait"][1, 3] = -1.0
+    b["gait"][2] = 0.0
+    P = gpu.params_of(b["robot"], h, dt)
+    r = gpu_solve(gpu, P, b)
+    assert r["status"][0] == 3 and (r["u"][0] == 0).all()
+    assert r["status"][1] == 2 and (r["u"][1] == 0).all()
+    assert r["status"][2] == 0 and (r["u"][2] == 0).all()
+    assert r["status"][3] == 0
+    # empty batch and single instance
+    e = {k: (v[:0] if isinstance(v, np.ndarray) else v) for k, v in b.items()}
+    assert gpu.mpc_solve_batch_host(P, e)["grf"].shape == (0, 12)
+    one = {k: (np.ascontiguousarray(v[3:4]) if isinstance(v, np.ndarray) else v) for k, v in b.items()}
+    assert np.array_equal(gpu.mpc_solve_batch_host(P, one, want_u=True)["u"][0], r["u"][3])
+    # API errors are codes, not crashes
+    bad = gpu.params_of(b["robot"], 17, dt)
+    with pytest.raises(gpu.QrGpuError):
+        gpu.mpc_solve_batch_host(bad, one)
