@@ -46,9 +46,10 @@ typedef struct {
 
 /* Solver knobs; pass NULL for the defaults written next to each field. */
 typedef struct {
-    int32_t max_ipm_iter;     /* 40    interior-point iteration cap                              */
-    int32_t max_polish_rounds;/* 12    active-set verification / correction rounds               */
-    double ipm_tol;           /* 1e-5  scaled stationarity and complementarity-gap tolerance     */
+    int32_t max_as_rounds;    /* 24    cold-start active-set rounds before the interior-point fallback */
+    int32_t max_ipm_iter;     /* 40    interior-point iteration cap (fallback path)               */
+    int32_t max_polish_rounds;/* 12    active-set verification / correction rounds after it       */
+    double ipm_tol;           /* 1e-7  fallback: scaled stationarity and complementarity-gap tolerance */
     double act_kappa;         /* 1e3   constraint i is guessed active when s_i < kappa*lambda_i   */
     double feas_tol;          /* 1e-9  admissible constraint violation after the polish [N]      */
     double mult_tol;          /* 1e-11 admissible negative multiplier after the polish           */
@@ -60,9 +61,11 @@ int qr_gpu_init(int device);
 void qr_gpu_shutdown(void);
 const char* qr_gpu_last_error(void);
 
-/* Number of SMs and max CTAs the fused kernel keeps resident per SM for this horizon (bench/roofline). */
-int qr_gpu_mpc_occupancy(int horizon, int* sm_count, int* ctas_per_sm, int* threads_per_cta,
-                         int* smem_bytes);
+/* Launch geometry of the fused kernel for instances with `stance_footsteps` non-swing entries in their
+ * contact table (the workspace is sized by classes of 8 foot-steps): SM count, resident CTAs per SM,
+ * threads per CTA, dynamic shared memory per CTA.  For bench / roofline reporting. */
+int qr_gpu_mpc_occupancy(int horizon, int stance_footsteps, int* sm_count, int* ctas_per_sm,
+                         int* threads_per_cta, int* smem_bytes);
 
 /* qr_gpu_mpc_solve_batch -- replaces SolveMPCKernel + GetMPCSolution
  * (qr_mpc_interface.h:200,215; qr_mpc_interface.cpp:334-356, 359-443, 446-451) for `batch`
@@ -77,7 +80,8 @@ int qr_gpu_mpc_occupancy(int horizon, int* sm_count, int* ctas_per_sm, int* thre
  *   grf_out        [batch][12]  step-0 ground reaction forces, world frame (GetMPCSolution(0..11))
  *   u_out          [batch][12h] or NULL  full solution vector
  *   status_out     [batch] or NULL
- *   iters_out      [batch][2] or NULL    {interior-point iterations, polish rounds}
+ *   iters_out      [batch][2] or NULL    {interior-point iterations (0 unless the fallback ran),
+ *                                         active-set rounds (all phases)}
  * All pointers are DEVICE pointers; the call is asynchronous on `cuda_stream` (a cudaStream_t). */
 int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_options* opt, int batch,
                            const float* p, const float* v, const float* quat, const float* w,

@@ -24,12 +24,13 @@ class MpcParams(C.Structure):
 
 class QpOptions(C.Structure):
     """qr_qp_options (include/qr_gpu.h)."""
-    _fields_ = [("max_ipm_iter", C.c_int32), ("max_polish_rounds", C.c_int32), ("ipm_tol", C.c_double),
+    _fields_ = [("max_as_rounds", C.c_int32), ("max_ipm_iter", C.c_int32), ("max_polish_rounds", C.c_int32),
+                ("_pad", C.c_int32), ("ipm_tol", C.c_double),
                 ("act_kappa", C.c_double), ("feas_tol", C.c_double), ("mult_tol", C.c_double)]
 
 
 def default_options() -> QpOptions:
-    return QpOptions(40, 12, 1e-5, 1e3, 1e-9, 1e-11)
+    return QpOptions(24, 40, 12, 0, 1e-7, 1e3, 1e-9, 1e-11)
 
 
 EXPORTS = ["qr_gpu_init", "qr_gpu_shutdown", "qr_gpu_last_error", "qr_gpu_mpc_occupancy",
@@ -130,8 +131,8 @@ def qp_solve_batch_device(horizon: int, mu: float, H, g, ub, x32, x64, status, i
     _check(rc, "qr_gpu_qp_solve_batch")
 
 
-def occupancy(horizon: int):
+def occupancy(horizon: int, stance_footsteps: int):
     sm, per, thr, smem = C.c_int(), C.c_int(), C.c_int(), C.c_int()
-    _check(lib().qr_gpu_mpc_occupancy(horizon, C.byref(sm), C.byref(per), C.byref(thr), C.byref(smem)),
+    _check(lib().qr_gpu_mpc_occupancy(horizon, stance_footsteps, C.byref(sm), C.byref(per), C.byref(thr), C.byref(smem)),
            "qr_gpu_mpc_occupancy")
     return dict(sm_count=sm.value, ctas_per_sm=per.value, threads_per_cta=thr.value, smem_bytes=smem.value)

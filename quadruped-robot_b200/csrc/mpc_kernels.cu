@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -19,27 +20,64 @@
 
 namespace {
 
-__global__ void __launch_bounds__(QR_NT) qr_mpc_fused_kernel(const QrMpcArgs A) {
+constexpr int QR_CLASS_STEP = 8;   // size classes: workspace capacities 8, 16, 24, ... stance foot-steps
+
+// Size classification: one thread per instance counts its stance foot-steps (gait * f_max > 0, the
+// rows SolveMPC would give a non-zero upper bound, qr_mpc_interface.cpp:387) and appends the instance
+// to the work list of the smallest workspace class that holds it.
+__global__ void qr_mpc_classify_kernel(const QrMpcArgs A, int nclass, int* counts, int* lists) {
+    const int prob = blockIdx.x * blockDim.x + threadIdx.x;
+    if (prob >= A.batch) return;
+    const int h4 = 4 * A.P.horizon;
+    const float fmax = A.fmax_i ? A.fmax_i[prob] : A.P.f_max;
+    const float* g = A.gait + (size_t)prob * h4;
+    int nf = 0;
+    for (int k = 0; k < h4; ++k) nf += (__fmul_rn(g[k], fmax) > 0.f) ? 1 : 0;
+    int c = (nf + QR_CLASS_STEP - 1) / QR_CLASS_STEP - 1;
+    c = c < 0 ? 0 : (c >= nclass ? nclass - 1 : c);
+    const int slot = atomicAdd(&counts[c], 1);
+    lists[(size_t)c * A.batch + slot] = prob;
+}
+
+// Fused SolveMPCKernel + GetMPCSolution.  Persistent CTAs; instances are handed out through an
+// atomic ticket so that the varying number of active-set rounds per instance balances out.
+__global__ void __launch_bounds__(QR_NT, 512 / QR_NT) qr_mpc_fused_kernel(const QrMpcArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_ticket;
     constexpr int NT = QR_NT;
-    double* Hs = A.scratch + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap);
-    for (int prob = blockIdx.x; prob < A.batch; prob += gridDim.x)
-        qr_mpc_solve_problem<NT>(A, prob, smem, Hs);
+    QrMpcSmem S;
+    qr_mpc_carve(S, smem, A.nfcap, A.P.horizon, A.scratch + (size_t)blockIdx.x * qr_fallback_doubles(A.nfcap),
+                 A.hs_global ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr);
+    qr_mpc_init_tables<NT>(S, A.nfcap);
+    const int total = A.count ? *A.count : A.batch;
+    for (;;) {
+        if (threadIdx.x == 0) s_ticket = atomicAdd(A.next, 1);
+        __syncthreads();
+        const int k = s_ticket;
+        __syncthreads();
+        if (k >= total) break;
+        qr_mpc_solve_problem<NT>(A, A.list ? A.list[k] : k, S);
+    }
 }
 
 __global__ void __launch_bounds__(QR_NT) qr_mpc_condense_kernel(const QrMpcArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NT = QR_NT;
+    QrMpcSmem S;
+    qr_mpc_carve(S, smem, A.nfcap, A.P.horizon, nullptr);
     for (int prob = blockIdx.x; prob < A.batch; prob += gridDim.x)
-        qr_mpc_condense_problem<NT>(A, prob, smem);
+        qr_mpc_condense_problem<NT>(A, prob, S);
 }
 
 __global__ void __launch_bounds__(QR_NT) qr_qp_solve_kernel(const QrMpcArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NT = QR_NT;
-    double* Hs = A.scratch + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap);
+    QrMpcSmem S;
+    qr_mpc_carve(S, smem, A.nfcap, A.P.horizon, A.scratch + (size_t)blockIdx.x * qr_fallback_doubles(A.nfcap),
+                 A.hs_global ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr);
+    qr_mpc_init_tables<NT>(S, A.nfcap);
     for (int prob = blockIdx.x; prob < A.batch; prob += gridDim.x)
-        qr_qp_solve_problem<NT>(A, prob, smem, Hs);
+        qr_qp_solve_problem<NT>(A, prob, S);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -52,6 +90,8 @@ struct Ctx {
     size_t smem_optin = 0;
     double* scratch = nullptr;
     size_t scratch_bytes = 0;
+    int* work = nullptr;          // [2*nclass] counters (counts, tickets) followed by [nclass][batch] lists
+    size_t work_bytes = 0;
     // staging buffers of the *_host entry point
     unsigned char* stage = nullptr;
     size_t stage_bytes = 0;
@@ -69,19 +109,30 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
 
 qr_qp_options default_options() {
     qr_qp_options o;
+    o.max_as_rounds = 24;
     o.max_ipm_iter = 40;
     o.max_polish_rounds = 12;
-    o.ipm_tol = 1e-5;
+    o.ipm_tol = 1e-7;
     o.act_kappa = 1e3;
     o.feas_tol = 1e-9;
     o.mult_tol = 1e-11;
     return o;
 }
 
+// Launch geometry of one size class.  *hs_global is set when H does not fit in shared memory next to
+// the matrix under factorisation (capacities above ~44 foot-steps) and has to live in the L2-resident
+// global scratch instead.
 template <typename Kern>
-int launch_geometry(Kern kern, int horizon, int batch, int* grid, size_t* smem, int* per_sm) {
-    const int nfcap = 4 * horizon;
-    const size_t bytes = qr_mpc_smem_bytes(nfcap, horizon);
+int launch_geometry(Kern kern, int nfcap, int horizon, int batch, int* grid, size_t* smem, int* per_sm,
+                    bool* hs_global = nullptr) {
+    size_t bytes = qr_mpc_smem_bytes(nfcap, horizon, true);
+    bool hsg = false;
+    if (bytes + 1024 > g_ctx.smem_optin) {
+        bytes = qr_mpc_smem_bytes(nfcap, horizon, false);
+        hsg = true;
+    }
+    if (hs_global) *hs_global = hsg;
+    else if (hsg) return fail(QR_EINVAL, "workspace does not fit in shared memory");
     if (bytes > g_ctx.smem_optin) return fail(QR_EINVAL, "horizon needs more shared memory than one CTA may use");
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return fail(QR_ECUDA, "cudaFuncSetAttribute", e);
@@ -98,8 +149,10 @@ int launch_geometry(Kern kern, int horizon, int batch, int* grid, size_t* smem, 
     return QR_OK;
 }
 
-int ensure_scratch(int grid, int nfcap) {
-    const size_t need = (size_t)grid * 9 * ((nfcap * (nfcap + 1)) / 2) * sizeof(double);
+// scratch layout: [grid][fallback vectors] followed by [grid][Hessian blocks] (the latter only when needed)
+int ensure_scratch(int grid, int nfcap, bool hs_global = false) {
+    size_t need = (size_t)grid * qr_fallback_doubles(nfcap) * sizeof(double);
+    if (hs_global) need += (size_t)grid * 9 * qr_ntri(nfcap) * sizeof(double);
     if (need <= g_ctx.scratch_bytes) return QR_OK;
     if (g_ctx.scratch) cudaFree(g_ctx.scratch);
     g_ctx.scratch = nullptr;
@@ -151,19 +204,42 @@ extern "C" int qr_gpu_init(int device) {
 extern "C" void qr_gpu_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_ctx.scratch) cudaFree(g_ctx.scratch);
+    if (g_ctx.work) cudaFree(g_ctx.work);
     if (g_ctx.stage) cudaFree(g_ctx.stage);
     if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
     g_ctx = Ctx();
 }
 
-extern "C" int qr_gpu_mpc_occupancy(int horizon, int* sm_count, int* ctas_per_sm, int* threads_per_cta,
-                                    int* smem_bytes) {
+int num_classes(int horizon) { return (4 * horizon + QR_CLASS_STEP - 1) / QR_CLASS_STEP; }
+int class_cap(int c, int horizon) {
+    const int cap = QR_CLASS_STEP * (c + 1);
+    return cap < 4 * horizon ? cap : 4 * horizon;
+}
+
+int ensure_work(int nclass, int batch) {
+    const size_t need = ((size_t)2 * nclass + (size_t)nclass * batch) * sizeof(int);
+    if (need <= g_ctx.work_bytes) return QR_OK;
+    if (g_ctx.work) cudaFree(g_ctx.work);
+    g_ctx.work = nullptr;
+    g_ctx.work_bytes = 0;
+    cudaError_t e = cudaMalloc(&g_ctx.work, need);
+    if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMalloc(work lists)", e);
+    g_ctx.work_bytes = need;
+    return QR_OK;
+}
+
+extern "C" int qr_gpu_mpc_occupancy(int horizon, int stance_footsteps, int* sm_count, int* ctas_per_sm,
+                                    int* threads_per_cta, int* smem_bytes) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
     if (horizon < 1 || horizon > QR_MAX_HORIZON) return fail(QR_EINVAL, "horizon out of range");
+    if (stance_footsteps < 0 || stance_footsteps > 4 * horizon) return fail(QR_EINVAL, "stance count out of range");
+    int c = (stance_footsteps + QR_CLASS_STEP - 1) / QR_CLASS_STEP - 1;
+    if (c < 0) c = 0;
     int grid = 0, occ = 0;
     size_t smem = 0;
-    int rc = launch_geometry(qr_mpc_fused_kernel, horizon, 1 << 30, &grid, &smem, &occ);
+    bool hsg = false;
+    int rc = launch_geometry(qr_mpc_fused_kernel, class_cap(c, horizon), horizon, 1 << 30, &grid, &smem, &occ, &hsg);
     if (rc) return rc;
     if (sm_count) *sm_count = g_ctx.sm_count;
     if (ctas_per_sm) *ctas_per_sm = occ;
@@ -184,25 +260,61 @@ extern "C" int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_option
     if (batch == 0) return QR_OK;
     if (!p || !v || !quat || !w || !r_feet || !rpy || !traj || !gait || !grf_out)
         return fail(QR_EINVAL, "null input/output pointer");
-    int grid = 0;
-    size_t smem = 0;
-    rc = launch_geometry(qr_mpc_fused_kernel, P->horizon, batch, &grid, &smem, nullptr);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int h = P->horizon, nclass = num_classes(h);
+    rc = ensure_work(nclass, batch);
     if (rc) return rc;
-    rc = ensure_scratch(grid, 4 * P->horizon);
-    if (rc) return rc;
+    int* counts = g_ctx.work;
+    int* tickets = g_ctx.work + nclass;
+    int* lists = g_ctx.work + 2 * nclass;
+    // geometry of every class first (so that the scratch is sized once, before any launch)
+    int grid[16];
+    size_t smem[16];
+    bool hsg[16];
+    size_t scratch_need = 0;
+    for (int c = 0; c < nclass; ++c) {
+        rc = launch_geometry(qr_mpc_fused_kernel, class_cap(c, h), h, batch, &grid[c], &smem[c], nullptr, &hsg[c]);
+        if (rc) return rc;
+        size_t need = (size_t)grid[c] * qr_fallback_doubles(class_cap(c, h));
+        if (hsg[c]) need += (size_t)grid[c] * 9 * qr_ntri(class_cap(c, h));
+        if (need > scratch_need) scratch_need = need;
+    }
+    if (scratch_need * sizeof(double) > g_ctx.scratch_bytes) {
+        if (g_ctx.scratch) cudaFree(g_ctx.scratch);
+        g_ctx.scratch = nullptr;
+        g_ctx.scratch_bytes = 0;
+        cudaError_t e = cudaMalloc(&g_ctx.scratch, scratch_need * sizeof(double));
+        if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMalloc(scratch)", e);
+        g_ctx.scratch_bytes = scratch_need * sizeof(double);
+    }
     QrMpcArgs A;
     memset(&A, 0, sizeof(A));
     A.P = *P;
     A.opt = opt ? *opt : default_options();
     A.batch = batch;
-    A.nfcap = 4 * P->horizon;
     A.p = p; A.v = v; A.quat = quat; A.w = w; A.r_feet = r_feet; A.rpy = rpy; A.traj = traj; A.gait = gait;
     A.mu_i = mu_i; A.fmax_i = fmax_i;
     A.grf_out = grf_out; A.u_out = u_out; A.status_out = status_out; A.iters_out = iters_out;
     A.scratch = g_ctx.scratch;
-    qr_mpc_fused_kernel<<<grid, QR_NT, smem, (cudaStream_t)cuda_stream>>>(A);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_fused_kernel", e);
+    cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)2 * nclass * sizeof(int), st);
+    if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemsetAsync(work counters)", e);
+    qr_mpc_classify_kernel<<<(batch + 255) / 256, 256, 0, st>>>(A, nclass, counts, lists);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_classify_kernel", e);
+    // largest workspaces first: their instances take longest
+    for (int c = nclass - 1; c >= 0; --c) {
+        // the attribute is per function: re-assert this class's dynamic shared memory size
+        e = cudaFuncSetAttribute(qr_mpc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem[c]);
+        if (e != cudaSuccess) return fail(QR_ECUDA, "cudaFuncSetAttribute", e);
+        A.nfcap = class_cap(c, h);
+        A.hs_global = hsg[c] ? g_ctx.scratch + (size_t)grid[c] * qr_fallback_doubles(A.nfcap) : nullptr;
+        A.list = lists + (size_t)c * batch;
+        A.count = counts + c;
+        A.next = tickets + c;
+        qr_mpc_fused_kernel<<<grid[c], QR_NT, smem[c], st>>>(A);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_fused_kernel", e);
+    }
     return QR_OK;
 }
 
@@ -219,14 +331,15 @@ extern "C" int qr_gpu_mpc_condense_batch(const qr_mpc_params* P, int batch, cons
         return fail(QR_EINVAL, "null input/output pointer");
     int grid = 0;
     size_t smem = 0;
-    rc = launch_geometry(qr_mpc_condense_kernel, P->horizon, batch, &grid, &smem, nullptr);
+    // the condense-only kernel needs the tables and the staged rows, not the QP workspace
+    rc = launch_geometry(qr_mpc_condense_kernel, QR_CLASS_STEP, P->horizon, batch, &grid, &smem, nullptr);
     if (rc) return rc;
     QrMpcArgs A;
     memset(&A, 0, sizeof(A));
     A.P = *P;
     A.opt = default_options();
     A.batch = batch;
-    A.nfcap = 4 * P->horizon;
+    A.nfcap = QR_CLASS_STEP;
     A.p = p; A.v = v; A.quat = quat; A.w = w; A.r_feet = r_feet; A.rpy = rpy; A.traj = traj; A.gait = gait;
     A.fmax_i = fmax_i;
     A.H_out = H_out; A.g_out = g_out; A.ub_out = ub_out;
@@ -250,9 +363,10 @@ extern "C" int qr_gpu_qp_solve_batch(int horizon, float mu, const qr_qp_options*
     if (!H || !g || !ub || (!x_out && !x_out_f64)) return fail(QR_EINVAL, "null input/output pointer");
     int grid = 0;
     size_t smem = 0;
-    rc = launch_geometry(qr_qp_solve_kernel, horizon, batch, &grid, &smem, nullptr);
+    bool hsg = false;
+    rc = launch_geometry(qr_qp_solve_kernel, 4 * horizon, horizon, batch, &grid, &smem, nullptr, &hsg);
     if (rc) return rc;
-    rc = ensure_scratch(grid, 4 * horizon);
+    rc = ensure_scratch(grid, 4 * horizon, hsg);
     if (rc) return rc;
     QrMpcArgs A;
     memset(&A, 0, sizeof(A));
@@ -264,6 +378,7 @@ extern "C" int qr_gpu_qp_solve_batch(int horizon, float mu, const qr_qp_options*
     A.H_in = H; A.g_in = g; A.ub_in = ub;
     A.x_out = x_out; A.x_out_f64 = x_out_f64; A.status_out = status_out; A.iters_out = iters_out;
     A.scratch = g_ctx.scratch;
+    A.hs_global = hsg ? g_ctx.scratch + (size_t)grid * qr_fallback_doubles(A.nfcap) : nullptr;
     qr_qp_solve_kernel<<<grid, QR_NT, smem, (cudaStream_t)cuda_stream>>>(A);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_qp_solve_kernel", e);
@@ -320,8 +435,6 @@ extern "C" int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_o
     float* dgait = up(gait, B * 4 * h);
     float* dmu = up(mu_i, B);
     float* dfm = up(fmax_i, B);
-    if (!mu_i) d += B;
-    if (!fmax_i) d += B;
     if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpyAsync H2D", e);
     float* dgrf = d; d += B * 12;
     float* du = nullptr;

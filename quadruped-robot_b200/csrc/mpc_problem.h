@@ -11,13 +11,19 @@ struct QrMpcArgs {
     qr_mpc_params P;
     qr_qp_options opt;
     int batch;
-    int nfcap;               // capacity (stance foot-steps) the workspace was carved for
+    int nfcap;               // capacity (stance foot-steps) this launch's workspace is carved for
     const float *p, *v, *quat, *w, *r_feet, *rpy, *traj, *gait, *mu_i, *fmax_i;
     float* grf_out;          // [batch][12]
     float* u_out;            // [batch][12h] or null
     int32_t* status_out;     // [batch] or null
     int32_t* iters_out;      // [batch][2] or null
-    double* scratch;         // [teams][9*ntri(nfcap)] symmetric Hessian blocks
+    double* scratch;         // [teams][qr_fallback_doubles(nfcap)] vectors of the interior-point fallback
+    double* hs_global;       // [teams][9*ntri(nfcap)] Hessian blocks when they do not fit in shared memory, else null
+    // work list of this launch (size class): problems list[0 .. *count), handed out through *next.
+    // list == null: problems 0 .. batch-1.
+    const int* list;
+    const int* count;
+    int* next;
     // condense-only outputs
     float *H_out, *g_out, *ub_out;
     // qp-only inputs / outputs
@@ -26,45 +32,52 @@ struct QrMpcArgs {
     double* x_out_f64;
 };
 
-QR_DEV int qr_ntri(int nf) { return (nf * (nf + 1)) / 2; }
+QR_HD int qr_ntri(int nf) { return (nf * (nf + 1)) / 2; }
+QR_HD size_t qr_fallback_doubles(int nfcap) { return (size_t)43 * nfcap + 8; }
+QR_HD size_t qr_kbytes(int nfcap) {
+    size_t kb = (size_t)9 * qr_ntri(nfcap) * sizeof(double);
+    return kb > sizeof(QrCondenseTables) ? kb : ((sizeof(QrCondenseTables) + 15) & ~(size_t)15);
+}
 
 // Shared-memory footprint in bytes for a workspace able to hold nfcap stance foot-steps.
-QR_HD size_t qr_mpc_smem_bytes(int nfcap, int horizon) {
-    size_t dbl = (size_t)9 * ((nfcap * (nfcap + 1)) / 2) + (size_t)83 * nfcap + 8;
-    size_t bytes = dbl * sizeof(double);
-    bytes += sizeof(QrCondenseTables);
-    bytes += (size_t)(16 * horizon + 32) * sizeof(float);    // staged traj + gait + state rows
-    bytes += (size_t)(3 * nfcap + 2 * 4 * horizon + 8) * sizeof(int);
+QR_HD size_t qr_mpc_smem_bytes(int nfcap, int horizon, bool hs_in_smem = true) {
+    size_t bytes = hs_in_smem ? (size_t)9 * qr_ntri(nfcap) * sizeof(double) : 0;   // Hs
+    bytes += qr_kbytes(nfcap);                                     // K (aliased by the condense tables)
+    bytes += (size_t)(9 + 9 + 7 * 3 + 1) * nfcap * sizeof(double) + 8 * sizeof(double);
+    bytes += (size_t)(16 * horizon + 32) * sizeof(float);          // staged traj + gait + state rows
+    bytes += (size_t)(3 * nfcap + (nfcap + 1) + 3 * nfcap + 2 * 4 * horizon + 8) * sizeof(int);
+    bytes += (size_t)qr_ntri(nfcap) * sizeof(unsigned short);
     return (bytes + 15) & ~(size_t)15;
 }
 
 struct QrMpcSmem {
     QrQpWork W;
-    QrCondenseTables* T;
+    QrCondenseTables* T;  // aliases W.K (dead before the first factorisation)
     float* traj;   // [12h]
     float* gait;   // [4h]
     float* state;  // [32]: p v quat w r_feet rpy
     int* fs;       // [4h] stance list: fs[s] = foot-step id 4*i + leg
     int* slot;     // [4h] inverse map (or -1)
     int* misc;     // [8]
+    double* scal;  // [8] scalars broadcast through shared memory (scal[0] = mu_)
 };
 
-QR_DEV void qr_mpc_carve(QrMpcSmem& S, unsigned char* base, int nfcap, int horizon) {
+QR_DEV void qr_mpc_carve(QrMpcSmem& S, unsigned char* base, int nfcap, int horizon, double* fallback,
+                         double* hs_global = nullptr) {
     double* d = reinterpret_cast<double*>(base);
     QrQpWork& W = S.W;
     const int n = 3 * nfcap, m = 5 * nfcap;
-    W.K = d; d += 9 * qr_ntri(nfcap);
+    if (hs_global) W.Hs = hs_global;
+    else { W.Hs = d; d += 9 * qr_ntri(nfcap); }
+    W.K = d; d = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d) + qr_kbytes(nfcap));
+    S.T = reinterpret_cast<QrCondenseTables*>(W.K);
     W.Dinv = d; d += 9 * nfcap;
-    W.Zs = d; d += 9 * nfcap;
-    W.ps = d; d += n;
-    W.g = d; d += n;  W.x = d; d += n;  W.xn = d; d += n; W.q = d; d += n; W.wv = d; d += n;
-    W.yv = d; d += n; W.dxa = d; d += n; W.dx = d; d += n; W.rd = d; d += n;
-    W.s = d; d += m; W.lam = d; d += m; W.dsa = d; d += m; W.dla = d; d += m; W.rc = d; d += m; W.dl = d; d += m;
+    W.zv = d; d += 9 * nfcap;
+    W.ps = d; d += n; W.g = d; d += n; W.xn = d; d += n; W.q = d; d += n; W.wv = d; d += n;
+    W.yv = d; d += n; W.dx = d; d += n;
     W.ubz = d; d += nfcap;
-    W.red = d; d += 4 * nfcap;
-    d += 8;
-    S.T = reinterpret_cast<QrCondenseTables*>(d);
-    float* f = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(d) + sizeof(QrCondenseTables));
+    S.scal = d; d += 8;
+    float* f = reinterpret_cast<float*>(d);
     S.traj = f; f += 12 * horizon;
     S.gait = f; f += 4 * horizon;
     S.state = f; f += 32;
@@ -72,14 +85,34 @@ QR_DEV void qr_mpc_carve(QrMpcSmem& S, unsigned char* base, int nfcap, int horiz
     W.act = ip; ip += nfcap;
     W.flag = ip; ip += nfcap;
     W.vert = ip; ip += nfcap;
+    W.foff = ip; ip += nfcap + 1;
+    W.rfoot = ip; ip += 3 * nfcap;
     S.fs = ip; ip += 4 * horizon;
     S.slot = ip; ip += 4 * horizon;
-    S.misc = ip;
+    S.misc = ip; ip += 8;
+    W.tri = reinterpret_cast<unsigned short*>(ip);
+    // interior-point fallback vectors (global)
+    double* gsc = fallback;
+    W.x = gsc; gsc += n; W.dxa = gsc; gsc += n; W.rd = gsc; gsc += n;
+    W.s = gsc; gsc += m; W.lam = gsc; gsc += m; W.dsa = gsc; gsc += m; W.dla = gsc; gsc += m;
+    W.rc = gsc; gsc += m; W.dl = gsc; gsc += m;
+    W.red = gsc;
+}
+
+// Once per launch: the triangular index decode table.
+template <int NT>
+QR_DEV void qr_mpc_init_tables(QrMpcSmem& S, int nfcap) {
+    QR_FOR(idx, qr_ntri(nfcap)) {
+        int I, J;
+        qr_tri_decode(idx, I, J);
+        S.W.tri[idx] = (unsigned short)((I << 8) | J);
+    }
+    QR_SYNC();
 }
 
 // Stage this problem's rows and build the stance list.  After return (and its trailing barrier):
 // S.state/traj/gait hold the inputs, S.fs/slot the stance map, W.nf, W.ubz, W.mu_ are set, and
-// S.misc[0] = per-instance status so far (0 ok, 2 negative bound, 3 non-finite input).
+// S.misc[0] = per-instance status so far (0 ok, 2 negative bound, 3 non-finite input / over capacity).
 template <int NT>
 QR_DEV void qr_mpc_stage(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
     const int h = A.P.horizon;
@@ -100,7 +133,7 @@ QR_DEV void qr_mpc_stage(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
         if (t == 0) {
             const float fmax = A.fmax_i ? A.fmax_i[prob] : A.P.f_max;
             const float mu = A.mu_i ? A.mu_i[prob] : A.P.mu;
-            S.W.mu_ = (double)QR_FDIV(1.f, mu);          // mu_ = 1.f / frictionCoeff (qr_mpc_interface.cpp:230)
+            S.scal[0] = (double)QR_FDIV(1.f, mu);        // mu_ = 1.f / frictionCoeff (qr_mpc_interface.cpp:230)
             int nf = 0, st = 0;
             for (int k = 0; k < 4 * h; ++k) {
                 const float ub = QR_FMUL(S.gait[k], fmax);   // U_b(5k+4) = gait * fMax (:387)
@@ -110,7 +143,7 @@ QR_DEV void qr_mpc_stage(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
                     S.slot[k] = -1;
                     if (ub < 0.f) st = 2;
                     if (!(ub == ub)) st = 3;
-                    if (ub > 0.f) st = 3;  // capacity exceeded (cannot happen when nfcap == 4h)
+                    if (ub > 0.f) st = 3;  // over capacity: the size classification makes this unreachable
                 }
             }
             for (int i = 0; i < 28; ++i) if (!(fabsf(S.state[i]) < 3.0e38f)) st = 3;
@@ -121,12 +154,13 @@ QR_DEV void qr_mpc_stage(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
     }
     QR_SYNC();
     S.W.nf = S.misc[1];
+    S.W.mu_ = S.scal[0];
 }
 
-// Condense into the solver workspace: symmetric Hessian blocks of the stance variables -> Hs
-// (global scratch), g -> W.g.  H_sym = (H + H')/2 evaluated in float64 from the two float32 entries.
+// Condense into the solver workspace: symmetric Hessian blocks of the stance variables -> W.Hs,
+// g -> W.g.  H_sym = (H + H')/2 evaluated in float64 from the two float32 entries.
 template <int NT>
-QR_DEV void qr_mpc_condense_to_work(const QrMpcArgs& A, QrMpcSmem& S, double* Hs) {
+QR_DEV void qr_mpc_condense_to_work(const QrMpcArgs& A, QrMpcSmem& S) {
     const int h = A.P.horizon;
     QrCondenseTables& T = *S.T;
     QR_THREADS(t) {
@@ -138,13 +172,12 @@ QR_DEV void qr_mpc_condense_to_work(const QrMpcArgs& A, QrMpcSmem& S, double* Hs
     const int nf = S.W.nf;
     QR_FOR(idx, 9 * qr_ntri(nf)) {
         const int b = idx / 9, e = idx - 9 * b;
-        int Sb, Tb;
-        qr_tri_decode(b, Sb, Tb);
-        const int ks = S.fs[Sb], kt = S.fs[Tb];
+        const int code = S.W.tri[b];
+        const int ks = S.fs[code >> 8], kt = S.fs[code & 255];
         const int r = e / 3, c = e - 3 * r;
         const float hst = qr_condense_h_entry(T, h, ks >> 2, ks & 3, r, kt >> 2, kt & 3, c);
         const float hts = qr_condense_h_entry(T, h, kt >> 2, kt & 3, c, ks >> 2, ks & 3, r);
-        Hs[idx] = 0.5 * ((double)hst + (double)hts);
+        S.W.Hs[idx] = 0.5 * ((double)hst + (double)hts);
     }
     QR_FOR(i, 3 * nf) {
         const int k = S.fs[i / 3];
@@ -156,42 +189,45 @@ QR_DEV void qr_mpc_condense_to_work(const QrMpcArgs& A, QrMpcSmem& S, double* Hs
 // Scatter the stance solution into the 12h force vector (swing foot-steps are exactly zero).
 template <int NT>
 QR_DEV void qr_mpc_scatter(const QrMpcArgs& A, int prob, QrMpcSmem& S, const double* x, int status,
-                           int ipm_iters, int polish_rounds) {
+                           int ipm_iters, int as_rounds) {
     const int h = A.P.horizon;
+    const bool valid = status != 2 && status != 3;
     QR_FOR(i, 12 * h) {
         const int k = i / 3, sl = S.slot[k];
-        const float val = (sl >= 0 && status != 2 && status != 3) ? (float)x[3 * sl + (i - 3 * k)] : 0.f;
+        const double v64 = (sl >= 0 && valid) ? x[3 * sl + (i - 3 * k)] : 0.0;
+        const float val = (float)v64;
         if (A.u_out) A.u_out[(size_t)prob * 12 * h + i] = val;
         if (i < 12 && A.grf_out) A.grf_out[(size_t)prob * 12 + i] = val;
         if (A.x_out) A.x_out[(size_t)prob * 12 * h + i] = val;
-        if (A.x_out_f64) A.x_out_f64[(size_t)prob * 12 * h + i] = (sl >= 0 && status != 2 && status != 3) ? x[3 * sl + (i - 3 * k)] : 0.0;
+        if (A.x_out_f64) A.x_out_f64[(size_t)prob * 12 * h + i] = v64;
     }
     QR_THREADS(t) {
         if (t == 0) {
             if (A.status_out) A.status_out[prob] = status;
-            if (A.iters_out) { A.iters_out[2 * prob] = ipm_iters; A.iters_out[2 * prob + 1] = polish_rounds; }
+            if (A.iters_out) { A.iters_out[2 * prob] = ipm_iters; A.iters_out[2 * prob + 1] = as_rounds; }
         }
     }
 }
 
+// breakdown guard: a non-finite result is reported, never returned as a force
+template <int NT>
+QR_DEV int qr_result_status(QrMpcSmem& S, const double* x, int status) {
+    int bad = 0;
+    QR_FOR(i, 3 * S.W.nf) bad |= !(fabs(x[i]) < 1e300);
+    return QR_ANY(bad) ? 3 : status;
+}
+
 // The fused path: SolveMPCKernel + GetMPCSolution for one instance.
 template <int NT>
-QR_DEV void qr_mpc_solve_problem(const QrMpcArgs& A, int prob, unsigned char* smem, double* Hs) {
-    QrMpcSmem S;
-    qr_mpc_carve(S, smem, A.nfcap, A.P.horizon);
+QR_DEV void qr_mpc_solve_problem(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
     qr_mpc_stage<NT>(A, prob, S);
     int status = S.misc[0];
     int it = 0, rounds = 0;
     const double* x = S.W.xn;
     if (status == 0) {
-        S.W.Hs = Hs;
-        qr_mpc_condense_to_work<NT>(A, S, Hs);
+        qr_mpc_condense_to_work<NT>(A, S);
         status = qr_qp_solve<NT>(S.W, A.opt, &it, &rounds, &x);
-        // breakdown guard: a non-finite result is reported, never returned as a force
-        QR_FOR(i, 3 * S.W.nf) S.W.red[i] = (fabs(x[i]) < 1e300) ? 0.0 : 1.0;
-        QR_SYNC();
-        if (S.W.nf > 0 && qr_red_max<NT>(S.W.red, 3 * S.W.nf) != 0.0) status = 3;
-        QR_SYNC();
+        status = qr_result_status<NT>(S, x, status);
     }
     qr_mpc_scatter<NT>(A, prob, S, x, status, it, rounds);
     QR_SYNC();
@@ -199,9 +235,7 @@ QR_DEV void qr_mpc_solve_problem(const QrMpcArgs& A, int prob, unsigned char* sm
 
 // Condense only: float32 H (n x n), g (n), ub (20h) exactly as SolveMPC hands them to qpOASES.
 template <int NT>
-QR_DEV void qr_mpc_condense_problem(const QrMpcArgs& A, int prob, unsigned char* smem) {
-    QrMpcSmem S;
-    qr_mpc_carve(S, smem, A.nfcap, A.P.horizon);
+QR_DEV void qr_mpc_condense_problem(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
     qr_mpc_stage<NT>(A, prob, S);
     const int h = A.P.horizon, n = 12 * h;
     QrCondenseTables& T = *S.T;
@@ -228,9 +262,7 @@ QR_DEV void qr_mpc_condense_problem(const QrMpcArgs& A, int prob, unsigned char*
 
 // QP only: caller-supplied float32 H, g, ub (the qpOASES call's inputs).
 template <int NT>
-QR_DEV void qr_qp_solve_problem(const QrMpcArgs& A, int prob, unsigned char* smem, double* Hs) {
-    QrMpcSmem S;
-    qr_mpc_carve(S, smem, A.nfcap, A.P.horizon);
+QR_DEV void qr_qp_solve_problem(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
     const int h = A.P.horizon, n = 12 * h;
     const float* H = A.H_in + (size_t)prob * n * n;
     const float* g = A.g_in + (size_t)prob * n;
@@ -238,37 +270,34 @@ QR_DEV void qr_qp_solve_problem(const QrMpcArgs& A, int prob, unsigned char* sme
     QR_THREADS(t) {
         if (t == 0) {
             const float mu = A.mu_i ? A.mu_i[prob] : A.P.mu;
-            S.W.mu_ = (double)QR_FDIV(1.f, mu);
+            S.scal[0] = (double)QR_FDIV(1.f, mu);
             int nf = 0, st = 0;
             for (int k = 0; k < 4 * h; ++k) {
                 const float u = ub[5 * k + 4];
                 if (u > 0.f && nf < A.nfcap) { S.fs[nf] = k; S.slot[k] = nf; S.W.ubz[nf] = (double)u; ++nf; }
-                else { S.slot[k] = -1; if (u < 0.f) st = 2; if (!(u == u)) st = 3; }
+                else { S.slot[k] = -1; if (u < 0.f) st = 2; if (!(u == u)) st = 3; if (u > 0.f) st = 3; }
             }
+            if (!(mu > 0.f)) st = 3;
             S.misc[0] = st; S.misc[1] = nf;
         }
     }
     QR_SYNC();
     S.W.nf = S.misc[1];
-    S.W.Hs = Hs;
+    S.W.mu_ = S.scal[0];
     int status = S.misc[0], it = 0, rounds = 0;
     const double* x = S.W.xn;
     if (status == 0) {
         const int nf = S.W.nf;
         QR_FOR(idx, 9 * qr_ntri(nf)) {
             const int b = idx / 9, e = idx - 9 * b;
-            int Sb, Tb;
-            qr_tri_decode(b, Sb, Tb);
-            const int ri = 3 * S.fs[Sb] + e / 3, ci = 3 * S.fs[Tb] + e % 3;
-            Hs[idx] = 0.5 * ((double)H[(size_t)ri * n + ci] + (double)H[(size_t)ci * n + ri]);
+            const int code = S.W.tri[b];
+            const int ri = 3 * S.fs[code >> 8] + e / 3, ci = 3 * S.fs[code & 255] + e % 3;
+            S.W.Hs[idx] = 0.5 * ((double)H[(size_t)ri * n + ci] + (double)H[(size_t)ci * n + ri]);
         }
         QR_FOR(i, 3 * nf) S.W.g[i] = (double)g[3 * S.fs[i / 3] + i % 3];
         QR_SYNC();
         status = qr_qp_solve<NT>(S.W, A.opt, &it, &rounds, &x);
-        QR_FOR(i, 3 * nf) S.W.red[i] = (fabs(x[i]) < 1e300) ? 0.0 : 1.0;
-        QR_SYNC();
-        if (nf > 0 && qr_red_max<NT>(S.W.red, 3 * nf) != 0.0) status = 3;
-        QR_SYNC();
+        status = qr_result_status<NT>(S, x, status);
     }
     qr_mpc_scatter<NT>(A, prob, S, x, status, it, rounds);
     QR_SYNC();

@@ -8,21 +8,23 @@
 // eliminated up front; the row 0 <= fz is implied by the pyramid rows and is dropped.  What is left
 // are nf "stance" foot-steps, n = 3*nf variables and 5 inequalities on each 3-vector.
 //
-// Method (not qpOASES' online active set -- that is inherently sequential):
-//   1. Mehrotra predictor-corrector interior point.  The constraint matrix is block diagonal
-//      (5 rows on 3 variables), so A'DA is block-diagonal 3x3 and every iteration is one Cholesky
-//      of K = H + blkdiag and two solves.  Run to a loose tolerance: it only has to identify the
-//      active set.
-//   2. Active-set polish.  Each foot-step's active rows define f = Z y + p with Z (3 x d, d<=3);
-//      Z is padded to 3x3 so the reduced KKT matrix Z'HZ (+ identity on padded slots) keeps the
-//      3x3 block structure and reuses the same factorisation.  After the equality-constrained solve
-//      the multipliers and the inactive rows are checked; wrong guesses are corrected and the solve
-//      repeated.  On exit the KKT conditions hold to feas_tol / mult_tol, i.e. the point is THE
-//      optimum of the strictly convex QP (H >= 2*alpha*I), not an approximation of it.
+// Method (not qpOASES' online active set -- one working-set change per iteration is inherently
+// sequential and needs 30-130 of them):
+//   1. Block active-set iteration from a cold start.  Every round guesses, per foot-step, which of
+//      its rows are active.  The active rows of a foot-step define f = Z y + p with Z (3 x d, d <= 3);
+//      all free directions of all foot-steps are packed into one dense reduced system
+//      (Z'HZ) y = -Z'(Hp + g), solved by a blocked Cholesky.  Then the multipliers of the active rows
+//      and the values of the inactive rows are checked for every foot-step at once and the guesses
+//      corrected (violated rows added, rows with a negative multiplier dropped).  When a round
+//      changes nothing the KKT conditions hold to feas_tol / mult_tol, i.e. the point is THE optimum
+//      of the strictly convex QP (H >= 2*alpha*I), not an approximation of it.  Typically 4-10 rounds.
+//   2. Fallback (about 0.1-1 % of instances, where the block updates cycle): Mehrotra
+//      predictor-corrector interior point to identify the active set (A'DA is block-diagonal 3x3 so
+//      an iteration is one Cholesky of H + blkdiag and two solves), then the same verification.
 //
 // Storage: symmetric matrices are lower block-triangular with full 3x3 blocks, block (S,T), S >= T,
-// at 9*(S*(S+1)/2 + T).  H lives in a per-CTA global scratch that stays L2-resident; K (the matrix
-// being factorised) lives in shared memory.
+// at 9*(S*(S+1)/2 + T).  H and the matrix under factorisation both live in shared memory; the
+// vectors only the fallback needs live in a per-CTA global scratch.
 #pragma once
 
 #include "qr_team.h"
@@ -31,36 +33,33 @@
 struct QrQpWork {
     int nf;             // stance foot-steps
     double mu_;         // 1/mu as the reference rounds it (float32 value)
-    const double* Hs;   // [9*ntri] symmetric block-packed Hessian (global scratch)
-    double* K;          // [9*ntri] shared: matrix under factorisation
-    double* Dinv;       // [9*nf]   inverse of the diagonal Cholesky blocks
-    double* Zs;         // [9*nf]   polish bases (3x3, zero-padded columns)
-    double* ps;         // [3*nf]   polish offsets
-    double* g;          // [n]
-    double* x;          // [n]  interior-point iterate
-    double* xn;         // [n]  polished iterate
-    double* q;          // [n]  H x + g
-    double* wv;         // [n]  solve work vector
-    double* yv;         // [n]  forward-solve result
-    double* dxa;        // [n]
-    double* dx;         // [n]
-    double* rd;         // [n]
-    double* s;          // [5*nf]
-    double* lam;        // [5*nf]
-    double* dsa;        // [5*nf]
-    double* dla;        // [5*nf]
-    double* rc;         // [5*nf]
-    double* dl;         // [5*nf]
-    double* ubz;        // [nf]
-    double* red;        // [4*nf] reduction scratch
-    int* act;           // [nf] active-row bit masks (bit c = row c; bit 4 = cap)
-    int* flag;          // [nf]
-    int* vert;          // [nf] polish: foot-step pinned to the apex f = 0
+    double* Hs;         // [9*ntri(cap)] shared: symmetric block-packed Hessian
+    double* K;          // [9*ntri(cap)] shared: matrix under factorisation
+    double* Dinv;       // [9*cap]  inverse of the diagonal Cholesky blocks
+    double* zv;         // [9*cap]  basis vector (3 doubles) of every reduced variable
+    double* ps;         // [3*cap]  offsets p of f = Z y + p
+    double* g;          // [3*cap]
+    double* xn;         // [3*cap]  current / final iterate
+    double* q;          // [3*cap]  H p + g, later H x + g
+    double* wv;         // [3*cap]  solve work vector
+    double* yv;         // [3*cap]  forward-solve result
+    double* dx;         // [3*cap]  solve result
+    double* ubz;        // [cap]
+    int* act;           // [cap] active-row bit masks (bit c = row c; bit 4 = cap)
+    int* vert;          // [cap] foot-step pinned to the apex f = 0
+    int* flag;          // [cap]
+    int* foff;          // [cap+1] first reduced variable of every foot-step
+    int* rfoot;         // [3*cap] foot-step of every reduced variable (-1: padding)
+    unsigned short* tri;// [ntri(cap)] lower-triangular index decode table, (I << 8) | J
+    // fallback-only vectors (global scratch)
+    double *x, *dxa, *rd;               // [3*cap]
+    double *s, *lam, *dsa, *dla, *rc, *dl;  // [5*cap]
+    double* red;                        // [4*cap]
 };
 
 QR_DEV int qr_blk(int S, int T) { return 9 * ((S * (S + 1)) / 2 + T); }
 
-// Decode a lower-triangular linear index idx -> (I, J), I >= J.
+// Decode a lower-triangular linear index idx -> (I, J), I >= J (used once per launch to fill W.tri).
 QR_DEV void qr_tri_decode(int idx, int& I, int& J) {
     int i = (int)((sqrtf(8.f * (float)idx + 1.f) - 1.f) * 0.5f);
     while ((i + 1) * (i + 2) / 2 <= idx) ++i;
@@ -84,9 +83,10 @@ QR_DEV double qr_sym_matvec_row(const double* Hs, const double* v, int nf, int i
     const double* row = Hs + qr_blk(S, 0) + 3 * a;
     for (int T = 0; T <= S; ++T, row += 9)
         acc += row[0] * v[3 * T] + row[1] * v[3 * T + 1] + row[2] * v[3 * T + 2];
+    const double* col = Hs + qr_blk(S + 1, S) + a;
     for (int T = S + 1; T < nf; ++T) {
-        const double* col = Hs + qr_blk(T, S) + a;
         acc += col[0] * v[3 * T] + col[3] * v[3 * T + 1] + col[6] * v[3 * T + 2];
+        col += 9 * (T + 1);
     }
     return acc;
 }
@@ -96,37 +96,29 @@ QR_DEV double qr_sym_matvec_row(const double* Hs, const double* v, int nf, int i
 struct QrChol3 {
     double i00, i11, i22, l10, l20, l21;
 };
-QR_DEV QrChol3 qr_chol3(const double* D, int* bad) {
+QR_DEV QrChol3 qr_chol3(const double* D) {
     QrChol3 c;
-    double d00 = D[0];
-    if (!(d00 > 1e-300)) { d00 = 1e-300; *bad = 1; }
-    c.i00 = qr_rsqrt(d00);
+    c.i00 = qr_rsqrt(qr_max(D[0], 1e-300));
     c.l10 = D[3] * c.i00;
     c.l20 = D[6] * c.i00;
-    double t = D[4] - c.l10 * c.l10;
-    if (!(t > 1e-300)) { t = 1e-300; *bad = 1; }
-    c.i11 = qr_rsqrt(t);
+    c.i11 = qr_rsqrt(qr_max(D[4] - c.l10 * c.l10, 1e-300));
     c.l21 = (D[7] - c.l20 * c.l10) * c.i11;
-    double u = D[8] - c.l20 * c.l20 - c.l21 * c.l21;
-    if (!(u > 1e-300)) { u = 1e-300; *bad = 1; }
-    c.i22 = qr_rsqrt(u);
+    c.i22 = qr_rsqrt(qr_max(D[8] - c.l20 * c.l20 - c.l21 * c.l21, 1e-300));
     return c;
 }
 
-// In-place blocked Cholesky K = L L'.  Off-diagonal blocks of K are overwritten with L; the diagonal
-// blocks are left untouched and their inverse factors go to Dinv (that is all the solves need).
-// Returns non-zero (uniformly) if a pivot had to be clamped.
+// In-place blocked Cholesky K = L L' of the leading nb x nb blocks.  Off-diagonal blocks of K are
+// overwritten with L; the diagonal blocks are left untouched and their inverse factors go to Dinv
+// (that is all the solves need).  Non-positive pivots are clamped (the caller's verification or the
+// final finiteness check catches a breakdown).
 template <int NT>
-QR_DEV int qr_blk_cholesky(QrQpWork& W) {
-    const int nf = W.nf;
+QR_DEV void qr_blk_cholesky(QrQpWork& W, int nb) {
     double* K = W.K;
-    QR_FOR(f, nf) W.flag[f] = 0;
-    for (int Kc = 0; Kc < nf; ++Kc) {
+    for (int Kc = 0; Kc < nb; ++Kc) {
         // panel: every row of the block column solves against the (redundantly factorised) diagonal block
-        QR_FOR(idx, 3 * (nf - Kc)) {
+        QR_FOR(idx, 3 * (nb - Kc)) {
             const int I = Kc + idx / 3, a = idx % 3;
-            int bad = 0;
-            const QrChol3 c = qr_chol3(K + qr_blk(Kc, Kc), &bad);
+            const QrChol3 c = qr_chol3(K + qr_blk(Kc, Kc));
             if (I == Kc) {
                 double* Di = W.Dinv + 9 * Kc;
                 if (a == 0) {
@@ -138,7 +130,6 @@ QR_DEV int qr_blk_cholesky(QrQpWork& W) {
                     Di[6] = -(c.l20 * c.i00 + c.l21 * inv10) * c.i22;
                     Di[7] = -c.l21 * c.i11 * c.i22;
                     Di[8] = c.i22;
-                    if (bad) W.flag[Kc] = 1;
                 }
             } else {
                 double* r = K + qr_blk(I, Kc) + 3 * a;
@@ -150,14 +141,14 @@ QR_DEV int qr_blk_cholesky(QrQpWork& W) {
         }
         QR_SYNC();
         // trailing update A_IJ -= L_IK L_JK'
-        const int nb = nf - Kc - 1;
-        QR_FOR(idx, (nb * (nb + 1)) / 2) {
-            int I, J;
-            qr_tri_decode(idx, I, J);
-            I += Kc + 1; J += Kc + 1;
-            const double* li = K + qr_blk(I, Kc);
+        const int nrem = nb - Kc - 1;
+        QR_FOR(idx, (nrem * (nrem + 1)) / 2) {
+            const int code = W.tri[idx];
+            const int I = (code >> 8) + Kc + 1, J = (code & 255) + Kc + 1;
+            const int rowI = (I * (I + 1)) / 2;
+            const double* li = K + 9 * (rowI + Kc);
             const double* lj = K + qr_blk(J, Kc);
-            double* a = K + qr_blk(I, J);
+            double* a = K + 9 * (rowI + J);
             double l[9], m[9];
 #pragma unroll
             for (int e = 0; e < 9; ++e) { l[e] = li[e]; m[e] = lj[e]; }
@@ -169,22 +160,17 @@ QR_DEV int qr_blk_cholesky(QrQpWork& W) {
         }
         QR_SYNC();
     }
-    int bad = 0;
-    for (int f = 0; f < nf; ++f) bad |= W.flag[f];
-    QR_SYNC();
-    return bad;
 }
 
-// Solve (L L') out = W.wv.  W.wv and W.yv are destroyed.
+// Solve (L L') out = W.wv on the leading nb blocks.  W.wv and W.yv are destroyed.
 template <int NT>
-QR_DEV void qr_blk_solve(QrQpWork& W, double* out) {
-    const int nf = W.nf;
+QR_DEV void qr_blk_solve(QrQpWork& W, int nb, double* out) {
     const double* K = W.K;
     double* v = W.wv;
     double* y = W.yv;
     // forward: L y = v
-    for (int Kc = 0; Kc < nf; ++Kc) {
-        QR_FOR(idx, 3 * (nf - Kc)) {
+    for (int Kc = 0; Kc < nb; ++Kc) {
+        QR_FOR(idx, 3 * (nb - Kc)) {
             const int I = Kc + idx / 3, a = idx % 3;
             const double* Di = W.Dinv + 9 * Kc;
             const double b0 = v[3 * Kc], b1 = v[3 * Kc + 1], b2 = v[3 * Kc + 2];
@@ -201,7 +187,7 @@ QR_DEV void qr_blk_solve(QrQpWork& W, double* out) {
         QR_SYNC();
     }
     // backward: L' out = y, in place on y (a step reads block Kc of y and updates blocks J < Kc)
-    for (int Kc = nf - 1; Kc >= 0; --Kc) {
+    for (int Kc = nb - 1; Kc >= 0; --Kc) {
         QR_FOR(idx, 3 * (Kc + 1)) {
             const int J = idx / 3, a = idx % 3;
             const double* Di = W.Dinv + 9 * Kc;
@@ -236,6 +222,186 @@ QR_DEV void qr_foot_At(double mu_, const double* t, double* o) {
     o[2] = t[0] + t[1] + t[2] + t[3] - t[4];
 }
 
+// Basis of one foot-step's active face: f = Z y + p with the d free directions in the first d
+// columns of Z (3x3 row-major).  act bits 0..3 = pyramid faces, bit 4 = cap.
+// Returns d, or -1 when the active rows pin f = 0 (apex of the pyramid).
+QR_DEV int qr_foot_basis(int act, double mu_, double ub, double* Z, double* p) {
+    const int a0 = act & 1, a1 = (act >> 1) & 1, a2 = (act >> 2) & 1, a3 = (act >> 3) & 1, cap = (act >> 4) & 1;
+    for (int e = 0; e < 9; ++e) Z[e] = 0.0;
+    p[0] = p[1] = p[2] = 0.0;
+    if (a0 + a1 == 2 || a2 + a3 == 2 || a0 + a1 + a2 + a3 >= 3) return -1;
+    const double im = 1.0 / mu_;
+    // active face mu_*fx + fz = 0 -> fx = -fz/mu_ ; face -mu_*fx + fz = 0 -> fx = +fz/mu_
+    const double kx = a0 ? -im : (a1 ? im : 0.0);
+    const double ky = a2 ? -im : (a3 ? im : 0.0);
+    int d = 0;
+    if (!(a0 | a1)) { Z[d] = 1.0; ++d; }                 // e_x
+    if (!(a2 | a3)) { Z[3 + d] = 1.0; ++d; }             // e_y
+    if (cap) {
+        p[0] = kx * ub; p[1] = ky * ub; p[2] = ub;
+    } else {
+        Z[d] = kx; Z[3 + d] = ky; Z[6 + d] = 1.0; ++d;   // (kx, ky, 1) * fz
+    }
+    return d;
+}
+
+// Block active-set iteration (see the header comment).  cold = 1: start with no row active;
+// cold = 0: start from the active set the interior-point iterate (W.s, W.lam) suggests.
+// Result in W.xn.  Returns rounds used; *ok = 1 when the KKT conditions were verified.
+template <int NT>
+QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int cold, int max_rounds) {
+    const int nf = W.nf, n = 3 * nf;
+    const double mu_ = W.mu_;
+    const double im = 1.0 / mu_;
+    QR_FOR(f, nf) {
+        int a = 0;
+        if (!cold)
+            for (int c = 0; c < 5; ++c)
+                if (W.s[5 * f + c] < opt.act_kappa * W.lam[5 * f + c]) a |= (1 << c);
+        W.act[f] = a;
+    }
+    QR_SYNC();
+    *ok = 0;
+    int round = 0;
+    for (; round < max_rounds; ++round) {
+        // ---- bases of the current guess; K is free here, its head is scratch for the 3x3 bases
+        double* Zfull = W.K;
+        QR_FOR(f, nf) {
+            const int d = qr_foot_basis(W.act[f], mu_, W.ubz[f], Zfull + 9 * f, W.ps + 3 * f);
+            W.vert[f] = d < 0;
+            W.flag[f] = d < 0 ? 0 : d;
+        }
+        QR_SYNC();
+        // ---- pack the free directions: prefix sum of d_f (serial, nf <= 64) and the z vectors
+        QR_THREADS(t) {
+            if (t == 0) {
+                int off = 0;
+                for (int f = 0; f < nf; ++f) { W.foff[f] = off; off += W.flag[f]; }
+                W.foff[nf] = off;
+            }
+        }
+        QR_SYNC();
+        const int nred = W.foff[nf];
+        const int nbr = (nred + 2) / 3;
+        QR_FOR(f, nf) {
+            const int off = W.foff[f], d = W.flag[f];
+            for (int c = 0; c < d; ++c) {
+                W.rfoot[off + c] = f;
+                W.zv[3 * (off + c)] = Zfull[9 * f + c];
+                W.zv[3 * (off + c) + 1] = Zfull[9 * f + 3 + c];
+                W.zv[3 * (off + c) + 2] = Zfull[9 * f + 6 + c];
+            }
+        }
+        QR_FOR(r, 3 * nbr - nred) W.rfoot[nred + r] = -1;
+        // hp = H p + g  -> q   (reads ps only)
+        QR_FOR(i, n) W.q[i] = qr_sym_matvec_row(W.Hs, W.ps, nf, i) + W.g[i];
+        QR_SYNC();
+        // ---- reduced matrix (Z'HZ), padded to a multiple of 3 with identity; right-hand side
+        QR_FOR(idx, 9 * ((nbr * (nbr + 1)) / 2)) {
+            const int b = idx / 9, e = idx - 9 * b;
+            const int code = W.tri[b];
+            const int r1 = 3 * (code >> 8) + e / 3, r2 = 3 * (code & 255) + e % 3;
+            const int f1 = W.rfoot[r1], f2 = W.rfoot[r2];
+            double val;
+            if (f1 < 0 || f2 < 0) {
+                val = (r1 == r2) ? 1.0 : 0.0;
+            } else {
+                const double* z1 = W.zv + 3 * r1;
+                const double* z2 = W.zv + 3 * r2;
+                double t0, t1, t2;   // t = H_{f1 f2} z2
+                if (f1 >= f2) {
+                    const double* Hb = W.Hs + qr_blk(f1, f2);
+                    t0 = Hb[0] * z2[0] + Hb[1] * z2[1] + Hb[2] * z2[2];
+                    t1 = Hb[3] * z2[0] + Hb[4] * z2[1] + Hb[5] * z2[2];
+                    t2 = Hb[6] * z2[0] + Hb[7] * z2[1] + Hb[8] * z2[2];
+                } else {
+                    const double* Hb = W.Hs + qr_blk(f2, f1);
+                    t0 = Hb[0] * z2[0] + Hb[3] * z2[1] + Hb[6] * z2[2];
+                    t1 = Hb[1] * z2[0] + Hb[4] * z2[1] + Hb[7] * z2[2];
+                    t2 = Hb[2] * z2[0] + Hb[5] * z2[1] + Hb[8] * z2[2];
+                }
+                val = z1[0] * t0 + z1[1] * t1 + z1[2] * t2;
+            }
+            W.K[idx] = val;
+        }
+        QR_FOR(r, 3 * nbr) {
+            const int f = W.rfoot[r];
+            W.wv[r] = f < 0 ? 0.0
+                            : -(W.zv[3 * r] * W.q[3 * f] + W.zv[3 * r + 1] * W.q[3 * f + 1] + W.zv[3 * r + 2] * W.q[3 * f + 2]);
+        }
+        QR_SYNC();
+        qr_blk_cholesky<NT>(W, nbr);
+        qr_blk_solve<NT>(W, nbr, W.dx);
+        QR_FOR(f, nf) {
+            double x0 = W.ps[3 * f], x1 = W.ps[3 * f + 1], x2 = W.ps[3 * f + 2];
+            const int off = W.foff[f], d = W.flag[f];
+            for (int c = 0; c < d; ++c) {
+                const double y = W.dx[off + c];
+                x0 += y * W.zv[3 * (off + c)];
+                x1 += y * W.zv[3 * (off + c) + 1];
+                x2 += y * W.zv[3 * (off + c) + 2];
+            }
+            W.xn[3 * f] = x0; W.xn[3 * f + 1] = x1; W.xn[3 * f + 2] = x2;
+        }
+        QR_SYNC();
+        QR_FOR(i, n) W.q[i] = qr_sym_matvec_row(W.Hs, W.xn, nf, i) + W.g[i];
+        QR_SYNC();
+        // ---- verify / correct the active sets
+        int changed = 0;
+        QR_FOR(f, nf) {
+            const double* r = W.q + 3 * f;
+            const int act = W.act[f];
+            int nact = act;
+            if (W.vert[f]) {
+                // apex: the gradient must lie in the cone spanned by the four face normals
+                if (r[2] < (fabs(r[0]) + fabs(r[1])) * im - opt.mult_tol) {
+                    const double l0 = r[0] > 0.0 ? r[0] * im : 0.0, l1 = r[0] < 0.0 ? -r[0] * im : 0.0;
+                    const double l2 = r[1] > 0.0 ? r[1] * im : 0.0, l3 = r[1] < 0.0 ? -r[1] * im : 0.0;
+                    nact = (l0 > 0.0 ? 1 : 0) | (l1 > 0.0 ? 2 : 0) | (l2 > 0.0 ? 4 : 0) | (l3 > 0.0 ? 8 : 0);
+                    const int hasx = nact & 3, hasy = nact & 12;
+                    if (hasx && hasy) {
+                        // least-squares multipliers on the edge; drop the face that would pull inward
+                        const double sx = (nact & 1) ? 1.0 : -1.0, sy = (nact & 4) ? 1.0 : -1.0;
+                        const double b0 = sx * mu_ * r[0] + r[2], b1 = sy * mu_ * r[1] + r[2];
+                        const double dd = mu_ * mu_ + 1.0, det = dd * dd - 1.0;
+                        const double lx = (dd * b0 - b1) / det, ly = (dd * b1 - b0) / det;
+                        if (lx < 0.0 || ly < 0.0) {
+                            if (lx < ly) nact &= ~3; else nact &= ~12;
+                        }
+                    }
+                }
+            } else {
+                double c[5];
+                qr_foot_constraints(mu_, W.ubz[f], W.xn + 3 * f, c);
+                int viol = 0;
+                for (int k = 0; k < 5; ++k)
+                    if (!((act >> k) & 1) && c[k] < -opt.feas_tol) viol |= (1 << k);
+                if (viol) {
+                    nact = act | viol;
+                } else if (act) {
+                    // multipliers of the (independent) active rows: r = sum lambda_c a_c
+                    const double lx = (act & 1) ? r[0] * im : ((act & 2) ? -r[0] * im : 0.0);
+                    const double ly = (act & 4) ? r[1] * im : ((act & 8) ? -r[1] * im : 0.0);
+                    const double lc = (act & 16) ? (lx + ly - r[2]) : 0.0;
+                    double worst = -opt.mult_tol;
+                    int drop = 0;
+                    if ((act & 3) && lx < worst) { worst = lx; drop = act & 3; }
+                    if ((act & 12) && ly < worst) { worst = ly; drop = act & 12; }
+                    if ((act & 16) && lc < worst) { worst = lc; drop = 16; }
+                    if (drop) nact = act & ~drop;
+                }
+            }
+            W.act[f] = nact;
+            changed |= (nact != act);
+        }
+        if (!QR_ANY(changed)) { *ok = 1; ++round; break; }
+    }
+    return round;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fallback: interior point.  Rare, so it is written for clarity; its vectors are in global scratch.
+// ------------------------------------------------------------------------------------------
 template <int NT>
 QR_DEV double qr_red_max(const double* r, int cnt) {
     double m = 0.0;
@@ -278,7 +444,7 @@ QR_DEV void qr_build_kkt(QrQpWork& W) {
 // Interior-point phase.  On exit W.x, W.s, W.lam hold the final iterate.  Returns iterations used;
 // *converged tells whether the tolerance was met.
 template <int NT>
-QR_DEV int qr_ipm(QrQpWork& W, const qr_qp_options& opt, int* converged) {
+QR_DEV int qr_ipm(QrQpWork& W, const qr_qp_options& opt, double tol, int* converged) {
     const int nf = W.nf, n = 3 * nf, m = 5 * nf;
     const double mu_ = W.mu_;
     double* red = W.red;
@@ -330,15 +496,15 @@ QR_DEV int qr_ipm(QrQpWork& W, const qr_qp_options& opt, int* converged) {
         const double rdmax = qr_red_max<NT>(red, nf);
         const double gap = qr_red_sum<NT>(red + nf, nf) / (double)m;
         QR_SYNC();
-        if (rdmax < opt.ipm_tol * gscale && gap < opt.ipm_tol) { *converged = 1; break; }
+        if (rdmax < tol * gscale && gap < tol) { *converged = 1; break; }
 
         qr_build_kkt<NT>(W);
-        qr_blk_cholesky<NT>(W);
+        qr_blk_cholesky<NT>(W, nf);
 
         // predictor: K dxa = -(Hx + g)
         QR_FOR(i, n) W.wv[i] = -W.q[i];
         QR_SYNC();
-        qr_blk_solve<NT>(W, W.dxa);
+        qr_blk_solve<NT>(W, nf, W.dxa);
         QR_FOR(f, nf) {
             const double* dxf = W.dxa + 3 * f;
             double ds[5];
@@ -385,7 +551,7 @@ QR_DEV int qr_ipm(QrQpWork& W, const qr_qp_options& opt, int* converged) {
             for (int a = 0; a < 3; ++a) W.wv[3 * f + a] = -W.rd[3 * f + a] - at[a];
         }
         QR_SYNC();
-        qr_blk_solve<NT>(W, W.dx);
+        qr_blk_solve<NT>(W, nf, W.dx);
         QR_FOR(f, nf) {
             const double* dxf = W.dx + 3 * f;
             double ds[5];
@@ -413,166 +579,35 @@ QR_DEV int qr_ipm(QrQpWork& W, const qr_qp_options& opt, int* converged) {
         QR_FOR(c, m) W.lam[c] += ad * W.dl[c];
         QR_SYNC();
         QR_FOR(i, n) W.q[i] = qr_sym_matvec_row(W.Hs, W.x, nf, i) + W.g[i];
-        QR_FOR(f, nf) qr_foot_constraints(mu_, W.ubz[f], W.x + 3 * f, W.s + 5 * f);
+        QR_FOR(f, nf) {
+            qr_foot_constraints(mu_, W.ubz[f], W.x + 3 * f, W.s + 5 * f);
+            for (int c = 0; c < 5; ++c) W.s[5 * f + c] = qr_max(W.s[5 * f + c], 1e-30);
+        }
         QR_SYNC();
     }
     return it;
 }
 
-// Basis of one foot-step's active face: f = Z y + p.  act bits 0..3 = pyramid faces, bit 4 = cap.
-// Returns 1 when the active rows pin f = 0 (apex of the pyramid).
-QR_DEV int qr_foot_basis(int act, double mu_, double ub, double* Z /*3x3 row-major*/, double* p) {
-    const int a0 = act & 1, a1 = (act >> 1) & 1, a2 = (act >> 2) & 1, a3 = (act >> 3) & 1, cap = (act >> 4) & 1;
-    for (int e = 0; e < 9; ++e) Z[e] = 0.0;
-    p[0] = p[1] = p[2] = 0.0;
-    if (a0 + a1 == 2 || a2 + a3 == 2 || a0 + a1 + a2 + a3 >= 3) return 1;
-    const double im = 1.0 / mu_;
-    // active face mu_*fx + fz = 0 -> fx = -fz/mu_ ; face -mu_*fx + fz = 0 -> fx = +fz/mu_
-    const double kx = a0 ? -im : (a1 ? im : 0.0);
-    const double ky = a2 ? -im : (a3 ? im : 0.0);
-    const int fx_free = !(a0 | a1), fy_free = !(a2 | a3);
-    if (fx_free) Z[0] = 1.0;            // column 0: e_x
-    if (fy_free) Z[4] = 1.0;            // column 1: e_y
-    if (cap) {
-        p[0] = kx * ub; p[1] = ky * ub; p[2] = ub;
-    } else {
-        Z[2] = kx; Z[5] = ky; Z[8] = 1.0;  // column 2: (kx, ky, 1) * fz
-    }
-    return 0;
-}
-
-// Active-set polish.  Starts from the interior-point iterate (W.x, W.s, W.lam); result in W.xn.
-// Returns rounds used; *ok = 1 when the KKT conditions were verified.
-template <int NT>
-QR_DEV int qr_polish(QrQpWork& W, const qr_qp_options& opt, int* ok) {
-    const int nf = W.nf, n = 3 * nf, ntri = (nf * (nf + 1)) / 2;
-    const double mu_ = W.mu_;
-    QR_FOR(f, nf) {
-        int a = 0;
-        for (int c = 0; c < 5; ++c)
-            if (W.s[5 * f + c] < opt.act_kappa * W.lam[5 * f + c]) a |= (1 << c);
-        W.act[f] = a;
-    }
-    QR_SYNC();
-    *ok = 0;
-    int round = 0;
-    for (; round < opt.max_polish_rounds; ++round) {
-        QR_FOR(f, nf) { W.vert[f] = qr_foot_basis(W.act[f], mu_, W.ubz[f], W.Zs + 9 * f, W.ps + 3 * f); }
-        QR_SYNC();
-        // hp = H p + g  -> q
-        QR_FOR(i, n) W.q[i] = qr_sym_matvec_row(W.Hs, W.ps, nf, i) + W.g[i];
-        // reduced matrix Z_S' H_ST Z_T (+ identity on padded slots)
-        QR_FOR(idx, ntri) {
-            int S, T;
-            qr_tri_decode(idx, S, T);
-            const double* Hb = W.Hs + 9 * idx;
-            const double* ZS = W.Zs + 9 * S;
-            const double* ZT = W.Zs + 9 * T;
-            double tmp[9];
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    tmp[3 * r + c] = Hb[3 * r] * ZT[c] + Hb[3 * r + 1] * ZT[3 + c] + Hb[3 * r + 2] * ZT[6 + c];
-            double* Kb = W.K + 9 * idx;
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    Kb[3 * r + c] = ZS[r] * tmp[c] + ZS[3 + r] * tmp[3 + c] + ZS[6 + r] * tmp[6 + c];
-            if (S == T) {
-                // a padded slot has an all-zero basis column
-                for (int c = 0; c < 3; ++c)
-                    if (ZS[c] == 0.0 && ZS[3 + c] == 0.0 && ZS[6 + c] == 0.0) Kb[4 * c] = 1.0;
-            }
-        }
-        QR_SYNC();
-        QR_FOR(i, n) {
-            const int f = i / 3, c = i - 3 * f;
-            const double* Z = W.Zs + 9 * f;
-            W.wv[i] = -(Z[c] * W.q[3 * f] + Z[3 + c] * W.q[3 * f + 1] + Z[6 + c] * W.q[3 * f + 2]);
-        }
-        QR_SYNC();
-        qr_blk_cholesky<NT>(W);
-        qr_blk_solve<NT>(W, W.dx);
-        QR_FOR(i, n) {
-            const int f = i / 3, a = i - 3 * f;
-            const double* Z = W.Zs + 9 * f;
-            const double* y = W.dx + 3 * f;
-            W.xn[i] = Z[3 * a] * y[0] + Z[3 * a + 1] * y[1] + Z[3 * a + 2] * y[2] + W.ps[i];
-        }
-        QR_SYNC();
-        QR_FOR(i, n) W.q[i] = qr_sym_matvec_row(W.Hs, W.xn, nf, i) + W.g[i];
-        QR_SYNC();
-        // verify / correct the active sets
-        QR_FOR(f, nf) {
-            const double* r = W.q + 3 * f;
-            const int act = W.act[f];
-            int nact = act, changed = 0;
-            const double im = 1.0 / mu_;
-            if (W.vert[f]) {
-                // apex: the gradient must lie in the cone spanned by the four face normals
-                if (r[2] < (fabs(r[0]) + fabs(r[1])) * im - opt.mult_tol) {
-                    const double l0 = r[0] > 0.0 ? r[0] * im : 0.0, l1 = r[0] < 0.0 ? -r[0] * im : 0.0;
-                    const double l2 = r[1] > 0.0 ? r[1] * im : 0.0, l3 = r[1] < 0.0 ? -r[1] * im : 0.0;
-                    nact = (l0 > 0.0 ? 1 : 0) | (l1 > 0.0 ? 2 : 0) | (l2 > 0.0 ? 4 : 0) | (l3 > 0.0 ? 8 : 0);
-                    const int hasx = nact & 3, hasy = nact & 12;
-                    if (hasx && hasy) {
-                        // least-squares multipliers on the edge; drop the face that would pull inward
-                        const double sx = (nact & 1) ? 1.0 : -1.0, sy = (nact & 4) ? 1.0 : -1.0;
-                        const double b0 = sx * mu_ * r[0] + r[2], b1 = sy * mu_ * r[1] + r[2];
-                        const double dd = mu_ * mu_ + 1.0, det = dd * dd - 1.0;
-                        const double lx = (dd * b0 - b1) / det, ly = (dd * b1 - b0) / det;
-                        if (lx < 0.0 || ly < 0.0) {
-                            if (lx < ly) nact &= ~3; else nact &= ~12;
-                        }
-                    }
-                    changed = 1;
-                }
-            } else {
-                double c[5];
-                qr_foot_constraints(mu_, W.ubz[f], W.xn + 3 * f, c);
-                int viol = 0;
-                for (int k = 0; k < 5; ++k)
-                    if (!((act >> k) & 1) && c[k] < -opt.feas_tol) viol |= (1 << k);
-                if (viol) {
-                    nact = act | viol;
-                    changed = 1;
-                } else if (act) {
-                    // multipliers of the (independent) active rows: r = sum lambda_c a_c
-                    const double lx = (act & 1) ? r[0] * im : ((act & 2) ? -r[0] * im : 0.0);
-                    const double ly = (act & 4) ? r[1] * im : ((act & 8) ? -r[1] * im : 0.0);
-                    const double lc = (act & 16) ? (lx + ly - r[2]) : 0.0;
-                    double worst = -opt.mult_tol;
-                    int drop = 0;
-                    if ((act & 3) && lx < worst) { worst = lx; drop = act & 3; }
-                    if ((act & 12) && ly < worst) { worst = ly; drop = act & 12; }
-                    if ((act & 16) && lc < worst) { worst = lc; drop = 16; }
-                    if (drop) { nact = act & ~drop; changed = 1; }
-                }
-            }
-            W.act[f] = nact;
-            W.red[f] = changed ? 1.0 : 0.0;
-        }
-        QR_SYNC();
-        const double any = qr_red_max<NT>(W.red, nf);
-        QR_SYNC();
-        if (any == 0.0) { *ok = 1; ++round; break; }
-    }
-    return round;
-}
-
 // Full solve on a prepared workspace (Hs, g, ubz, mu_ set).  Result in W.xn (verified) or W.x.
 // Returns the per-instance status code of qr_gpu.h.
 template <int NT>
-QR_DEV int qr_qp_solve(QrQpWork& W, const qr_qp_options& opt, int* ipm_iters, int* polish_rounds,
+QR_DEV int qr_qp_solve(QrQpWork& W, const qr_qp_options& opt, int* ipm_iters, int* as_rounds,
                        const double** result) {
     int conv = 0, ok = 0;
-    *ipm_iters = 0; *polish_rounds = 0;
+    *ipm_iters = 0; *as_rounds = 0;
     *result = W.xn;
     if (W.nf == 0) return 0;
-    *ipm_iters = qr_ipm<NT>(W, opt, &conv);
-    *polish_rounds = qr_polish<NT>(W, opt, &ok);
-    if (!ok) { *result = W.x; return 1; }
-    return 0;
+    // 1. block active-set iteration from a cold start
+    *as_rounds = qr_active_set<NT>(W, opt, &ok, 1, opt.max_as_rounds);
+    if (ok) return 0;
+    // 2. fallback: interior point to identify the active set (tightening the tolerance once if the
+    //    verification still does not settle), then the same verification
+    double tol = opt.ipm_tol;
+    for (int attempt = 0; attempt < 2; ++attempt, tol *= 1e-2) {
+        *ipm_iters += qr_ipm<NT>(W, opt, tol, &conv);
+        *as_rounds += qr_active_set<NT>(W, opt, &ok, 0, opt.max_polish_rounds);
+        if (ok) return 0;
+    }
+    *result = W.x;
+    return 1;
 }

@@ -32,6 +32,13 @@ __device__ __forceinline__ void qr_team_sync() {
 #define QR_FOR(i, n) for (int i = threadIdx.x; i < (n); i += NT)
 #define QR_THREADS(t) for (int t = threadIdx.x, _qr_once = 1; _qr_once; _qr_once = 0)
 #define QR_SYNC() qr_team_sync<NT>()
+// barrier + "does any thread of the team hold a non-zero flag"
+template <int NT>
+__device__ __forceinline__ int qr_team_any(int v) {
+    if (NT <= 32) { int r = __any_sync(0xffffffffu, v); __syncwarp(); return r; }
+    return __syncthreads_or(v);
+}
+#define QR_ANY(v) qr_team_any<NT>(v)
 // float32 arithmetic that must not be contracted into FMAs (bit-exact condensing)
 #define QR_FMUL(a, b) __fmul_rn((a), (b))
 #define QR_FADD(a, b) __fadd_rn((a), (b))
@@ -42,6 +49,7 @@ __device__ __forceinline__ void qr_team_sync() {
 #define QR_FOR(i, n) for (int i = 0; i < (n); ++i)
 #define QR_THREADS(t) for (int t = 0; t < NT; ++t)
 #define QR_SYNC() ((void)0)
+#define QR_ANY(v) (v)
 #define QR_FMUL(a, b) ((a) * (b))
 #define QR_FADD(a, b) ((a) + (b))
 #define QR_FSUB(a, b) ((a) - (b))

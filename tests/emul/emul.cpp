@@ -11,9 +11,28 @@
 
 static qr_qp_options emul_default_options() {
     qr_qp_options o;
-    o.max_ipm_iter = 40; o.max_polish_rounds = 12; o.ipm_tol = 1e-5; o.act_kappa = 1e3;
+    o.max_as_rounds = 24; o.max_ipm_iter = 40; o.max_polish_rounds = 12; o.ipm_tol = 1e-7; o.act_kappa = 1e3;
     o.feas_tol = 1e-9; o.mult_tol = 1e-11;
     return o;
+}
+
+// Workspace of one emulated team, sized like the CUDA launch of the same size class would be.
+struct EmulTeam {
+    std::vector<unsigned char> smem;
+    std::vector<double> fallback;
+    QrMpcSmem S;
+    EmulTeam(int nfcap, int horizon) : smem(qr_mpc_smem_bytes(nfcap, horizon) + 64), fallback(qr_fallback_doubles(nfcap)) {
+        qr_mpc_carve(S, smem.data(), nfcap, horizon, fallback.data());
+        qr_mpc_init_tables<128>(S, nfcap);
+    }
+};
+
+static int class_cap_of(const float* gait, float fmax, int horizon) {
+    int nf = 0;
+    for (int k = 0; k < 4 * horizon; ++k) nf += (gait[k] * fmax > 0.f) ? 1 : 0;
+    int cap = ((nf + 7) / 8) * 8;
+    if (cap < 8) cap = 8;
+    return cap < 4 * horizon ? cap : 4 * horizon;
 }
 
 extern "C" int qr_emul_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_options* opt, int batch,
@@ -22,16 +41,18 @@ extern "C" int qr_emul_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_optio
                                        const float* gait, const float* mu_i, const float* fmax_i,
                                        float* grf_out, float* u_out, double* u_out_f64,
                                        int32_t* status_out, int32_t* iters_out) {
-    const int nfcap = 4 * P->horizon;
-    std::vector<unsigned char> smem(qr_mpc_smem_bytes(nfcap, P->horizon) + 64);
-    std::vector<double> Hs(9 * ((nfcap * (nfcap + 1)) / 2));
     QrMpcArgs A;
     memset(&A, 0, sizeof(A));
-    A.P = *P; A.opt = opt ? *opt : emul_default_options(); A.batch = batch; A.nfcap = nfcap;
+    A.P = *P; A.opt = opt ? *opt : emul_default_options(); A.batch = batch;
     A.p = p; A.v = v; A.quat = quat; A.w = w; A.r_feet = r_feet; A.rpy = rpy; A.traj = traj; A.gait = gait;
     A.mu_i = mu_i; A.fmax_i = fmax_i;
     A.grf_out = grf_out; A.u_out = u_out; A.x_out_f64 = u_out_f64; A.status_out = status_out; A.iters_out = iters_out;
-    for (int i = 0; i < batch; ++i) qr_mpc_solve_problem<128>(A, i, smem.data(), Hs.data());
+    for (int i = 0; i < batch; ++i) {
+        // same size classification as qr_mpc_classify_kernel
+        A.nfcap = class_cap_of(gait + (size_t)i * 4 * P->horizon, fmax_i ? fmax_i[i] : P->f_max, P->horizon);
+        EmulTeam team(A.nfcap, P->horizon);
+        qr_mpc_solve_problem<128>(A, i, team.S);
+    }
     return 0;
 }
 
@@ -39,29 +60,26 @@ extern "C" int qr_emul_mpc_condense_batch(const qr_mpc_params* P, int batch, con
                                           const float* quat, const float* w, const float* r_feet,
                                           const float* rpy, const float* traj, const float* gait,
                                           const float* fmax_i, float* H_out, float* g_out, float* ub_out) {
-    const int nfcap = 4 * P->horizon;
-    std::vector<unsigned char> smem(qr_mpc_smem_bytes(nfcap, P->horizon) + 64);
     QrMpcArgs A;
     memset(&A, 0, sizeof(A));
-    A.P = *P; A.opt = emul_default_options(); A.batch = batch; A.nfcap = nfcap;
+    A.P = *P; A.opt = emul_default_options(); A.batch = batch; A.nfcap = 4 * P->horizon;
     A.p = p; A.v = v; A.quat = quat; A.w = w; A.r_feet = r_feet; A.rpy = rpy; A.traj = traj; A.gait = gait;
     A.fmax_i = fmax_i; A.H_out = H_out; A.g_out = g_out; A.ub_out = ub_out;
-    for (int i = 0; i < batch; ++i) qr_mpc_condense_problem<128>(A, i, smem.data());
+    EmulTeam team(A.nfcap, P->horizon);
+    for (int i = 0; i < batch; ++i) qr_mpc_condense_problem<128>(A, i, team.S);
     return 0;
 }
 
 extern "C" int qr_emul_qp_solve_batch(int horizon, float mu, const qr_qp_options* opt, int batch,
                                       const float* H, const float* g, const float* ub, const float* mu_i,
                                       float* x_out, double* x_out_f64, int32_t* status_out, int32_t* iters_out) {
-    const int nfcap = 4 * horizon;
-    std::vector<unsigned char> smem(qr_mpc_smem_bytes(nfcap, horizon) + 64);
-    std::vector<double> Hs(9 * ((nfcap * (nfcap + 1)) / 2));
     QrMpcArgs A;
     memset(&A, 0, sizeof(A));
     A.P.horizon = horizon; A.P.mu = mu;
-    A.opt = opt ? *opt : emul_default_options(); A.batch = batch; A.nfcap = nfcap;
+    A.opt = opt ? *opt : emul_default_options(); A.batch = batch; A.nfcap = 4 * horizon;
     A.mu_i = mu_i; A.H_in = H; A.g_in = g; A.ub_in = ub;
     A.x_out = x_out; A.x_out_f64 = x_out_f64; A.status_out = status_out; A.iters_out = iters_out;
-    for (int i = 0; i < batch; ++i) qr_qp_solve_problem<128>(A, i, smem.data(), Hs.data());
+    EmulTeam team(A.nfcap, horizon);
+    for (int i = 0; i < batch; ++i) qr_qp_solve_problem<128>(A, i, team.S);
     return 0;
 }
