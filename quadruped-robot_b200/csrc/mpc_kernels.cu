@@ -453,3 +453,14 @@ extern "C" int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_o
     if (e != cudaSuccess) return fail(QR_ECUDA, "cudaStreamSynchronize", e);
     return QR_OK;
 }
+
+#ifdef QR_PROFILE
+// Debug builds only (-DQR_PROFILE): read and clear the per-phase cycle table.
+extern "C" int qr_gpu_debug_profile(unsigned long long* out64) {
+    cudaError_t e = cudaMemcpyFromSymbol(out64, qr_prof_table, 64 * sizeof(unsigned long long));
+    if (e != cudaSuccess) return QR_ECUDA;
+    unsigned long long zero[64] = {0};
+    cudaMemcpyToSymbol(qr_prof_table, zero, sizeof(zero));
+    return QR_OK;
+}
+#endif

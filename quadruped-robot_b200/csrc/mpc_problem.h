@@ -33,7 +33,7 @@ struct QrMpcArgs {
 };
 
 QR_HD int qr_ntri(int nf) { return (nf * (nf + 1)) / 2; }
-QR_HD size_t qr_fallback_doubles(int nfcap) { return (size_t)43 * nfcap + 8; }
+QR_HD size_t qr_fallback_doubles(int nfcap) { return (size_t)46 * nfcap + 8; }
 QR_HD size_t qr_kbytes(int nfcap) {
     size_t kb = (size_t)9 * qr_ntri(nfcap) * sizeof(double);
     return kb > sizeof(QrCondenseTables) ? kb : ((sizeof(QrCondenseTables) + 15) & ~(size_t)15);
@@ -43,7 +43,7 @@ QR_HD size_t qr_kbytes(int nfcap) {
 QR_HD size_t qr_mpc_smem_bytes(int nfcap, int horizon, bool hs_in_smem = true) {
     size_t bytes = hs_in_smem ? (size_t)9 * qr_ntri(nfcap) * sizeof(double) : 0;   // Hs
     bytes += qr_kbytes(nfcap);                                     // K (aliased by the condense tables)
-    bytes += (size_t)(9 + 9 + 7 * 3 + 1) * nfcap * sizeof(double) + 8 * sizeof(double);
+    bytes += (size_t)(9 + 9 + 6 * 3 + 1) * nfcap * sizeof(double) + 8 * sizeof(double);
     bytes += (size_t)(16 * horizon + 32) * sizeof(float);          // staged traj + gait + state rows
     bytes += (size_t)(3 * nfcap + (nfcap + 1) + 3 * nfcap + 2 * 4 * horizon + 8) * sizeof(int);
     bytes += (size_t)qr_ntri(nfcap) * sizeof(unsigned short);
@@ -74,7 +74,7 @@ QR_DEV void qr_mpc_carve(QrMpcSmem& S, unsigned char* base, int nfcap, int horiz
     W.Dinv = d; d += 9 * nfcap;
     W.zv = d; d += 9 * nfcap;
     W.ps = d; d += n; W.g = d; d += n; W.xn = d; d += n; W.q = d; d += n; W.wv = d; d += n;
-    W.yv = d; d += n; W.dx = d; d += n;
+    W.dx = d; d += n;
     W.ubz = d; d += nfcap;
     S.scal = d; d += 8;
     float* f = reinterpret_cast<float*>(d);
@@ -93,7 +93,7 @@ QR_DEV void qr_mpc_carve(QrMpcSmem& S, unsigned char* base, int nfcap, int horiz
     W.tri = reinterpret_cast<unsigned short*>(ip);
     // interior-point fallback vectors (global)
     double* gsc = fallback;
-    W.x = gsc; gsc += n; W.dxa = gsc; gsc += n; W.rd = gsc; gsc += n;
+    W.x = gsc; gsc += n; W.dxa = gsc; gsc += n; W.rd = gsc; gsc += n; W.yv = gsc; gsc += n;
     W.s = gsc; gsc += m; W.lam = gsc; gsc += m; W.dsa = gsc; gsc += m; W.dla = gsc; gsc += m;
     W.rc = gsc; gsc += m; W.dl = gsc; gsc += m;
     W.red = gsc;
@@ -220,17 +220,21 @@ QR_DEV int qr_result_status(QrMpcSmem& S, const double* x, int status) {
 // The fused path: SolveMPCKernel + GetMPCSolution for one instance.
 template <int NT>
 QR_DEV void qr_mpc_solve_problem(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
+    QR_PROF_DECL;
     qr_mpc_stage<NT>(A, prob, S);
+    QR_PROF(20);
     int status = S.misc[0];
     int it = 0, rounds = 0;
     const double* x = S.W.xn;
     if (status == 0) {
         qr_mpc_condense_to_work<NT>(A, S);
-        status = qr_qp_solve<NT>(S.W, A.opt, &it, &rounds, &x);
+        QR_PROF(21);
+        status = qr_qp_solve<NT>(S.W, A.opt, &it, &rounds, &x QR_PROF_PASS);
         status = qr_result_status<NT>(S, x, status);
     }
     qr_mpc_scatter<NT>(A, prob, S, x, status, it, rounds);
     QR_SYNC();
+    QR_PROF(22);
 }
 
 // Condense only: float32 H (n x n), g (n), ub (20h) exactly as SolveMPC hands them to qpOASES.
@@ -296,7 +300,8 @@ QR_DEV void qr_qp_solve_problem(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
         }
         QR_FOR(i, 3 * nf) S.W.g[i] = (double)g[3 * S.fs[i / 3] + i % 3];
         QR_SYNC();
-        status = qr_qp_solve<NT>(S.W, A.opt, &it, &rounds, &x);
+        QR_PROF_DECL;
+        status = qr_qp_solve<NT>(S.W, A.opt, &it, &rounds, &x QR_PROF_PASS);
         status = qr_result_status<NT>(S, x, status);
     }
     qr_mpc_scatter<NT>(A, prob, S, x, status, it, rounds);

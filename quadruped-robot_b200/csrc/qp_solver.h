@@ -35,14 +35,13 @@ struct QrQpWork {
     double mu_;         // 1/mu as the reference rounds it (float32 value)
     double* Hs;         // [9*ntri(cap)] shared: symmetric block-packed Hessian
     double* K;          // [9*ntri(cap)] shared: matrix under factorisation
-    double* Dinv;       // [9*cap]  inverse of the diagonal Cholesky blocks
+    double* Dinv;       // [9*cap]  inverses of the 3x3 pivot blocks of the LDL' factorisation
     double* zv;         // [9*cap]  basis vector (3 doubles) of every reduced variable
     double* ps;         // [3*cap]  offsets p of f = Z y + p
     double* g;          // [3*cap]
     double* xn;         // [3*cap]  current / final iterate
     double* q;          // [3*cap]  H p + g, later H x + g
-    double* wv;         // [3*cap]  solve work vector
-    double* yv;         // [3*cap]  forward-solve result
+    double* wv;         // [3*cap]  right-hand side / solve work vector
     double* dx;         // [3*cap]  solve result
     double* ubz;        // [cap]
     int* act;           // [cap] active-row bit masks (bit c = row c; bit 4 = cap)
@@ -52,7 +51,7 @@ struct QrQpWork {
     int* rfoot;         // [3*cap] foot-step of every reduced variable (-1: padding)
     unsigned short* tri;// [ntri(cap)] lower-triangular index decode table, (I << 8) | J
     // fallback-only vectors (global scratch)
-    double *x, *dxa, *rd;               // [3*cap]
+    double *x, *dxa, *rd, *yv;          // [3*cap]
     double *s, *lam, *dsa, *dla, *rc, *dl;  // [5*cap]
     double* red;                        // [4*cap]
 };
@@ -76,21 +75,384 @@ QR_DEV double qr_rsqrt(double v) {
 #endif
 }
 
-// Row i of (Hs * v), Hs symmetric block-packed.
+// Row i of (Hs * v), Hs symmetric block-packed.  Three independent accumulators keep the FMA
+// dependency chain a third as long.
 QR_DEV double qr_sym_matvec_row(const double* Hs, const double* v, int nf, int i) {
     const int S = i / 3, a = i - 3 * S;
-    double acc = 0.0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
     const double* row = Hs + qr_blk(S, 0) + 3 * a;
-    for (int T = 0; T <= S; ++T, row += 9)
-        acc += row[0] * v[3 * T] + row[1] * v[3 * T + 1] + row[2] * v[3 * T + 2];
+    for (int T = 0; T <= S; ++T, row += 9) {
+        a0 += row[0] * v[3 * T];
+        a1 += row[1] * v[3 * T + 1];
+        a2 += row[2] * v[3 * T + 2];
+    }
     const double* col = Hs + qr_blk(S + 1, S) + a;
     for (int T = S + 1; T < nf; ++T) {
-        acc += col[0] * v[3 * T] + col[3] * v[3 * T + 1] + col[6] * v[3 * T + 2];
+        a0 += col[0] * v[3 * T];
+        a1 += col[3] * v[3 * T + 1];
+        a2 += col[6] * v[3 * T + 2];
         col += 9 * (T + 1);
+    }
+    return (a0 + a1) + a2;
+}
+
+// Row i of (Hs * p) where p is non-zero only on foot-steps whose cap row is active (act bit 4).
+QR_DEV double qr_sym_matvec_row_capped(const double* Hs, const double* p, const int* act, int nf, int i) {
+    const int S = i / 3, a = i - 3 * S;
+    double acc = 0.0;
+    for (int T = 0; T < nf; ++T) {
+        if (!(act[T] & 16)) continue;
+        if (T <= S) {
+            const double* row = Hs + qr_blk(S, T) + 3 * a;
+            acc += row[0] * p[3 * T] + row[1] * p[3 * T + 1] + row[2] * p[3 * T + 2];
+        } else {
+            const double* col = Hs + qr_blk(T, S) + a;
+            acc += col[0] * p[3 * T] + col[3] * p[3 * T + 1] + col[6] * p[3 * T + 2];
+        }
     }
     return acc;
 }
 
+// Inverse of a symmetric positive definite 3x3 block [a b c; b d e; c e f] by its adjugate: one
+// reciprocal and no square root, so the dependent chain is short (cofactors -> determinant -> 1/det).
+// Written as a full symmetric 3x3 (row-major) to o[0..8].  A non-positive determinant is clamped
+// (the caller's verification and the final finiteness check catch a breakdown).
+QR_DEV void qr_inv3_sym(double a, double b, double c, double d, double e, double f, double* o) {
+    const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
+    const double c11 = a * f - c * c, c12 = b * c - a * e, c22 = a * d - b * b;
+    double det = a * c00 + b * c01 + c * c02;
+    if (!(det > 1e-300)) det = 1e-300;
+    const double r = 1.0 / det;
+    o[0] = c00 * r; o[1] = c01 * r; o[2] = c02 * r;
+    o[3] = o[1];    o[4] = c11 * r; o[5] = c12 * r;
+    o[6] = o[2];    o[7] = o[5];    o[8] = c22 * r;
+}
+
+// Block LDL' factorisation K = L D L' of the leading nb x nb blocks (3x3 pivot blocks, no pivoting:
+// K is symmetric positive definite), fused with the forward substitution of the right-hand side
+// W.wv when with_rhs != 0.
+//
+// One barrier per block column.  In step Kc every thread owning a trailing tile (I,J), I >= J > Kc,
+// reads the UNSCALED column tiles W_IK, W_JK and the pivot inverse Dinv_K and applies
+//     A_IJ -= (W_IK Dinv_K) W_JK'
+// (the scaling by Dinv_K is redone per tile: redundant flops are cheaper than a second barrier).
+// The thread that produces the next pivot block (Kc+1,Kc+1) inverts it on the spot and publishes
+// Dinv_{K+1}; that block is never written back.  The right-hand side is treated as one more block
+// row: y_J -= W_JK (Dinv_K y_K).  On exit: off-diagonal tiles hold W = L D (unscaled columns),
+// W.Dinv the pivot inverses, and W.wv = L^{-1} rhs.
+template <int NT>
+QR_DEV void qr_ldl_factor(QrQpWork& W, int nb, int with_rhs QR_PROF_ARG) {
+    double* K = W.K;
+    double* y = W.wv;
+    QR_THREADS(t) {
+        if (t == 0) {
+            const double* D = K;
+            qr_inv3_sym(D[0], D[3], D[6], D[4], D[7], D[8], W.Dinv);
+        }
+    }
+    QR_SYNC();
+    for (int Kc = 0; Kc < nb; ++Kc) {
+        const int nrem = nb - Kc - 1;
+        const int ntile = (nrem * (nrem + 1)) / 2;
+        const double* Di = W.Dinv + 9 * Kc;
+        QR_FOR(idx, ntile + (with_rhs ? nrem : 0)) {
+            const double d0 = Di[0], d1 = Di[1], d2 = Di[2], d4 = Di[4], d5 = Di[5], d8 = Di[8];
+            if (idx < ntile) {
+                const int code = W.tri[idx];
+                const int I = (code >> 8) + Kc + 1, J = (code & 255) + Kc + 1;
+                const int rowI = (I * (I + 1)) / 2;
+                const double* wi = K + 9 * (rowI + Kc);
+                const double* wj = K + qr_blk(J, Kc);
+                double* a = K + 9 * (rowI + J);
+                double m[9], t[9], r[9];
+#pragma unroll
+                for (int e = 0; e < 9; ++e) { m[e] = wj[e]; r[e] = a[e]; }
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const double w0 = wi[3 * q], w1 = wi[3 * q + 1], w2 = wi[3 * q + 2];
+                    t[3 * q] = w0 * d0 + w1 * d1 + w2 * d2;
+                    t[3 * q + 1] = w0 * d1 + w1 * d4 + w2 * d5;
+                    t[3 * q + 2] = w0 * d2 + w1 * d5 + w2 * d8;
+                }
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        r[3 * q + c] -= t[3 * q] * m[3 * c] + t[3 * q + 1] * m[3 * c + 1] + t[3 * q + 2] * m[3 * c + 2];
+                if (I == Kc + 1 && J == Kc + 1) {
+                    qr_inv3_sym(r[0], r[3], r[6], r[4], r[7], r[8], W.Dinv + 9 * (Kc + 1));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) a[e] = r[e];
+                }
+            } else {
+                const int J = Kc + 1 + (idx - ntile);
+                const double y0 = y[3 * Kc], y1 = y[3 * Kc + 1], y2 = y[3 * Kc + 2];
+                const double t0 = d0 * y0 + d1 * y1 + d2 * y2;
+                const double t1 = d1 * y0 + d4 * y1 + d5 * y2;
+                const double t2 = d2 * y0 + d5 * y1 + d8 * y2;
+                const double* wj = K + qr_blk(J, Kc);
+                y[3 * J] -= wj[0] * t0 + wj[1] * t1 + wj[2] * t2;
+                y[3 * J + 1] -= wj[3] * t0 + wj[4] * t1 + wj[5] * t2;
+                y[3 * J + 2] -= wj[6] * t0 + wj[7] * t1 + wj[8] * t2;
+            }
+        }
+        QR_SYNC();
+        QR_PROF(11);
+    }
+}
+
+// Stand-alone forward substitution W.wv <- L^{-1} W.wv for a further right-hand side (the
+// interior-point fallback solves twice per factorisation).
+template <int NT>
+QR_DEV void qr_ldl_forward(QrQpWork& W, int nb QR_PROF_ARG) {
+    const double* K = W.K;
+    double* y = W.wv;
+    for (int Kc = 0; Kc + 1 < nb; ++Kc) {
+        const double* Di = W.Dinv + 9 * Kc;
+        QR_FOR(idx, 3 * (nb - Kc - 1)) {
+            const int I = Kc + 1 + idx / 3, a = idx % 3;
+            const double y0 = y[3 * Kc], y1 = y[3 * Kc + 1], y2 = y[3 * Kc + 2];
+            const double t0 = Di[0] * y0 + Di[1] * y1 + Di[2] * y2;
+            const double t1 = Di[3] * y0 + Di[4] * y1 + Di[5] * y2;
+            const double t2 = Di[6] * y0 + Di[7] * y1 + Di[8] * y2;
+            const double* r = K + qr_blk(I, Kc) + 3 * a;
+            y[3 * I + a] -= r[0] * t0 + r[1] * t1 + r[2] * t2;
+        }
+        QR_SYNC();
+    }
+    QR_PROF(12);
+}
+
+// Backward substitution: out = L'^{-1} D^{-1} W.wv, i.e. x_K = Dinv_K (y_K - sum_{I>K} W_IK' x_I).
+// In place on W.wv (a step reads block Kc and updates blocks J < Kc).
+template <int NT>
+QR_DEV void qr_ldl_backward(QrQpWork& W, int nb, double* out QR_PROF_ARG) {
+    const double* K = W.K;
+    double* y = W.wv;
+    for (int Kc = nb - 1; Kc >= 0; --Kc) {
+        const double* Di = W.Dinv + 9 * Kc;
+        QR_FOR(idx, 3 * (Kc + 1)) {
+            const int J = idx / 3, a = idx % 3;
+            const double b0 = y[3 * Kc], b1 = y[3 * Kc + 1], b2 = y[3 * Kc + 2];
+            const double x0 = Di[0] * b0 + Di[1] * b1 + Di[2] * b2;
+            const double x1 = Di[3] * b0 + Di[4] * b1 + Di[5] * b2;
+            const double x2 = Di[6] * b0 + Di[7] * b1 + Di[8] * b2;
+            if (J == Kc) {
+                out[3 * Kc + a] = (a == 0 ? x0 : (a == 1 ? x1 : x2));
+            } else {
+                const double* blk = K + qr_blk(Kc, J);   // W_KJ, column a of it
+                y[3 * J + a] -= blk[a] * x0 + blk[3 + a] * x1 + blk[6 + a] * x2;
+            }
+        }
+        QR_SYNC();
+    }
+    QR_PROF(13);
+}
+
+// Constraint values of one foot-step: c0..c3 pyramid faces, c4 = ub - fz.
+QR_DEV void qr_foot_constraints(double mu_, double ub, const double* f, double* c) {
+    c[0] = mu_ * f[0] + f[2];
+    c[1] = -mu_ * f[0] + f[2];
+    c[2] = mu_ * f[1] + f[2];
+    c[3] = -mu_ * f[1] + f[2];
+    c[4] = ub - f[2];
+}
+// A_f' t for one foot-step (t has 5 entries).
+QR_DEV void qr_foot_At(double mu_, const double* t, double* o) {
+    o[0] = mu_ * (t[0] - t[1]);
+    o[1] = mu_ * (t[2] - t[3]);
+    o[2] = t[0] + t[1] + t[2] + t[3] - t[4];
+}
+
+// Basis of one foot-step's active face: f = Z y + p with the d free directions in the first d
+// columns of Z (3x3 row-major).  act bits 0..3 = pyramid faces, bit 4 = cap.
+// Returns d, or -1 when the active rows pin f = 0 (apex of the pyramid).
+QR_DEV int qr_foot_basis(int act, double mu_, double ub, double* Z, double* p) {
+    const int a0 = act & 1, a1 = (act >> 1) & 1, a2 = (act >> 2) & 1, a3 = (act >> 3) & 1, cap = (act >> 4) & 1;
+    for (int e = 0; e < 9; ++e) Z[e] = 0.0;
+    p[0] = p[1] = p[2] = 0.0;
+    if (a0 + a1 == 2 || a2 + a3 == 2 || a0 + a1 + a2 + a3 >= 3) return -1;
+    const double im = 1.0 / mu_;
+    // active face mu_*fx + fz = 0 -> fx = -fz/mu_ ; face -mu_*fx + fz = 0 -> fx = +fz/mu_
+    const double kx = a0 ? -im : (a1 ? im : 0.0);
+    const double ky = a2 ? -im : (a3 ? im : 0.0);
+    int d = 0;
+    if (!(a0 | a1)) { Z[d] = 1.0; ++d; }                 // e_x
+    if (!(a2 | a3)) { Z[3 + d] = 1.0; ++d; }             // e_y
+    if (cap) {
+        p[0] = kx * ub; p[1] = ky * ub; p[2] = ub;
+    } else {
+        Z[d] = kx; Z[3 + d] = ky; Z[6 + d] = 1.0; ++d;   // (kx, ky, 1) * fz
+    }
+    return d;
+}
+
+// Block active-set iteration (see the header comment).  cold = 1: start with no row active;
+// cold = 0: start from the active set the interior-point iterate (W.s, W.lam) suggests.
+// Result in W.xn.  Returns rounds used; *ok = 1 when the KKT conditions were verified.
+template <int NT>
+QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int cold, int max_rounds QR_PROF_ARG) {
+    const int nf = W.nf, n = 3 * nf;
+    const double mu_ = W.mu_;
+    const double im = 1.0 / mu_;
+    QR_FOR(f, nf) {
+        int a = 0;
+        if (!cold)
+            for (int c = 0; c < 5; ++c)
+                if (W.s[5 * f + c] < opt.act_kappa * W.lam[5 * f + c]) a |= (1 << c);
+        W.act[f] = a;
+    }
+    QR_SYNC();
+    *ok = 0;
+    int round = 0;
+    for (; round < max_rounds; ++round) {
+        // ---- bases of the current guess; K is free here, its head is scratch for the 3x3 bases
+        double* Zfull = W.K;
+        QR_FOR(f, nf) {
+            const int d = qr_foot_basis(W.act[f], mu_, W.ubz[f], Zfull + 9 * f, W.ps + 3 * f);
+            W.vert[f] = d < 0;
+            W.flag[f] = d < 0 ? 0 : d;
+        }
+        QR_SYNC();
+        QR_PROF(1);
+        // ---- pack the free directions: every foot-step finds its offset (sum of d_g, g < f) itself
+        QR_FOR(f, nf) {
+            int off = 0;
+            for (int gidx = 0; gidx < f; ++gidx) off += W.flag[gidx];
+            const int d = W.flag[f];
+            W.foff[f] = off;
+            for (int c = 0; c < d; ++c) {
+                W.rfoot[off + c] = f;
+                W.zv[3 * (off + c)] = Zfull[9 * f + c];
+                W.zv[3 * (off + c) + 1] = Zfull[9 * f + 3 + c];
+                W.zv[3 * (off + c) + 2] = Zfull[9 * f + 6 + c];
+            }
+            if (f == nf - 1) {
+                const int tot = off + d;
+                W.foff[nf] = tot;
+                for (int r = tot; r < 3 * ((tot + 2) / 3); ++r) W.rfoot[r] = -1;
+            }
+        }
+        // hp = H p + g  -> q   (p is non-zero only where the cap row is active)
+        QR_FOR(i, n) W.q[i] = qr_sym_matvec_row_capped(W.Hs, W.ps, W.act, nf, i) + W.g[i];
+        QR_SYNC();
+        QR_PROF(3);
+        const int nred = W.foff[nf];
+        const int nbr = (nred + 2) / 3;
+        // ---- reduced matrix (Z'HZ), padded to a multiple of 3 with identity; right-hand side
+        QR_FOR(idx, 9 * ((nbr * (nbr + 1)) / 2)) {
+            const int b = idx / 9, e = idx - 9 * b;
+            const int code = W.tri[b];
+            const int r1 = 3 * (code >> 8) + e / 3, r2 = 3 * (code & 255) + e % 3;
+            const int f1 = W.rfoot[r1], f2 = W.rfoot[r2];
+            double val;
+            if (f1 < 0 || f2 < 0) {
+                val = (r1 == r2) ? 1.0 : 0.0;
+            } else {
+                const double* z1 = W.zv + 3 * r1;
+                const double* z2 = W.zv + 3 * r2;
+                double t0, t1, t2;   // t = H_{f1 f2} z2
+                if (f1 >= f2) {
+                    const double* Hb = W.Hs + qr_blk(f1, f2);
+                    t0 = Hb[0] * z2[0] + Hb[1] * z2[1] + Hb[2] * z2[2];
+                    t1 = Hb[3] * z2[0] + Hb[4] * z2[1] + Hb[5] * z2[2];
+                    t2 = Hb[6] * z2[0] + Hb[7] * z2[1] + Hb[8] * z2[2];
+                } else {
+                    const double* Hb = W.Hs + qr_blk(f2, f1);
+                    t0 = Hb[0] * z2[0] + Hb[3] * z2[1] + Hb[6] * z2[2];
+                    t1 = Hb[1] * z2[0] + Hb[4] * z2[1] + Hb[7] * z2[2];
+                    t2 = Hb[2] * z2[0] + Hb[5] * z2[1] + Hb[8] * z2[2];
+                }
+                val = z1[0] * t0 + z1[1] * t1 + z1[2] * t2;
+            }
+            W.K[idx] = val;
+        }
+        QR_FOR(r, 3 * nbr) {
+            const int f = W.rfoot[r];
+            W.wv[r] = f < 0 ? 0.0
+                            : -(W.zv[3 * r] * W.q[3 * f] + W.zv[3 * r + 1] * W.q[3 * f + 1] + W.zv[3 * r + 2] * W.q[3 * f + 2]);
+        }
+        QR_SYNC();
+        QR_PROF(4);
+        qr_ldl_factor<NT>(W, nbr, 1 QR_PROF_PASS);
+        qr_ldl_backward<NT>(W, nbr, W.dx QR_PROF_PASS);
+        QR_FOR(f, nf) {
+            double x0 = W.ps[3 * f], x1 = W.ps[3 * f + 1], x2 = W.ps[3 * f + 2];
+            const int off = W.foff[f], d = W.flag[f];
+            for (int c = 0; c < d; ++c) {
+                const double y = W.dx[off + c];
+                x0 += y * W.zv[3 * (off + c)];
+                x1 += y * W.zv[3 * (off + c) + 1];
+                x2 += y * W.zv[3 * (off + c) + 2];
+            }
+            W.xn[3 * f] = x0; W.xn[3 * f + 1] = x1; W.xn[3 * f + 2] = x2;
+        }
+        QR_SYNC();
+        QR_PROF(5);
+        QR_FOR(i, n) W.q[i] = qr_sym_matvec_row(W.Hs, W.xn, nf, i) + W.g[i];
+        QR_SYNC();
+        QR_PROF(6);
+        // ---- verify / correct the active sets
+        int changed = 0;
+        QR_FOR(f, nf) {
+            const double* r = W.q + 3 * f;
+            const int act = W.act[f];
+            int nact = act;
+            if (W.vert[f]) {
+                // apex: the gradient must lie in the cone spanned by the four face normals
+                if (r[2] < (fabs(r[0]) + fabs(r[1])) * im - opt.mult_tol) {
+                    const double l0 = r[0] > 0.0 ? r[0] * im : 0.0, l1 = r[0] < 0.0 ? -r[0] * im : 0.0;
+                    const double l2 = r[1] > 0.0 ? r[1] * im : 0.0, l3 = r[1] < 0.0 ? -r[1] * im : 0.0;
+                    nact = (l0 > 0.0 ? 1 : 0) | (l1 > 0.0 ? 2 : 0) | (l2 > 0.0 ? 4 : 0) | (l3 > 0.0 ? 8 : 0);
+                    const int hasx = nact & 3, hasy = nact & 12;
+                    if (hasx && hasy) {
+                        // least-squares multipliers on the edge; drop the face that would pull inward
+                        const double sx = (nact & 1) ? 1.0 : -1.0, sy = (nact & 4) ? 1.0 : -1.0;
+                        const double b0 = sx * mu_ * r[0] + r[2], b1 = sy * mu_ * r[1] + r[2];
+                        const double dd = mu_ * mu_ + 1.0, det = dd * dd - 1.0;
+                        const double lx = (dd * b0 - b1) / det, ly = (dd * b1 - b0) / det;
+                        if (lx < 0.0 || ly < 0.0) {
+                            if (lx < ly) nact &= ~3; else nact &= ~12;
+                        }
+                    }
+                }
+            } else {
+                double c[5];
+                qr_foot_constraints(mu_, W.ubz[f], W.xn + 3 * f, c);
+                int viol = 0;
+                for (int k = 0; k < 5; ++k)
+                    if (!((act >> k) & 1) && c[k] < -opt.feas_tol) viol |= (1 << k);
+                if (viol) {
+                    nact = act | viol;
+                } else if (act) {
+                    // multipliers of the (independent) active rows: r = sum lambda_c a_c
+                    const double lx = (act & 1) ? r[0] * im : ((act & 2) ? -r[0] * im : 0.0);
+                    const double ly = (act & 4) ? r[1] * im : ((act & 8) ? -r[1] * im : 0.0);
+                    const double lc = (act & 16) ? (lx + ly - r[2]) : 0.0;
+                    double worst = -opt.mult_tol;
+                    int drop = 0;
+                    if ((act & 3) && lx < worst) { worst = lx; drop = act & 3; }
+                    if ((act & 12) && ly < worst) { worst = ly; drop = act & 12; }
+                    if ((act & 16) && lc < worst) { worst = lc; drop = 16; }
+                    if (drop) nact = act & ~drop;
+                }
+            }
+            W.act[f] = nact;
+            changed |= (nact != act);
+        }
+        const int any_changed = QR_ANY(changed);
+        QR_PROF(7);
+        if (!any_changed) { *ok = 1; ++round; break; }
+    }
+    return round;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fallback linear algebra: blocked Cholesky with triangular solves against the 3x3 diagonal factors
+// (backward stable; the explicit pivot inverses of qr_ldl_factor lose too many digits on the
+// interior-point matrices, whose barrier terms span ten orders of magnitude).
+// ------------------------------------------------------------------------------------------
 // Cholesky factor of a 3x3 SPD block given by its lower part, as the reciprocal pivots and the
 // off-diagonal entries (all a thread needs for its own forward substitution).
 struct QrChol3 {
@@ -112,7 +474,7 @@ QR_DEV QrChol3 qr_chol3(const double* D) {
 // (that is all the solves need).  Non-positive pivots are clamped (the caller's verification or the
 // final finiteness check catches a breakdown).
 template <int NT>
-QR_DEV void qr_blk_cholesky(QrQpWork& W, int nb) {
+QR_DEV void qr_blk_cholesky(QrQpWork& W, int nb) {  // interior-point fallback only
     double* K = W.K;
     for (int Kc = 0; Kc < nb; ++Kc) {
         // panel: every row of the block column solves against the (redundantly factorised) diagonal block
@@ -207,198 +569,6 @@ QR_DEV void qr_blk_solve(QrQpWork& W, int nb, double* out) {
     }
 }
 
-// Constraint values of one foot-step: c0..c3 pyramid faces, c4 = ub - fz.
-QR_DEV void qr_foot_constraints(double mu_, double ub, const double* f, double* c) {
-    c[0] = mu_ * f[0] + f[2];
-    c[1] = -mu_ * f[0] + f[2];
-    c[2] = mu_ * f[1] + f[2];
-    c[3] = -mu_ * f[1] + f[2];
-    c[4] = ub - f[2];
-}
-// A_f' t for one foot-step (t has 5 entries).
-QR_DEV void qr_foot_At(double mu_, const double* t, double* o) {
-    o[0] = mu_ * (t[0] - t[1]);
-    o[1] = mu_ * (t[2] - t[3]);
-    o[2] = t[0] + t[1] + t[2] + t[3] - t[4];
-}
-
-// Basis of one foot-step's active face: f = Z y + p with the d free directions in the first d
-// columns of Z (3x3 row-major).  act bits 0..3 = pyramid faces, bit 4 = cap.
-// Returns d, or -1 when the active rows pin f = 0 (apex of the pyramid).
-QR_DEV int qr_foot_basis(int act, double mu_, double ub, double* Z, double* p) {
-    const int a0 = act & 1, a1 = (act >> 1) & 1, a2 = (act >> 2) & 1, a3 = (act >> 3) & 1, cap = (act >> 4) & 1;
-    for (int e = 0; e < 9; ++e) Z[e] = 0.0;
-    p[0] = p[1] = p[2] = 0.0;
-    if (a0 + a1 == 2 || a2 + a3 == 2 || a0 + a1 + a2 + a3 >= 3) return -1;
-    const double im = 1.0 / mu_;
-    // active face mu_*fx + fz = 0 -> fx = -fz/mu_ ; face -mu_*fx + fz = 0 -> fx = +fz/mu_
-    const double kx = a0 ? -im : (a1 ? im : 0.0);
-    const double ky = a2 ? -im : (a3 ? im : 0.0);
-    int d = 0;
-    if (!(a0 | a1)) { Z[d] = 1.0; ++d; }                 // e_x
-    if (!(a2 | a3)) { Z[3 + d] = 1.0; ++d; }             // e_y
-    if (cap) {
-        p[0] = kx * ub; p[1] = ky * ub; p[2] = ub;
-    } else {
-        Z[d] = kx; Z[3 + d] = ky; Z[6 + d] = 1.0; ++d;   // (kx, ky, 1) * fz
-    }
-    return d;
-}
-
-// Block active-set iteration (see the header comment).  cold = 1: start with no row active;
-// cold = 0: start from the active set the interior-point iterate (W.s, W.lam) suggests.
-// Result in W.xn.  Returns rounds used; *ok = 1 when the KKT conditions were verified.
-template <int NT>
-QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int cold, int max_rounds) {
-    const int nf = W.nf, n = 3 * nf;
-    const double mu_ = W.mu_;
-    const double im = 1.0 / mu_;
-    QR_FOR(f, nf) {
-        int a = 0;
-        if (!cold)
-            for (int c = 0; c < 5; ++c)
-                if (W.s[5 * f + c] < opt.act_kappa * W.lam[5 * f + c]) a |= (1 << c);
-        W.act[f] = a;
-    }
-    QR_SYNC();
-    *ok = 0;
-    int round = 0;
-    for (; round < max_rounds; ++round) {
-        // ---- bases of the current guess; K is free here, its head is scratch for the 3x3 bases
-        double* Zfull = W.K;
-        QR_FOR(f, nf) {
-            const int d = qr_foot_basis(W.act[f], mu_, W.ubz[f], Zfull + 9 * f, W.ps + 3 * f);
-            W.vert[f] = d < 0;
-            W.flag[f] = d < 0 ? 0 : d;
-        }
-        QR_SYNC();
-        // ---- pack the free directions: prefix sum of d_f (serial, nf <= 64) and the z vectors
-        QR_THREADS(t) {
-            if (t == 0) {
-                int off = 0;
-                for (int f = 0; f < nf; ++f) { W.foff[f] = off; off += W.flag[f]; }
-                W.foff[nf] = off;
-            }
-        }
-        QR_SYNC();
-        const int nred = W.foff[nf];
-        const int nbr = (nred + 2) / 3;
-        QR_FOR(f, nf) {
-            const int off = W.foff[f], d = W.flag[f];
-            for (int c = 0; c < d; ++c) {
-                W.rfoot[off + c] = f;
-                W.zv[3 * (off + c)] = Zfull[9 * f + c];
-                W.zv[3 * (off + c) + 1] = Zfull[9 * f + 3 + c];
-                W.zv[3 * (off + c) + 2] = Zfull[9 * f + 6 + c];
-            }
-        }
-        QR_FOR(r, 3 * nbr - nred) W.rfoot[nred + r] = -1;
-        // hp = H p + g  -> q   (reads ps only)
-        QR_FOR(i, n) W.q[i] = qr_sym_matvec_row(W.Hs, W.ps, nf, i) + W.g[i];
-        QR_SYNC();
-        // ---- reduced matrix (Z'HZ), padded to a multiple of 3 with identity; right-hand side
-        QR_FOR(idx, 9 * ((nbr * (nbr + 1)) / 2)) {
-            const int b = idx / 9, e = idx - 9 * b;
-            const int code = W.tri[b];
-            const int r1 = 3 * (code >> 8) + e / 3, r2 = 3 * (code & 255) + e % 3;
-            const int f1 = W.rfoot[r1], f2 = W.rfoot[r2];
-            double val;
-            if (f1 < 0 || f2 < 0) {
-                val = (r1 == r2) ? 1.0 : 0.0;
-            } else {
-                const double* z1 = W.zv + 3 * r1;
-                const double* z2 = W.zv + 3 * r2;
-                double t0, t1, t2;   // t = H_{f1 f2} z2
-                if (f1 >= f2) {
-                    const double* Hb = W.Hs + qr_blk(f1, f2);
-                    t0 = Hb[0] * z2[0] + Hb[1] * z2[1] + Hb[2] * z2[2];
-                    t1 = Hb[3] * z2[0] + Hb[4] * z2[1] + Hb[5] * z2[2];
-                    t2 = Hb[6] * z2[0] + Hb[7] * z2[1] + Hb[8] * z2[2];
-                } else {
-                    const double* Hb = W.Hs + qr_blk(f2, f1);
-                    t0 = Hb[0] * z2[0] + Hb[3] * z2[1] + Hb[6] * z2[2];
-                    t1 = Hb[1] * z2[0] + Hb[4] * z2[1] + Hb[7] * z2[2];
-                    t2 = Hb[2] * z2[0] + Hb[5] * z2[1] + Hb[8] * z2[2];
-                }
-                val = z1[0] * t0 + z1[1] * t1 + z1[2] * t2;
-            }
-            W.K[idx] = val;
-        }
-        QR_FOR(r, 3 * nbr) {
-            const int f = W.rfoot[r];
-            W.wv[r] = f < 0 ? 0.0
-                            : -(W.zv[3 * r] * W.q[3 * f] + W.zv[3 * r + 1] * W.q[3 * f + 1] + W.zv[3 * r + 2] * W.q[3 * f + 2]);
-        }
-        QR_SYNC();
-        qr_blk_cholesky<NT>(W, nbr);
-        qr_blk_solve<NT>(W, nbr, W.dx);
-        QR_FOR(f, nf) {
-            double x0 = W.ps[3 * f], x1 = W.ps[3 * f + 1], x2 = W.ps[3 * f + 2];
-            const int off = W.foff[f], d = W.flag[f];
-            for (int c = 0; c < d; ++c) {
-                const double y = W.dx[off + c];
-                x0 += y * W.zv[3 * (off + c)];
-                x1 += y * W.zv[3 * (off + c) + 1];
-                x2 += y * W.zv[3 * (off + c) + 2];
-            }
-            W.xn[3 * f] = x0; W.xn[3 * f + 1] = x1; W.xn[3 * f + 2] = x2;
-        }
-        QR_SYNC();
-        QR_FOR(i, n) W.q[i] = qr_sym_matvec_row(W.Hs, W.xn, nf, i) + W.g[i];
-        QR_SYNC();
-        // ---- verify / correct the active sets
-        int changed = 0;
-        QR_FOR(f, nf) {
-            const double* r = W.q + 3 * f;
-            const int act = W.act[f];
-            int nact = act;
-            if (W.vert[f]) {
-                // apex: the gradient must lie in the cone spanned by the four face normals
-                if (r[2] < (fabs(r[0]) + fabs(r[1])) * im - opt.mult_tol) {
-                    const double l0 = r[0] > 0.0 ? r[0] * im : 0.0, l1 = r[0] < 0.0 ? -r[0] * im : 0.0;
-                    const double l2 = r[1] > 0.0 ? r[1] * im : 0.0, l3 = r[1] < 0.0 ? -r[1] * im : 0.0;
-                    nact = (l0 > 0.0 ? 1 : 0) | (l1 > 0.0 ? 2 : 0) | (l2 > 0.0 ? 4 : 0) | (l3 > 0.0 ? 8 : 0);
-                    const int hasx = nact & 3, hasy = nact & 12;
-                    if (hasx && hasy) {
-                        // least-squares multipliers on the edge; drop the face that would pull inward
-                        const double sx = (nact & 1) ? 1.0 : -1.0, sy = (nact & 4) ? 1.0 : -1.0;
-                        const double b0 = sx * mu_ * r[0] + r[2], b1 = sy * mu_ * r[1] + r[2];
-                        const double dd = mu_ * mu_ + 1.0, det = dd * dd - 1.0;
-                        const double lx = (dd * b0 - b1) / det, ly = (dd * b1 - b0) / det;
-                        if (lx < 0.0 || ly < 0.0) {
-                            if (lx < ly) nact &= ~3; else nact &= ~12;
-                        }
-                    }
-                }
-            } else {
-                double c[5];
-                qr_foot_constraints(mu_, W.ubz[f], W.xn + 3 * f, c);
-                int viol = 0;
-                for (int k = 0; k < 5; ++k)
-                    if (!((act >> k) & 1) && c[k] < -opt.feas_tol) viol |= (1 << k);
-                if (viol) {
-                    nact = act | viol;
-                } else if (act) {
-                    // multipliers of the (independent) active rows: r = sum lambda_c a_c
-                    const double lx = (act & 1) ? r[0] * im : ((act & 2) ? -r[0] * im : 0.0);
-                    const double ly = (act & 4) ? r[1] * im : ((act & 8) ? -r[1] * im : 0.0);
-                    const double lc = (act & 16) ? (lx + ly - r[2]) : 0.0;
-                    double worst = -opt.mult_tol;
-                    int drop = 0;
-                    if ((act & 3) && lx < worst) { worst = lx; drop = act & 3; }
-                    if ((act & 12) && ly < worst) { worst = ly; drop = act & 12; }
-                    if ((act & 16) && lc < worst) { worst = lc; drop = 16; }
-                    if (drop) nact = act & ~drop;
-                }
-            }
-            W.act[f] = nact;
-            changed |= (nact != act);
-        }
-        if (!QR_ANY(changed)) { *ok = 1; ++round; break; }
-    }
-    return round;
-}
-
 // ------------------------------------------------------------------------------------------
 // Fallback: interior point.  Rare, so it is written for clarity; its vectors are in global scratch.
 // ------------------------------------------------------------------------------------------
@@ -444,7 +614,7 @@ QR_DEV void qr_build_kkt(QrQpWork& W) {
 // Interior-point phase.  On exit W.x, W.s, W.lam hold the final iterate.  Returns iterations used;
 // *converged tells whether the tolerance was met.
 template <int NT>
-QR_DEV int qr_ipm(QrQpWork& W, const qr_qp_options& opt, double tol, int* converged) {
+QR_DEV int qr_ipm(QrQpWork& W, const qr_qp_options& opt, double tol, int* converged QR_PROF_ARG) {
     const int nf = W.nf, n = 3 * nf, m = 5 * nf;
     const double mu_ = W.mu_;
     double* red = W.red;
@@ -500,7 +670,6 @@ QR_DEV int qr_ipm(QrQpWork& W, const qr_qp_options& opt, double tol, int* conver
 
         qr_build_kkt<NT>(W);
         qr_blk_cholesky<NT>(W, nf);
-
         // predictor: K dxa = -(Hx + g)
         QR_FOR(i, n) W.wv[i] = -W.q[i];
         QR_SYNC();
@@ -592,20 +761,20 @@ QR_DEV int qr_ipm(QrQpWork& W, const qr_qp_options& opt, double tol, int* conver
 // Returns the per-instance status code of qr_gpu.h.
 template <int NT>
 QR_DEV int qr_qp_solve(QrQpWork& W, const qr_qp_options& opt, int* ipm_iters, int* as_rounds,
-                       const double** result) {
+                       const double** result QR_PROF_ARG) {
     int conv = 0, ok = 0;
     *ipm_iters = 0; *as_rounds = 0;
     *result = W.xn;
     if (W.nf == 0) return 0;
     // 1. block active-set iteration from a cold start
-    *as_rounds = qr_active_set<NT>(W, opt, &ok, 1, opt.max_as_rounds);
+    *as_rounds = qr_active_set<NT>(W, opt, &ok, 1, opt.max_as_rounds QR_PROF_PASS);
     if (ok) return 0;
     // 2. fallback: interior point to identify the active set (tightening the tolerance once if the
     //    verification still does not settle), then the same verification
     double tol = opt.ipm_tol;
     for (int attempt = 0; attempt < 2; ++attempt, tol *= 1e-2) {
-        *ipm_iters += qr_ipm<NT>(W, opt, tol, &conv);
-        *as_rounds += qr_active_set<NT>(W, opt, &ok, 0, opt.max_polish_rounds);
+        *ipm_iters += qr_ipm<NT>(W, opt, tol, &conv QR_PROF_PASS);
+        *as_rounds += qr_active_set<NT>(W, opt, &ok, 0, opt.max_polish_rounds QR_PROF_PASS);
         if (ok) return 0;
     }
     *result = W.x;

@@ -56,6 +56,30 @@ __device__ __forceinline__ int qr_team_any(int v) {
 #define QR_FDIV(a, b) ((a) / (b))
 #endif
 
+// Optional per-phase cycle profile (debug builds only: -DQR_PROFILE).  Thread 0 of every team adds the
+// cycles since the previous mark to a global table; marks sit right after barriers.
+#if defined(QR_PROFILE) && defined(__CUDACC__)
+__device__ unsigned long long qr_prof_table[64];
+#endif
+#if defined(QR_PROFILE) && defined(__CUDA_ARCH__)
+__device__ __forceinline__ void qr_prof_mark(int tag, long long& last) {
+    if (threadIdx.x == 0) {
+        const long long now = clock64();
+        atomicAdd(&qr_prof_table[tag], (unsigned long long)(now - last));
+        last = now;
+    }
+}
+#define QR_PROF_DECL long long qr_prof_last = clock64()
+#define QR_PROF(tag) qr_prof_mark(tag, qr_prof_last)
+#define QR_PROF_ARG , long long& qr_prof_last
+#define QR_PROF_PASS , qr_prof_last
+#else
+#define QR_PROF_DECL
+#define QR_PROF(tag) ((void)0)
+#define QR_PROF_ARG
+#define QR_PROF_PASS
+#endif
+
 QR_DEV double qr_min(double a, double b) { return a < b ? a : b; }
 QR_DEV double qr_max(double a, double b) { return a > b ? a : b; }
 QR_DEV int qr_imin(int a, int b) { return a < b ? a : b; }

@@ -146,8 +146,11 @@ def test_full_size_properties(gpu, oracle, pkg):
         stat, feas = oracle.kkt_certificate(H, g, A, np.zeros(20 * h), ub.astype(float), r["u"][i].astype(float))
         # float32 output rounding (<= 8e-6 N) times ||H|| bounds the visible stationarity residual
         assert stat < 5e-7 and feas < 1e-4, (i, stat, feas)
-    # iteration statistics stay in the expected band
-    assert r["iters"][:, 0].max() <= 40 and r["iters"][:, 1].max() <= 12
+    # iteration statistics stay in the expected band: a handful of active-set rounds, and the
+    # interior-point fallback on well under 1 % of the instances
+    assert r["iters"][:, 1].max() <= 24 + 2 * 12
+    assert (r["iters"][:, 0] > 0).mean() < 0.01
+    assert r["iters"][:, 1].mean() < 9
 
 
 def test_edge_cases(gpu, pkg):
