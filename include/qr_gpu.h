@@ -120,6 +120,58 @@ int qr_gpu_qp_solve_batch(int horizon, float mu, const qr_qp_options* opt, int b
                           float* x_out, double* x_out_f64, int32_t* status_out, int32_t* iters_out,
                           void* cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Whole-body control
+ * ------------------------------------------------------------------------------------------------- */
+
+/* Geometry the reference reads from the robot's yaml in BuildDynamicModel
+ * (src/robots/qr_robot_a1_sim.cpp:176-186; config/<robot>/*.yaml: body_size, hip_l, upper_l, lower_l).
+ * Link masses, inertias and joint locations are the constants hard-coded there. */
+typedef struct {
+    float body_size[3];
+    float hip_len, upper_len, lower_len;
+} qr_wbc_model;
+
+/* qr_gpu_wbc_solve_batch -- replaces one recomputing tick of qrWbcLocomotionController<float>::Run
+ * (src/controllers/wbc/qr_wbc_locomotion_controller.cpp:108-219): FloatingBaseModel::setState /
+ * contactJacobians / massMatrix / generalizedGravityForce / generalizedCoriolisForce
+ * (src/dynamics/floating_base_model.cpp:469-806), the task / contact updates (task_set/*.cpp,
+ * qr_single_contact.cpp), qrMultitaskProjection::FindConfiguration (qr_multitask_projection.cpp:38-106)
+ * and qrWholeBodyImpulseCtrl::GetModelRes / MakeTorque (qr_wholebody_impulse_ctrl.cpp:50-126) including
+ * the QuadProg++ solve (:113), for `batch` independent robots.  Rows:
+ *   state   [batch][37]  quat(w,x,y,z) pos(3) body twist (omega_body, v_body) q(12) qd(12)
+ *                        (FBModelState as filled by UpdateModel :141-157)
+ *   cmd     [batch][66]  qrWbcCtrlData (controllers/qr_state_dataflow.h:133-193): pBody_des vBody_des
+ *                        aBody_des pBody_RPY_des vBody_Ori_des (3 each), pFoot_des[4] vFoot_des[4]
+ *                        aFoot_des[4] Fr_des[4] (12 each), then the vBody_Ori_des of the PREVIOUS call (3):
+ *                        the orientation task's velocity error uses it (qr_task_body_orientation.cpp:68)
+ *   contact [batch][4]   contact_state (int32 0/1)
+ *   tau_out [batch][12]  joint torques jointTorqueCmd (the reference applies those of stance legs, :205-219)
+ *   fr_out  [batch][12] or NULL   optimal reaction forces (qrWBICExtraData::optimalFr scattered per leg)
+ *   qdes_out, qddes_out [batch][12] or NULL   desiredJPos / desiredJVel of the kinematic WBC
+ *   status_out [batch] or NULL   0 ok, 1 QP fallback iterate, 3 non-finite
+ * The every-second-call gating of Run and the stance-only write-back stay with the caller.
+ * Device pointers, asynchronous on the stream.  Arithmetic is float64 (the reference: float32 with a
+ * float64 QP). */
+int qr_gpu_wbc_solve_batch(const qr_wbc_model* model, int batch, const float* state, const float* cmd,
+                           const int32_t* contact, float* tau_out, float* fr_out, float* qdes_out,
+                           float* qddes_out, int32_t* status_out, void* cuda_stream);
+
+/* Same with float64 outputs and the intermediate model quantities (tests): dbg [batch][630] =
+ * H(324) G(18) Cqd(18) Jc of the four feet (216) Jcdqd(12) pFoot(12) vFoot(12) qddot(18); any may be NULL. */
+int qr_gpu_wbc_solve_batch_f64(const qr_wbc_model* model, int batch, const float* state, const float* cmd,
+                               const int32_t* contact, double* tau_out, double* fr_out, double* qdes_out,
+                               double* qddes_out, double* dbg_out, int32_t* status_out, void* cuda_stream);
+
+/* qr_gpu_swing_parabola_batch -- replaces SwingFootTrajectory::GenerateTrajectoryPoint in MPC mode
+ * (src/controllers/qr_foot_trajectory_generator.cpp:322-343 -> qrFootParabolaPatternGenerator :188-215 ->
+ * qrQuadraticSpline::getPoint, src/utils/qr_geometry.cpp:157-190): start,end [batch][3], height, phase
+ * [batch], phase_module 0/1; pos_out [batch][3] (velocity / acceleration are identically zero in the
+ * reference), valid_out [batch] (0 when the generator rejects the phase). */
+int qr_gpu_swing_parabola_batch(int batch, const float* start, const float* end, const float* height,
+                                const float* phase, int phase_module, float* pos_out, int32_t* valid_out,
+                                void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

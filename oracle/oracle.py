@@ -219,3 +219,45 @@ def kkt_certificate(H, g, A, lb, ub, x, act_tol: float = 1e-7):
         return float(np.abs(grad).max()), feas
     y, _ = nnls(M, grad, maxiter=50 * M.shape[1])
     return float(np.abs(M @ y - grad).max()), feas
+
+
+# ---------------------------------------------------------------------------------------------
+# Whole-body control oracle
+# ---------------------------------------------------------------------------------------------
+class WbcModel(C.Structure):
+    _fields_ = [("body_size", C.c_float * 3), ("hip_len", C.c_float), ("upper_len", C.c_float), ("lower_len", C.c_float)]
+
+
+def wbc_model_of(robot) -> WbcModel:
+    m = WbcModel()
+    m.body_size[:] = robot.body_size
+    m.hip_len, m.upper_len, m.lower_len = robot.hip_len, robot.upper_len, robot.lower_len
+    return m
+
+
+def wbc_step(model: WbcModel, state, cmd, contact, precision: str = "f64"):
+    """One WBC tick for one robot.  Returns dict(tau, fr, qdes, qddes, H, G, C, Jc, Jcdqd, pGC, vGC, qdd, rc)."""
+    dt = np.float64 if precision == "f64" else np.float32
+    ptr = _dp if precision == "f64" else _fp
+    tau, fr, qdes, qddes = (np.zeros(12, dt) for _ in range(4))
+    dbg = np.zeros(324 + 18 + 18 + 216 + 12 + 12 + 12 + 18, dt)
+    state = np.ascontiguousarray(state, np.float32)
+    cmd = np.ascontiguousarray(cmd, np.float32)
+    contact = np.ascontiguousarray(contact, np.int32)
+    fn = lib().qro_wbc_step_f64 if precision == "f64" else lib().qro_wbc_step_f32
+    rc = fn(C.byref(model), _fp(state), _fp(cmd), _ip(contact), ptr(tau), ptr(fr), ptr(qdes), ptr(qddes), ptr(dbg))
+    o = 0
+    out = dict(tau=tau, fr=fr, qdes=qdes, qddes=qddes, rc=rc)
+    for name, n, shape in (("H", 324, (18, 18)), ("G", 18, (18,)), ("C", 18, (18,)), ("Jc", 216, (4, 3, 18)),
+                           ("Jcdqd", 12, (4, 3)), ("pGC", 12, (4, 3)), ("vGC", 12, (4, 3)), ("qdd", 18, (18,))):
+        out[name] = dbg[o:o + n].reshape(shape).copy()
+        o += n
+    return out
+
+
+def swing_parabola(start, end, height, t, phase_module=False):
+    start = np.ascontiguousarray(start, np.float32)
+    end = np.ascontiguousarray(end, np.float32)
+    pos = np.zeros(3, np.float32)
+    ok = lib().qro_swing_parabola(_fp(start), _fp(end), C.c_float(height), C.c_float(t), int(phase_module), _fp(pos))
+    return pos, bool(ok)

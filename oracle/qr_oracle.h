@@ -90,6 +90,34 @@ double qro_mpc_time_batch(const qro_mpc_params* P, int count, const float* p, co
                           const float* traj, const float* gait, int nWSR, double* x_all,
                           double* lat, int* capped);
 
+/* ------------------------------------------------------------------------------------------------
+ * Whole-body control step (wbc_oracle.cpp): floating-base dynamics + tasks/contacts + kinematic WBC +
+ * WBIC with the reference's QuadProg++.  One recomputing tick of qrWbcLocomotionController<float>::Run.
+ *   model       link lengths / body box of the robot (A1: a1_sim.yaml, Lite3: lite3_sim/robot.yaml); the
+ *               masses/inertias/locations hard-coded in BuildDynamicModel are inside the oracle
+ *   state[37]   quat(w,x,y,z) pos(3) body twist(6: omega_body, v_body) q(12) qd(12)
+ *   cmd[66]     pBody_des vBody_des aBody_des pBody_RPY_des vBody_Ori_des (3 each) pFoot_des[4] vFoot_des[4]
+ *               aFoot_des[4] Fr_des[4] (12 each) prev vBody_Ori_des (3: the desiredVel the orientation task
+ *               kept from the previous call, qr_task_body_orientation.cpp:68)
+ *   contact[4]  contact_state
+ * Outputs: tau[12] (all legs; the reference applies the stance ones), fr[12] optimal reaction forces
+ * (zeros for swing legs), qdes[12] / qddes[12] from the kinematic WBC; dbg (may be NULL):
+ * H(324) G(18) C(18) Jc of the 4 feet (216) Jcdqd(12) pGC(12) vGC(12) qddot(18).
+ * _f32 computes in float like the reference, _f64 the same algorithm in double.  Returns 1 when
+ * QuadProg++ reports infeasibility (the reference ignores it). */
+typedef struct {
+    float body_size[3];
+    float hip_len, upper_len, lower_len;
+} qro_wbc_model;
+int qro_wbc_step_f32(const qro_wbc_model* model, const float* state, const float* cmd, const int* contact,
+                     float* tau, float* fr, float* qdes, float* qddes, float* dbg);
+int qro_wbc_step_f64(const qro_wbc_model* model, const float* state, const float* cmd, const int* contact,
+                     double* tau, double* fr, double* qdes, double* qddes, double* dbg);
+
+/* Swing-foot position in MPC mode (parabola generator); returns 0 when the phase is rejected. */
+int qro_swing_parabola(const float* start, const float* end, float height, float t, int phase_module,
+                       float* pos);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,7 +35,20 @@ def default_options() -> QpOptions:
 
 EXPORTS = ["qr_gpu_init", "qr_gpu_shutdown", "qr_gpu_last_error", "qr_gpu_mpc_occupancy",
            "qr_gpu_mpc_solve_batch", "qr_gpu_mpc_solve_batch_host", "qr_gpu_mpc_condense_batch",
-           "qr_gpu_qp_solve_batch"]
+           "qr_gpu_qp_solve_batch", "qr_gpu_wbc_solve_batch", "qr_gpu_wbc_solve_batch_f64",
+           "qr_gpu_swing_parabola_batch"]
+
+
+class WbcModel(C.Structure):
+    """qr_wbc_model (include/qr_gpu.h)."""
+    _fields_ = [("body_size", C.c_float * 3), ("hip_len", C.c_float), ("upper_len", C.c_float), ("lower_len", C.c_float)]
+
+
+def wbc_model_of(robot) -> WbcModel:
+    m = WbcModel()
+    m.body_size[:] = robot.body_size
+    m.hip_len, m.upper_len, m.lower_len = robot.hip_len, robot.upper_len, robot.lower_len
+    return m
 
 
 def lib():
@@ -136,3 +149,24 @@ def occupancy(horizon: int, stance_footsteps: int):
     _check(lib().qr_gpu_mpc_occupancy(horizon, stance_footsteps, C.byref(sm), C.byref(per), C.byref(thr), C.byref(smem)),
            "qr_gpu_mpc_occupancy")
     return dict(sm_count=sm.value, ctas_per_sm=per.value, threads_per_cta=thr.value, smem_bytes=smem.value)
+
+
+def wbc_solve_batch_device(model: WbcModel, state, cmd, contact, tau, stream_ptr: int, fr=None, qdes=None, qddes=None,
+                           status=None):
+    """float32 outputs (torch CUDA tensors); asynchronous on the stream."""
+    rc = lib().qr_gpu_wbc_solve_batch(C.byref(model), state.shape[0], _vp(state), _vp(cmd), _vp(contact), _vp(tau),
+                                      _vp(fr), _vp(qdes), _vp(qddes), _vp(status), C.c_void_p(stream_ptr))
+    _check(rc, "qr_gpu_wbc_solve_batch")
+
+
+def wbc_solve_batch_device_f64(model: WbcModel, state, cmd, contact, tau, stream_ptr: int, fr=None, qdes=None,
+                               qddes=None, dbg=None, status=None):
+    rc = lib().qr_gpu_wbc_solve_batch_f64(C.byref(model), state.shape[0], _vp(state), _vp(cmd), _vp(contact), _vp(tau),
+                                          _vp(fr), _vp(qdes), _vp(qddes), _vp(dbg), _vp(status), C.c_void_p(stream_ptr))
+    _check(rc, "qr_gpu_wbc_solve_batch_f64")
+
+
+def swing_parabola_batch_device(start, end, height, phase, phase_module: bool, pos, valid, stream_ptr: int):
+    rc = lib().qr_gpu_swing_parabola_batch(start.shape[0], _vp(start), _vp(end), _vp(height), _vp(phase),
+                                           int(phase_module), _vp(pos), _vp(valid), C.c_void_p(stream_ptr))
+    _check(rc, "qr_gpu_swing_parabola_batch")

@@ -464,3 +464,112 @@ extern "C" int qr_gpu_debug_profile(unsigned long long* out64) {
     return QR_OK;
 }
 #endif
+
+// ==================================================================================================
+// Whole-body control and swing-foot kernels
+// ==================================================================================================
+#include "wbc_problem.h"
+
+namespace {
+
+constexpr int QR_WBC_NT = 32;   // one warp per robot
+
+__global__ void __launch_bounds__(QR_WBC_NT) qr_wbc_kernel(const QrWbcArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NT = QR_WBC_NT;
+    QrWbcWork W;
+    qr_wbc_carve(W, smem);
+    qr_wbc_init_tables<NT>(W);
+    for (int prob = blockIdx.x; prob < A.batch; prob += gridDim.x) qr_wbc_problem<NT>(A, prob, W);
+}
+
+__global__ void qr_swing_parabola_kernel(int batch, const float* start, const float* end, const float* height,
+                                         const float* phase, int phase_module, float* pos, int32_t* valid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    float o[3] = {0.f, 0.f, 0.f};
+    const int ok = qr_swing_parabola(start + 3 * (size_t)i, end + 3 * (size_t)i, height[i], phase[i], phase_module, o);
+    pos[3 * (size_t)i] = o[0]; pos[3 * (size_t)i + 1] = o[1]; pos[3 * (size_t)i + 2] = o[2];
+    if (valid) valid[i] = ok;
+}
+
+QrWbcModelDev* g_wbc_model_dev = nullptr;
+qr_wbc_model g_wbc_model_host;
+bool g_wbc_model_valid = false;
+
+int wbc_launch(const qr_wbc_model* model, int batch, const float* state, const float* cmd, const int32_t* contact,
+               QrWbcArgs& A, void* cuda_stream) {
+    if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
+    if (!model || batch < 0) return fail(QR_EINVAL, "null model or negative batch");
+    if (batch == 0) return QR_OK;
+    if (!state || !cmd || !contact) return fail(QR_EINVAL, "null input pointer");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (!g_wbc_model_dev) {
+        cudaError_t e = cudaMalloc(&g_wbc_model_dev, sizeof(QrWbcModelDev));
+        if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMalloc(wbc model)", e);
+    }
+    if (!g_wbc_model_valid || memcmp(&g_wbc_model_host, model, sizeof(*model)) != 0) {
+        QrWbcModelDev host;
+        qr_wbc_host::build(model, &host);
+        // synchronous upload (the constants change only when the robot model changes)
+        cudaError_t e = cudaMemcpy(g_wbc_model_dev, &host, sizeof(host), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpy(wbc model)", e);
+        g_wbc_model_host = *model;
+        g_wbc_model_valid = true;
+    }
+    const size_t smem = qr_wbc_smem_bytes();
+    cudaError_t e = cudaFuncSetAttribute(qr_wbc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(QR_ECUDA, "cudaFuncSetAttribute(wbc)", e);
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qr_wbc_kernel, QR_WBC_NT, smem);
+    if (e != cudaSuccess) return fail(QR_ECUDA, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(wbc)", e);
+    int grid = g_ctx.sm_count * (occ < 1 ? 1 : occ);
+    if (grid > batch) grid = batch;
+    A.model = g_wbc_model_dev;
+    A.opt = default_options();
+    A.batch = batch;
+    A.state = state; A.cmd = cmd; A.contact = contact;
+    qr_wbc_kernel<<<grid, QR_WBC_NT, smem, st>>>(A);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_wbc_kernel", e);
+    return QR_OK;
+}
+
+}  // namespace
+
+extern "C" int qr_gpu_wbc_solve_batch(const qr_wbc_model* model, int batch, const float* state, const float* cmd,
+                                      const int32_t* contact, float* tau_out, float* fr_out, float* qdes_out,
+                                      float* qddes_out, int32_t* status_out, void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (batch > 0 && !tau_out) return fail(QR_EINVAL, "null output pointer");
+    QrWbcArgs A;
+    memset(&A, 0, sizeof(A));
+    A.tau32 = tau_out; A.fr32 = fr_out; A.qdes32 = qdes_out; A.qddes32 = qddes_out; A.status = status_out;
+    return wbc_launch(model, batch, state, cmd, contact, A, cuda_stream);
+}
+
+extern "C" int qr_gpu_wbc_solve_batch_f64(const qr_wbc_model* model, int batch, const float* state, const float* cmd,
+                                          const int32_t* contact, double* tau_out, double* fr_out, double* qdes_out,
+                                          double* qddes_out, double* dbg_out, int32_t* status_out, void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (batch > 0 && !tau_out) return fail(QR_EINVAL, "null output pointer");
+    QrWbcArgs A;
+    memset(&A, 0, sizeof(A));
+    A.tau64 = tau_out; A.fr64 = fr_out; A.qdes64 = qdes_out; A.qddes64 = qddes_out; A.dbg = dbg_out; A.status = status_out;
+    return wbc_launch(model, batch, state, cmd, contact, A, cuda_stream);
+}
+
+extern "C" int qr_gpu_swing_parabola_batch(int batch, const float* start, const float* end, const float* height,
+                                           const float* phase, int phase_module, float* pos_out, int32_t* valid_out,
+                                           void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
+    if (batch < 0) return fail(QR_EINVAL, "negative batch");
+    if (batch == 0) return QR_OK;
+    if (!start || !end || !height || !phase || !pos_out) return fail(QR_EINVAL, "null pointer");
+    qr_swing_parabola_kernel<<<(batch + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(batch, start, end, height, phase,
+                                                                                       phase_module, pos_out, valid_out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_swing_parabola_kernel", e);
+    return QR_OK;
+}

@@ -44,6 +44,8 @@ __device__ __forceinline__ int qr_team_any(int v) {
 #define QR_FADD(a, b) __fadd_rn((a), (b))
 #define QR_FSUB(a, b) __fsub_rn((a), (b))
 #define QR_FDIV(a, b) __fdiv_rn((a), (b))
+#define QR_DMUL(a, b) __dmul_rn((a), (b))
+#define QR_DADD(a, b) __dadd_rn((a), (b))
 #else
 // ---- host emulation (tests only) ---------------------------------------------------------
 #define QR_FOR(i, n) for (int i = 0; i < (n); ++i)
@@ -54,6 +56,8 @@ __device__ __forceinline__ int qr_team_any(int v) {
 #define QR_FADD(a, b) ((a) + (b))
 #define QR_FSUB(a, b) ((a) - (b))
 #define QR_FDIV(a, b) ((a) / (b))
+#define QR_DMUL(a, b) ((a) * (b))
+#define QR_DADD(a, b) ((a) + (b))
 #endif
 
 // Optional per-phase cycle profile (debug builds only: -DQR_PROFILE).  Thread 0 of every team adds the

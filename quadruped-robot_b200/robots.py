@@ -25,6 +25,12 @@ class RobotMPC:
     body_height: float
     mu: float = 0.45
     alpha: float = 4e-6
+    # whole-body model geometry (config/<robot>/*.yaml: body_size, hip_l, upper_l, lower_l); the link
+    # masses / inertias are the A1 numbers hard-coded in BuildDynamicModel for every robot
+    body_size: Tuple[float, float, float] = (0.267, 0.194, 0.114)
+    hip_len: float = 0.08505
+    upper_len: float = 0.2
+    lower_len: float = 0.2
 
     @property
     def f_max(self) -> float:
@@ -43,7 +49,7 @@ LITE3 = RobotMPC(
     weights=(20, 20, 10, 40, 40, 150, 0.5, 1, 1, 5, 5, 10),
     com_offset=(-0.012, -0.000, 0.0),
     hip_positions=((0.1745, -0.15, 0), (0.1745, 0.15, 0), (-0.1745, -0.15, 0), (-0.1745, 0.15, 0)),
-    body_height=0.27)
+    body_height=0.27, body_size=(0.349, 0.124, 0.15), hip_len=0.0985, upper_len=0.20, lower_len=0.20)
 
 ALIENGO = RobotMPC(
     name="aliengo", mass=20.0, inertia=(0.24, 0.80, 1.0),

@@ -145,3 +145,80 @@ def make_mpc_batch(robot: str | RobotMPC = "a1", horizon: int = 10, dt: float = 
     out["horizon"] = h
     out["dt"] = dt
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Whole-body-control workloads
+# ------------------------------------------------------------------------------------------------
+def _rx(a):
+    c, s = np.cos(a), np.sin(a)
+    o, z = np.ones_like(a), np.zeros_like(a)
+    return np.stack([np.stack([o, z, z], -1), np.stack([z, c, -s], -1), np.stack([z, s, c], -1)], -2)
+
+
+def _ry(a):
+    c, s = np.cos(a), np.sin(a)
+    o, z = np.ones_like(a), np.zeros_like(a)
+    return np.stack([np.stack([c, z, s], -1), np.stack([z, o, z], -1), np.stack([-s, z, c], -1)], -2)
+
+
+def foot_positions_world(rb: RobotMPC, rpy: np.ndarray, pos: np.ndarray, q: np.ndarray) -> np.ndarray:
+    """Analytic forward kinematics of the four feet [B,4,3] for the tree of BuildDynamicModel
+    (src/robots/qr_robot_a1_sim.cpp:176-345): abad about x at (+-0.1805, +-0.047, 0), hip about y at
+    (0, +-hip_len, 0), knee about y at (0, 0, -upper_len), foot at (0, -+0.004, -lower_len)."""
+    B = q.shape[0]
+    R = _rot_zyx(rpy)
+    out = np.empty((B, 4, 3))
+    for leg in range(4):
+        sx = 1.0 if leg < 2 else -1.0
+        sy = -1.0 if leg % 2 == 0 else 1.0
+        t_abad = np.array([sx * 0.1805, sy * 0.047, 0.0])
+        t_hip = np.array([0.0, sy * rb.hip_len, 0.0])
+        t_knee = np.array([0.0, 0.0, -rb.upper_len])
+        t_foot = np.array([0.0, -sy * 0.004, -rb.lower_len])
+        q0, q1, q2 = q[:, 3 * leg], q[:, 3 * leg + 1], q[:, 3 * leg + 2]
+        p = t_knee + np.einsum("bij,j->bi", _ry(q2), t_foot)
+        p = t_hip + np.einsum("bij,bj->bi", _ry(q1), p)
+        p = t_abad + np.einsum("bij,bj->bi", _rx(q0), p)
+        out[:, leg] = pos + np.einsum("bij,bj->bi", R, p)
+    return out
+
+
+def make_wbc_batch(robot: str | RobotMPC = "lite3", batch: int = 1024, seed: int = 0) -> dict:
+    """Randomised WBC inputs: state[B,37] (quat pos twist q qd), cmd[B,66] (the qrWbcCtrlData fields +
+    the previous orientation-velocity command), contact[B,4] int32.  Trot-like contact patterns
+    (a diagonal pair, three or four feet in stance)."""
+    rb = ROBOTS[robot] if isinstance(robot, str) else robot
+    rng = np.random.default_rng(seed)
+    B = batch
+    U = rng.uniform
+    rpy = np.stack([U(-0.1, 0.1, B), U(-0.1, 0.1, B), U(-np.pi, np.pi, B)], 1)
+    pos = np.stack([U(-1, 1, B), U(-1, 1, B), rb.body_height + U(-0.02, 0.02, B)], 1)
+    twist = np.concatenate([U(-0.5, 0.5, (B, 3)), np.stack([U(-0.5, 1.0, B), U(-0.3, 0.3, B), U(-0.1, 0.1, B)], 1)], 1)
+    stand = np.tile(np.array([0.0, 0.9, -1.8]), 4)
+    q = stand[None, :] + U(-0.2, 0.2, (B, 12))
+    qd = U(-1, 1, (B, 12))
+    state = np.concatenate([_quat_from_rpy(rpy), pos, twist, q, qd], 1)
+    patterns = np.array([[1, 0, 0, 1], [0, 1, 1, 0], [1, 1, 1, 1], [1, 1, 0, 1], [0, 1, 1, 1], [1, 0, 1, 1], [1, 1, 1, 0]], np.int32)
+    contact = patterns[rng.integers(0, len(patterns), B)]
+    feet = foot_positions_world(rb, rpy, pos, q)
+    nc = contact.sum(1)
+    fr = np.zeros((B, 4, 3))
+    fr[..., 0] = U(-10, 10, (B, 4))
+    fr[..., 1] = U(-10, 10, (B, 4))
+    fr[..., 2] = (rb.mass * 9.81 / nc)[:, None] + U(-10, 10, (B, 4))
+    fr *= contact[..., None]
+    cmd = np.concatenate([
+        pos + U(-0.03, 0.03, (B, 3)),                                    # pBody_des
+        np.stack([U(-0.5, 1.0, B), U(-0.3, 0.3, B), np.zeros(B)], 1),    # vBody_des
+        np.zeros((B, 3)),                                                # aBody_des
+        rpy + np.stack([U(-0.05, 0.05, B), U(-0.05, 0.05, B), U(-0.1, 0.1, B)], 1),  # pBody_RPY_des
+        np.stack([np.zeros(B), np.zeros(B), U(-0.5, 0.5, B)], 1),        # vBody_Ori_des
+        (feet + U(-0.1, 0.1, (B, 4, 3))).reshape(B, 12),                 # pFoot_des
+        U(-0.5, 0.5, (B, 12)),                                           # vFoot_des
+        U(-2, 2, (B, 12)),                                               # aFoot_des
+        fr.reshape(B, 12),                                               # Fr_des (from the MPC)
+        np.stack([np.zeros(B), np.zeros(B), U(-0.5, 0.5, B)], 1),        # previous vBody_Ori_des
+    ], 1)
+    return dict(state=np.ascontiguousarray(state, F32), cmd=np.ascontiguousarray(cmd, F32),
+                contact=np.ascontiguousarray(contact, np.int32), rpy=rpy, robot=rb)

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../quadruped-robot_b200/csrc/mpc_problem.h"
+#include "../../quadruped-robot_b200/csrc/wbc_problem.h"
 
 static qr_qp_options emul_default_options() {
     qr_qp_options o;
@@ -82,4 +83,26 @@ extern "C" int qr_emul_qp_solve_batch(int horizon, float mu, const qr_qp_options
     EmulTeam team(A.nfcap, horizon);
     for (int i = 0; i < batch; ++i) qr_qp_solve_problem<128>(A, i, team.S);
     return 0;
+}
+
+extern "C" int qr_emul_wbc_solve_batch(const qr_wbc_model* model, int batch, const float* state, const float* cmd,
+                                       const int32_t* contact, double* tau, double* fr, double* qdes, double* qddes,
+                                       double* dbg, int32_t* status) {
+    QrWbcModelDev M;
+    qr_wbc_host::build(model, &M);
+    std::vector<unsigned char> smem(qr_wbc_smem_bytes() + 64);
+    QrWbcWork W;
+    qr_wbc_carve(W, smem.data());
+    qr_wbc_init_tables<32>(W);
+    QrWbcArgs A;
+    memset(&A, 0, sizeof(A));
+    A.model = &M; A.opt = emul_default_options(); A.batch = batch;
+    A.state = state; A.cmd = cmd; A.contact = contact;
+    A.tau64 = tau; A.fr64 = fr; A.qdes64 = qdes; A.qddes64 = qddes; A.dbg = dbg; A.status = status;
+    for (int i = 0; i < batch; ++i) qr_wbc_problem<32>(A, i, W);
+    return 0;
+}
+
+extern "C" int qr_emul_swing_parabola(const float* start, const float* end, float height, float t, int phase_module, float* pos) {
+    return qr_swing_parabola(start, end, height, t, phase_module, pos);
 }

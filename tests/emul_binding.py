@@ -68,6 +68,44 @@ class Emul:
         return dict(x64=x64, status=st, iters=it)
 
 
+class WbcModelC(C.Structure):
+    _fields_ = [("body_size", C.c_float * 3), ("hip_len", C.c_float), ("upper_len", C.c_float), ("lower_len", C.c_float)]
+
+
+def _wbc_model(robot):
+    m = WbcModelC()
+    m.body_size[:] = robot.body_size
+    m.hip_len, m.upper_len, m.lower_len = robot.hip_len, robot.upper_len, robot.lower_len
+    return m
+
+
+def wbc_solve(self, batch):
+    """Host emulation of the WBC device code: dict(tau, fr, qdes, qddes, dbg, status) in float64."""
+    B = batch["state"].shape[0]
+    tau, fr, qdes, qddes = (np.zeros((B, 12)) for _ in range(4))
+    dbg = np.zeros((B, 630))
+    st = np.zeros(B, np.int32)
+    m = _wbc_model(batch["robot"])
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    self.lib.qr_emul_wbc_solve_batch(C.byref(m), B, self._fp(batch["state"]), self._fp(batch["cmd"]),
+                                     batch["contact"].ctypes.data_as(C.POINTER(C.c_int)), dp(tau), dp(fr), dp(qdes),
+                                     dp(qddes), dp(dbg), st.ctypes.data_as(C.POINTER(C.c_int)))
+    return dict(tau=tau, fr=fr, qdes=qdes, qddes=qddes, dbg=dbg, status=st)
+
+
+def swing_parabola(self, start, end, height, t, phase_module=False):
+    start = np.ascontiguousarray(start, np.float32)
+    end = np.ascontiguousarray(end, np.float32)
+    pos = np.zeros(3, np.float32)
+    ok = self.lib.qr_emul_swing_parabola(self._fp(start), self._fp(end), C.c_float(height), C.c_float(t),
+                                         int(phase_module), self._fp(pos))
+    return pos, bool(ok)
+
+
+Emul.wbc_solve = wbc_solve
+Emul.swing_parabola = swing_parabola
+
+
 def load():
     if _stale():
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", "-shared", "-o", _SO, _SRC],
