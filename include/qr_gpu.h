@@ -120,6 +120,28 @@ int qr_gpu_qp_solve_batch(int horizon, float mu, const qr_qp_options* opt, int b
                           float* x_out, double* x_out_f64, int32_t* status_out, int32_t* iters_out,
                           void* cuda_stream);
 
+/* qr_gpu_mpc_inputs_batch -- replaces the per-tick input preparation of MPCStanceLegController: the contact
+ * table mpcTable (Run, qr_mpc_stance_leg_controller.cpp:282-303; bit-exact masks) and the reference trajectory
+ * trajAll (UpdateMPC, :345-376), written straight into the `gait` / `traj` rows qr_gpu_mpc_solve_batch reads.
+ *   progress, duty [batch][4]   gaitGenerator->phaseInFullCycle / dutyFactor
+ *   early_contact  [batch][4] or NULL   legState == EARLY_CONTACT flags
+ *   contacts       [batch][4] or NULL   measured contact flags overwriting row 0 (:301-303)
+ *   traj_init      [batch][12]  {rollComp, pitchComp, yawDes, xDes, yDes, bodyHeight, 0, 0, yawRate, vxW, vyW, 0}
+ *   pos_xy         [batch][2]   actual base x, y (the start is clipped to +-0.1 m of it, :347-356)
+ *   num_horizon_l = max(2, int(fullCyclePeriod / 0.4)) (:50).  Either output may be NULL. */
+int qr_gpu_mpc_inputs_batch(int horizon, int num_horizon_l, float dt_mpc, int batch, const float* progress,
+                            const float* duty, const int32_t* early_contact, const int32_t* contacts,
+                            const float* traj_init, const float* pos_xy, float* gait_out, float* traj_out,
+                            void* cuda_stream);
+
+/* qr_gpu_mpc_leg_torque_batch -- replaces the post-processing of the MPC forces: f_ff = -R_base^T f
+ * (SolveDenseMPC, qr_mpc_stance_leg_controller.cpp:402-409) and tau_leg = J_leg^T f_ff (GetAction :139-141 ->
+ * qrRobot::MapContactForceToJointTorques, src/robots/qr_robot.cpp:241-251, analytic Jacobian :148-172).
+ *   quat [batch][4] (w,x,y,z), q [batch][12] motor angles, grf [batch][12] world-frame forces
+ *   f_ff_out [batch][12] or NULL, tau_out [batch][12] */
+int qr_gpu_mpc_leg_torque_batch(float hip_len, float upper_len, float lower_len, int batch, const float* quat,
+                                const float* q, const float* grf, float* f_ff_out, float* tau_out, void* cuda_stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Whole-body control
  * ------------------------------------------------------------------------------------------------- */

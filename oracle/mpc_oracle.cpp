@@ -360,3 +360,40 @@ extern "C" double qro_mpc_time_batch(const qro_mpc_params* P, int count, const f
     if (capped) *capped = ncap;
     return std::chrono::duration<double>(t1 - t0).count();
 }
+
+// GRF -> joint torques: SolveDenseMPC (qr_mpc_stance_leg_controller.cpp:402-409, f_ff = -R_base^T f) followed by
+// GetAction -> qrRobot::MapContactForceToJointTorques (qr_mpc_stance_leg_controller.cpp:139-141;
+// src/robots/qr_robot.cpp:241-251) with the analytic leg Jacobian (qr_robot.cpp:148-172, UpdateDataFlow :62-66).
+// quat = (w,x,y,z); R_base = quaternionToRotationMatrix(quat)^T (qr_robot.cpp:70).  Float32 throughout, with
+// the float overloads of sqrt / sin / cos and the double pow(-1, leg+1) of the reference.
+extern "C" void qro_mpc_grf_to_torque(float hip_len, float upper_len, float lower_len, const float* quat,
+                                      const float* q, const float* f_world, float* f_ff_out, float* tau) {
+    const float e0 = quat[0], e1 = quat[1], e2 = quat[2], e3 = quat[3];
+    // utils/qr_se3.h:186-203 builds R (row-major below) and returns its transpose; baseRMat transposes back
+    const float Rb[9] = {1 - 2 * (e2 * e2 + e3 * e3), 2 * (e1 * e2 - e0 * e3), 2 * (e1 * e3 + e0 * e2),
+                         2 * (e1 * e2 + e0 * e3), 1 - 2 * (e1 * e1 + e3 * e3), 2 * (e2 * e3 - e0 * e1),
+                         2 * (e1 * e3 - e0 * e2), 2 * (e2 * e3 + e0 * e1), 1 - 2 * (e1 * e1 + e2 * e2)};
+    for (int leg = 0; leg < 4; ++leg) {
+        const float* f = f_world + 3 * leg;
+        float ff[3];
+        for (int a = 0; a < 3; ++a) ff[a] = ((-Rb[a]) * f[0] + (-Rb[3 + a]) * f[1]) + (-Rb[6 + a]) * f[2];
+        const float* t = q + 3 * leg;
+        const float sh = hip_len * pow(-1, leg + 1);
+        const float lEff = sqrt(upper_len * upper_len + lower_len * lower_len + 2 * upper_len * lower_len * cos(t[2]));
+        const float tEff = t[1] + t[2] / 2;
+        float J[9];
+        J[0] = 0;
+        J[1] = -lEff * cos(tEff);
+        J[2] = lower_len * upper_len * sin(t[2]) * sin(tEff) / lEff - lEff * cos(tEff) / 2;
+        J[3] = -sh * sin(t[0]) + lEff * cos(t[0]) * cos(tEff);
+        J[4] = -lEff * sin(t[0]) * sin(tEff);
+        J[5] = -lower_len * upper_len * sin(t[0]) * sin(t[2]) * cos(tEff) / lEff - lEff * sin(t[0]) * sin(tEff) / 2;
+        J[6] = sh * cos(t[0]) + lEff * sin(t[0]) * cos(tEff);
+        J[7] = lEff * sin(tEff) * cos(t[0]);
+        J[8] = lower_len * upper_len * sin(t[2]) * cos(t[0]) * cos(tEff) / lEff + lEff * sin(tEff) * cos(t[0]) / 2;
+        for (int a = 0; a < 3; ++a) {
+            tau[3 * leg + a] = (J[a] * ff[0] + J[3 + a] * ff[1]) + J[6 + a] * ff[2];   // J^T f_ff
+            if (f_ff_out) f_ff_out[3 * leg + a] = ff[a];
+        }
+    }
+}

@@ -261,3 +261,14 @@ def swing_parabola(start, end, height, t, phase_module=False):
     pos = np.zeros(3, np.float32)
     ok = lib().qro_swing_parabola(_fp(start), _fp(end), C.c_float(height), C.c_float(t), int(phase_module), _fp(pos))
     return pos, bool(ok)
+
+
+def grf_to_torque(robot, quat, q, f_world):
+    quat = np.ascontiguousarray(quat, np.float32)
+    q = np.ascontiguousarray(q, np.float32)
+    f_world = np.ascontiguousarray(f_world, np.float32)
+    ff = np.zeros(12, np.float32)
+    tau = np.zeros(12, np.float32)
+    lib().qro_mpc_grf_to_torque(C.c_float(robot.hip_len), C.c_float(robot.upper_len), C.c_float(robot.lower_len),
+                                _fp(quat), _fp(q), _fp(f_world), _fp(ff), _fp(tau))
+    return ff, tau

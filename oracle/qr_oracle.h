@@ -82,6 +82,12 @@ void qro_mpc_reference_traj(int horizon, float dt_mpc, const float* init, const 
  * R_base[9] row-major (base->world).  f_world[12] = solution entries 0..11; f_ff[12] out (3*leg+axis). */
 void qro_mpc_grf_to_leg_force(const float* R_base, const double* x, float* f_world, float* f_ff);
 
+/* GRF -> leg force in the base frame -> joint torques through the analytic leg Jacobian
+ * (qr_mpc_stance_leg_controller.cpp:402-409, 139-141; src/robots/qr_robot.cpp:148-172, 241-251).
+ * quat (w,x,y,z), q[12], f_world[12]; f_ff_out[12] (may be NULL), tau[12]. */
+void qro_mpc_grf_to_torque(float hip_len, float upper_len, float lower_len, const float* quat, const float* q,
+                           const float* f_world, float* f_ff_out, float* tau);
+
 /* Wall-clock a batch of `count` independent SolveMPC calls (cold QProblem each) in this process.
  * Inputs are SoA-free: arrays of `count` consecutive problems.  Returns seconds; per-problem
  * seconds in lat[count] (may be NULL); number of RET_MAX_NWSR_REACHED in *capped. */

@@ -36,7 +36,7 @@ def default_options() -> QpOptions:
 EXPORTS = ["qr_gpu_init", "qr_gpu_shutdown", "qr_gpu_last_error", "qr_gpu_mpc_occupancy",
            "qr_gpu_mpc_solve_batch", "qr_gpu_mpc_solve_batch_host", "qr_gpu_mpc_condense_batch",
            "qr_gpu_qp_solve_batch", "qr_gpu_wbc_solve_batch", "qr_gpu_wbc_solve_batch_f64",
-           "qr_gpu_swing_parabola_batch"]
+           "qr_gpu_swing_parabola_batch", "qr_gpu_mpc_inputs_batch", "qr_gpu_mpc_leg_torque_batch"]
 
 
 class WbcModel(C.Structure):
@@ -170,3 +170,17 @@ def swing_parabola_batch_device(start, end, height, phase, phase_module: bool, p
     rc = lib().qr_gpu_swing_parabola_batch(start.shape[0], _vp(start), _vp(end), _vp(height), _vp(phase),
                                            int(phase_module), _vp(pos), _vp(valid), C.c_void_p(stream_ptr))
     _check(rc, "qr_gpu_swing_parabola_batch")
+
+
+def mpc_inputs_batch_device(horizon, num_horizon_l, dt_mpc, progress, duty, early, contacts, traj_init, pos_xy,
+                            gait_out, traj_out, stream_ptr: int):
+    rc = lib().qr_gpu_mpc_inputs_batch(horizon, num_horizon_l, C.c_float(dt_mpc), progress.shape[0], _vp(progress), _vp(duty),
+                                       _vp(early), _vp(contacts), _vp(traj_init), _vp(pos_xy), _vp(gait_out), _vp(traj_out),
+                                       C.c_void_p(stream_ptr))
+    _check(rc, "qr_gpu_mpc_inputs_batch")
+
+
+def mpc_leg_torque_batch_device(robot, quat, q, grf, f_ff, tau, stream_ptr: int):
+    rc = lib().qr_gpu_mpc_leg_torque_batch(C.c_float(robot.hip_len), C.c_float(robot.upper_len), C.c_float(robot.lower_len),
+                                           quat.shape[0], _vp(quat), _vp(q), _vp(grf), _vp(f_ff), _vp(tau), C.c_void_p(stream_ptr))
+    _check(rc, "qr_gpu_mpc_leg_torque_batch")

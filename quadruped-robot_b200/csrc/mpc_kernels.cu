@@ -573,3 +573,65 @@ extern "C" int qr_gpu_swing_parabola_batch(int batch, const float* start, const 
     if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_swing_parabola_kernel", e);
     return QR_OK;
 }
+
+// ==================================================================================================
+// MPC pre- and post-processing (contact table, reference trajectory, GRF -> joint torques)
+// ==================================================================================================
+#include "mpc_io.h"
+
+namespace {
+
+__global__ void qr_mpc_inputs_kernel(int h, int num_horizon_l, float dt_mpc, int batch, const float* progress,
+                                     const float* duty, const int32_t* early, const int32_t* contacts,
+                                     const float* traj_init, const float* pos_xy, float* gait_out, float* traj_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    if (gait_out)
+        qr_mpc_contact_table(h, num_horizon_l, progress + 4 * (size_t)i, duty + 4 * (size_t)i,
+                             early ? early + 4 * (size_t)i : nullptr, contacts ? contacts + 4 * (size_t)i : nullptr,
+                             gait_out + (size_t)4 * h * i);
+    if (traj_out)
+        qr_mpc_reference_traj(h, dt_mpc, traj_init + 12 * (size_t)i, pos_xy + 2 * (size_t)i, traj_out + (size_t)12 * h * i);
+}
+
+__global__ void qr_mpc_leg_torque_kernel(float hip_len, float upper_len, float lower_len, int batch, const float* quat,
+                                         const float* q, const float* grf, float* f_ff_out, float* tau_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    qr_mpc_grf_to_torque(hip_len, upper_len, lower_len, quat + 4 * (size_t)i, q + 12 * (size_t)i, grf + 12 * (size_t)i,
+                         f_ff_out ? f_ff_out + 12 * (size_t)i : nullptr, tau_out + 12 * (size_t)i);
+}
+
+}  // namespace
+
+extern "C" int qr_gpu_mpc_inputs_batch(int horizon, int num_horizon_l, float dt_mpc, int batch, const float* progress,
+                                       const float* duty, const int32_t* early_contact, const int32_t* contacts,
+                                       const float* traj_init, const float* pos_xy, float* gait_out, float* traj_out,
+                                       void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
+    if (horizon < 1 || horizon > QR_MAX_HORIZON || num_horizon_l < 1 || batch < 0) return fail(QR_EINVAL, "bad size argument");
+    if (batch == 0) return QR_OK;
+    if (gait_out && (!progress || !duty)) return fail(QR_EINVAL, "contact table needs progress and duty");
+    if (traj_out && (!traj_init || !pos_xy)) return fail(QR_EINVAL, "trajectory needs traj_init and pos_xy");
+    qr_mpc_inputs_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(
+        horizon, num_horizon_l, dt_mpc, batch, progress, duty, early_contact, contacts, traj_init, pos_xy, gait_out, traj_out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_inputs_kernel", e);
+    return QR_OK;
+}
+
+extern "C" int qr_gpu_mpc_leg_torque_batch(float hip_len, float upper_len, float lower_len, int batch, const float* quat,
+                                           const float* q, const float* grf, float* f_ff_out, float* tau_out,
+                                           void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
+    if (batch < 0) return fail(QR_EINVAL, "negative batch");
+    if (batch == 0) return QR_OK;
+    if (!quat || !q || !grf || !tau_out) return fail(QR_EINVAL, "null pointer");
+    qr_mpc_leg_torque_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(hip_len, upper_len, lower_len, batch,
+                                                                                       quat, q, grf, f_ff_out, tau_out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_leg_torque_kernel", e);
+    return QR_OK;
+}

@@ -9,6 +9,7 @@
 
 #include "../../quadruped-robot_b200/csrc/mpc_problem.h"
 #include "../../quadruped-robot_b200/csrc/wbc_problem.h"
+#include "../../quadruped-robot_b200/csrc/mpc_io.h"
 
 static qr_qp_options emul_default_options() {
     qr_qp_options o;
@@ -105,4 +106,16 @@ extern "C" int qr_emul_wbc_solve_batch(const qr_wbc_model* model, int batch, con
 
 extern "C" int qr_emul_swing_parabola(const float* start, const float* end, float height, float t, int phase_module, float* pos) {
     return qr_swing_parabola(start, end, height, t, phase_module, pos);
+}
+
+extern "C" void qr_emul_mpc_contact_table(int h, int nhl, const float* progress, const float* duty, const int32_t* early,
+                                          const int32_t* contacts, float* table) {
+    qr_mpc_contact_table(h, nhl, progress, duty, early, contacts, table);
+}
+extern "C" void qr_emul_mpc_reference_traj(int h, float dt, const float* init, const float* pos_xy, float* traj) {
+    qr_mpc_reference_traj(h, dt, init, pos_xy, traj);
+}
+extern "C" void qr_emul_mpc_grf_to_torque(float hip, float up, float low, const float* quat, const float* q, const float* f,
+                                          float* ff, float* tau) {
+    qr_mpc_grf_to_torque(hip, up, low, quat, q, f, ff, tau);
 }
