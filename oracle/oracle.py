@@ -88,6 +88,34 @@ def mpc_build(P: MpcParams, batch: dict, i: int, want_ab: bool = False):
     return (H, g, ub, Aqp, Bqp) if want_ab else (H, g, ub)
 
 
+
+_REF = None
+
+
+def ref_mpc_available() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libqr_mpc_ref.so"))
+
+
+def ref_mpc_solve(P: MpcParams, batch: dict, i: int):
+    """The reference's OWN qr_mpc_interface.cpp (oracle/_ref/libqr_mpc_ref.so, compiled unmodified
+    against oracle/mini_eigen): SetupProblem + SolveMPCKernel + GetMPCSolution on problem i.
+    Returns (H, g, ub, x) read back from the reference's qpOASES buffers (float64)."""
+    global _REF
+    if _REF is None:
+        _REF = C.CDLL(os.path.join(_HERE, "_ref", "libqr_mpc_ref.so"))
+    h = P.horizon
+    n, m = 12 * h, 20 * h
+    H, g, ub, x = np.empty((n, n)), np.empty(n), np.empty(m), np.empty(n)
+    params = np.array([P.dt, P.mu, P.f_max, P.mass, P.alpha], np.float64)
+    inertia = np.array(P.inertia[:], np.float32)
+    weights = np.array(P.weights[:], np.float32)
+    rows = [np.ascontiguousarray(batch[k][i], np.float32) for k in ("p", "v", "quat", "w", "r_feet", "rpy", "traj", "gait")]
+    rc = _REF.qr_ref_mpc_solve(h, _dp(params), _fp(inertia), _fp(weights), *[_fp(r) for r in rows],
+                               _dp(H), _dp(g), _dp(ub), _dp(x))
+    assert rc == 0
+    return H, g, ub, x
+
+
 def mpc_qpoases(h: int, mu: float, H, g, ub, nWSR: int = 100000):
     """The reference's qpOASES call on float32 QP data.  Returns x, info(rval, nWSR), kkt, cstat."""
     n, m = 12 * h, 20 * h

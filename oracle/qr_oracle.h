@@ -10,11 +10,15 @@
  * from /root/reference/quadruped/extern/qpOASES/src) exactly as SolveMPC does (:428-438).
  *
  * Pinning status: the reference repository holds NO test, golden vector or fixture for this path
- * (SURVEY.md section 4 / 8c).  The restatement is pinned instead against the reference's own
- * qr_mpc_interface.cpp compiled unmodified against oracle/mini_eigen (oracle/_ref/libqr_mpc_ref.so)
- * -- see oracle/README.md.  Eigen's own summation order is not reproducible here (Eigen is not
- * installed), so bit-level agreement with a true Eigen build is UNPINNED; all float32 products in
- * the oracle are plain sequential sums without FMA contraction.
+ * (SURVEY.md section 4 / 8c).  The MPC restatement is pinned instead against the reference ITSELF run
+ * here: its own qr_mpc_interface.cpp compiled unmodified against oracle/mini_eigen
+ * (oracle/_ref/libqr_mpc_ref.so, ref_shim.cpp) -- H, g, U_b and the stock qpOASES solution agree bit
+ * for bit when both sides evaluate the matrix exponential by its finite series, and to float32
+ * rounding (3e-7) with Eigen's Pade evaluation; tests/test_oracle.py holds both checks.  The rounding
+ * of a true Eigen build is not reproducible here (Eigen is not installed) and stays UNPINNED; all
+ * float32 products in the oracle are plain sequential sums without FMA contraction.  The WBC
+ * restatement (wbc_oracle.cpp) has no compiled-reference counterpart: WBC parity is UNPINNED beyond
+ * the reference's own QuadProg++ and the physics identities of tests/test_wbc.py.
  */
 #ifndef QR_ORACLE_H
 #define QR_ORACLE_H
