@@ -20,6 +20,9 @@
 #include <ostream>
 #include <vector>
 
+#define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+#define EIGEN_STL_VECTOR_SPECIALIZATION_DEFINED
+
 namespace Eigen {
 
 const int Dynamic = -1;
@@ -54,6 +57,8 @@ struct traits<Block<M, BR, BC>> {
     typedef typename traits<M>::Scalar Scalar;
     enum { Rows = BR, Cols = BC };
 };
+template <class T>
+struct traits<const T> : traits<T> {};
 template <class M>
 struct traits<DiagonalView<M>> {
     typedef typename traits<M>::Scalar Scalar;
@@ -137,6 +142,60 @@ public:
     }
     Block<Derived, Dynamic, 1> segment(int s, int n) { return Block<Derived, Dynamic, 1>(derived(), s, 0, n, 1); }
     DiagonalView<Derived> diagonal() { return DiagonalView<Derived>(derived()); }
+    Block<Derived, Dynamic, Dynamic> topRows(int n) { return block(0, 0, n, cols()); }
+    Block<Derived, Dynamic, Dynamic> bottomRows(int n) { return block(rows() - n, 0, n, cols()); }
+    Block<Derived, Dynamic, Dynamic> leftCols(int n) { return block(0, 0, rows(), n); }
+    Block<Derived, Dynamic, Dynamic> rightCols(int n) { return block(0, cols() - n, rows(), n); }
+    Block<const Derived, Dynamic, Dynamic> topRows(int n) const { return block(0, 0, n, cols()); }
+    Block<const Derived, Dynamic, Dynamic> bottomRows(int n) const { return block(rows() - n, 0, n, cols()); }
+    Block<const Derived, Dynamic, Dynamic> leftCols(int n) const { return block(0, 0, rows(), n); }
+    Block<const Derived, Dynamic, Dynamic> rightCols(int n) const { return block(0, cols() - n, rows(), n); }
+
+    // Fixed-size views (`m.template block<3, 3>(i, j)` and friends).
+#define MINI_EIGEN_VIEW2(NAME, I0, J0)                                                                      \
+    template <int BR, int BC>                                                                               \
+    Block<Derived, BR, BC> NAME() { return Block<Derived, BR, BC>(derived(), I0, J0, BR, BC); }             \
+    template <int BR, int BC>                                                                               \
+    Block<const Derived, BR, BC> NAME() const { return Block<const Derived, BR, BC>(derived(), I0, J0, BR, BC); }
+    MINI_EIGEN_VIEW2(topLeftCorner, 0, 0)
+    MINI_EIGEN_VIEW2(topRightCorner, 0, cols() - BC)
+    MINI_EIGEN_VIEW2(bottomLeftCorner, rows() - BR, 0)
+    MINI_EIGEN_VIEW2(bottomRightCorner, rows() - BR, cols() - BC)
+#undef MINI_EIGEN_VIEW2
+    template <int BR, int BC>
+    Block<Derived, BR, BC> block(int i, int j) { return Block<Derived, BR, BC>(derived(), i, j, BR, BC); }
+    template <int BR, int BC>
+    Block<const Derived, BR, BC> block(int i, int j) const { return Block<const Derived, BR, BC>(derived(), i, j, BR, BC); }
+    template <int N>
+    Block<Derived, N, 1> head() { return Block<Derived, N, 1>(derived(), 0, 0, N, 1); }
+    template <int N>
+    Block<const Derived, N, 1> head() const { return Block<const Derived, N, 1>(derived(), 0, 0, N, 1); }
+    template <int N>
+    Block<Derived, N, 1> tail() { return Block<Derived, N, 1>(derived(), rows() - N, 0, N, 1); }
+    template <int N>
+    Block<const Derived, N, 1> tail() const { return Block<const Derived, N, 1>(derived(), rows() - N, 0, N, 1); }
+    template <int N>
+    Block<Derived, N, 1> segment(int s) { return Block<Derived, N, 1>(derived(), s, 0, N, 1); }
+    template <int N>
+    Block<const Derived, N, 1> segment(int s) const { return Block<const Derived, N, 1>(derived(), s, 0, N, 1); }
+    template <int N>
+    Block<Derived, N, ColsAtCompileTime> topRows() { return Block<Derived, N, ColsAtCompileTime>(derived(), 0, 0, N, cols()); }
+    template <int N>
+    Block<const Derived, N, ColsAtCompileTime> topRows() const { return Block<const Derived, N, ColsAtCompileTime>(derived(), 0, 0, N, cols()); }
+    template <int N>
+    Block<Derived, N, ColsAtCompileTime> bottomRows() { return Block<Derived, N, ColsAtCompileTime>(derived(), rows() - N, 0, N, cols()); }
+    template <int N>
+    Block<const Derived, N, ColsAtCompileTime> bottomRows() const { return Block<const Derived, N, ColsAtCompileTime>(derived(), rows() - N, 0, N, cols()); }
+    template <int N>
+    Block<Derived, RowsAtCompileTime, N> leftCols() { return Block<Derived, RowsAtCompileTime, N>(derived(), 0, 0, rows(), N); }
+    template <int N>
+    Block<const Derived, RowsAtCompileTime, N> leftCols() const { return Block<const Derived, RowsAtCompileTime, N>(derived(), 0, 0, rows(), N); }
+    template <int N>
+    Block<Derived, RowsAtCompileTime, N> rightCols() { return Block<Derived, RowsAtCompileTime, N>(derived(), 0, cols() - N, rows(), N); }
+    template <int N>
+    Block<const Derived, RowsAtCompileTime, N> rightCols() const { return Block<const Derived, RowsAtCompileTime, N>(derived(), 0, cols() - N, rows(), N); }
+    Block<const Derived, Dynamic, 1> segment(int s, int n) const { return Block<const Derived, Dynamic, 1>(derived(), s, 0, n, 1); }
+    TransposedObject adjoint() const { return transpose(); }
 
     // Reductions.
     Scalar trace() const {
@@ -259,8 +318,17 @@ struct MatStorage<S, R, C, false> {
     const S* data() const { return d.data(); }
 };
 
+// A 1 x 1 result (inner product written as a^T * b) converts to its scalar.
+template <class Derived, class S, bool OneByOne>
+struct ScalarConv {};
+template <class Derived, class S>
+struct ScalarConv<Derived, S, true> {
+    operator S() const { return static_cast<const Derived*>(this)->coeff(0, 0); }
+};
+
 template <class Scalar_, int Rows_, int Cols_>
-class Matrix : public MatrixBase<Matrix<Scalar_, Rows_, Cols_>> {
+class Matrix : public MatrixBase<Matrix<Scalar_, Rows_, Cols_>>,
+               public ScalarConv<Matrix<Scalar_, Rows_, Cols_>, Scalar_, Rows_ == 1 && Cols_ == 1> {
     MatStorage<Scalar_, Rows_, Cols_> st;
 
 public:
@@ -316,6 +384,22 @@ public:
     void resize(int r, NoChange_t) { st.resize(r, cols()); }
     void resize(NoChange_t, int c) { st.resize(rows(), c); }
     void resize(int n) { st.resize(Cols_ == 1 ? n : 1, Cols_ == 1 ? 1 : n); }
+    using Base::setZero;
+    Matrix& setZero(int r, int c) {
+        st.resize(r, c);
+        return Base::setZero();
+    }
+    Matrix& setZero(int n) {
+        resize(n);
+        return Base::setZero();
+    }
+    void conservativeResize(int r, int c) {
+        Matrix old = *this;
+        st.resize(r, c);
+        for (int j = 0; j < c && j < old.cols(); ++j)
+            for (int i = 0; i < r && i < old.rows(); ++i) coeffRef(i, j) = old.coeff(i, j);
+    }
+    void conservativeResize(int n) { conservativeResize(Cols_ == 1 ? n : 1, Cols_ == 1 ? 1 : n); }
 
     static Matrix Zero() { return Matrix().setZero(); }
     static Matrix Zero(int r, int c) { return Matrix(r, c).setZero(); }
@@ -324,6 +408,15 @@ public:
     static Matrix Identity(int r, int c) { return Matrix(r, c).setIdentity(); }
     static Matrix Ones() { return Matrix().setConstant(Scalar(1)); }
     static Matrix Constant(Scalar v) { return Matrix().setConstant(v); }
+    static Matrix Constant(int n, Scalar v) { return Matrix(n).setConstant(v); }
+    static Matrix Constant(int r, int c, Scalar v) { return Matrix(r, c).setConstant(v); }
+    template <class O>
+    Matrix& operator*=(const MatrixBase<O>& o) {
+        Matrix t = (*this) * o;
+        *this = t;
+        return *this;
+    }
+    using Base::operator*=;
 };
 
 typedef Matrix<float, Dynamic, Dynamic> MatrixXf;
@@ -602,18 +695,110 @@ public:
 typedef Quaternion<float> Quaternionf;
 typedef Quaternion<double> Quaterniond;
 
-// Only named by templates of the reference headers that the MPC translation unit never instantiates.
+// Thin singular value decomposition by one-sided (Hestenes) Jacobi rotations on the columns of the
+// taller of (A, A^T); singular values sorted in decreasing order.  Eigen's JacobiSVD is two-sided with
+// a QR preconditioner: same factorisation, different rounding.
 template <class M>
 class JacobiSVD {
 public:
-    JacobiSVD(const M&, unsigned = 0) {}
-    const M& singularValues() const { return m; }
-    const M& matrixU() const { return m; }
-    const M& matrixV() const { return m; }
+    typedef typename M::Scalar Scalar;
+    typedef Matrix<Scalar, Dynamic, 1> SingularValuesType;
+    JacobiSVD() {}
+    JacobiSVD(const M& a, unsigned = 0) { compute(a); }
+    JacobiSVD& compute(const M& a, unsigned = 0) {
+        const bool wide = a.rows() < a.cols();
+        M B = wide ? M(a.transpose()) : a;   // n x k, n >= k
+        const int n = B.rows(), k = B.cols();
+        M V(k, k);
+        V.setIdentity();
+        const double eps = sizeof(Scalar) == 4 ? 1e-7 : 1e-15;
+        for (int sweep = 0; sweep < 60; ++sweep) {
+            double off = 0;
+            for (int p = 0; p < k - 1; ++p)
+                for (int q = p + 1; q < k; ++q) {
+                    double alpha = 0, beta = 0, gamma = 0;
+                    for (int i = 0; i < n; ++i) {
+                        alpha += double(B.coeff(i, p)) * B.coeff(i, p);
+                        beta += double(B.coeff(i, q)) * B.coeff(i, q);
+                        gamma += double(B.coeff(i, p)) * B.coeff(i, q);
+                    }
+                    if (gamma == 0) continue;
+                    double rel = std::fabs(gamma) / std::sqrt(alpha * beta + 1e-300);
+                    if (rel > off) off = rel;
+                    double zeta = (beta - alpha) / (2 * gamma);
+                    double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1 + zeta * zeta));
+                    double c = 1 / std::sqrt(1 + t * t), sn = c * t;
+                    for (int i = 0; i < n; ++i) {
+                        Scalar bp = B.coeff(i, p), bq = B.coeff(i, q);
+                        B.coeffRef(i, p) = Scalar(c * bp - sn * bq);
+                        B.coeffRef(i, q) = Scalar(sn * bp + c * bq);
+                    }
+                    for (int i = 0; i < k; ++i) {
+                        Scalar vp = V.coeff(i, p), vq = V.coeff(i, q);
+                        V.coeffRef(i, p) = Scalar(c * vp - sn * vq);
+                        V.coeffRef(i, q) = Scalar(sn * vp + c * vq);
+                    }
+                }
+            if (off < eps) break;
+        }
+        std::vector<double> sig(k);
+        std::vector<int> order(k);
+        for (int j = 0; j < k; ++j) {
+            double s2 = 0;
+            for (int i = 0; i < n; ++i) s2 += double(B.coeff(i, j)) * B.coeff(i, j);
+            sig[j] = std::sqrt(s2);
+            order[j] = j;
+        }
+        for (int a1 = 0; a1 < k; ++a1)   // selection sort, stable enough for k <= 18
+            for (int b1 = a1 + 1; b1 < k; ++b1)
+                if (sig[order[b1]] > sig[order[a1]]) std::swap(order[a1], order[b1]);
+        M Ub(n, k), Vs(k, k);
+        s_.resize(k);
+        for (int j = 0; j < k; ++j) {
+            const int o = order[j];
+            s_.coeffRef(j) = Scalar(sig[o]);
+            for (int i = 0; i < n; ++i) Ub.coeffRef(i, j) = sig[o] > 0 ? Scalar(B.coeff(i, o) / sig[o]) : Scalar(0);
+            for (int i = 0; i < k; ++i) Vs.coeffRef(i, j) = V.coeff(i, o);
+        }
+        if (wide) {   // A^T = Ub S Vs^T  =>  A = Vs S Ub^T
+            u_ = Vs;
+            v_ = Ub;
+        } else {
+            u_ = Ub;
+            v_ = Vs;
+        }
+        return *this;
+    }
+    const SingularValuesType& singularValues() const { return s_; }
+    const M& matrixU() const { return u_; }
+    const M& matrixV() const { return v_; }
 
 private:
-    M m;
+    M u_, v_;
+    SingularValuesType s_;
 };
+
+// Linear solves the reference spells as a rank-revealing QR; here: LU with partial pivoting.
+template <class M>
+class ColPivHouseholderQR {
+    M a;
+
+public:
+    ColPivHouseholderQR() {}
+    explicit ColPivHouseholderQR(const M& m) : a(m) {}
+    ColPivHouseholderQR& compute(const M& m) {
+        a = m;
+        return *this;
+    }
+    template <class B>
+    typename MatrixBase<B>::PlainObject solve(const MatrixBase<B>& b) const {
+        M lu = a;
+        typename MatrixBase<B>::PlainObject x = b.eval();
+        mini_lu_solve<typename M::Scalar>(lu.rows(), x.cols(), lu.data(), x.data());
+        return x;
+    }
+};
+
 template <class T, int Dim, int Mode>
 class Transform {
 public:

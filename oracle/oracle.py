@@ -29,7 +29,7 @@ def build(force: bool = False) -> str:
     have_ref = os.path.isdir("/root/reference/quadruped/extern/qpOASES/src")
     if force or not os.path.exists(so) or have_ref:
         if have_ref:
-            subprocess.run(["make", "-s", "-j8", "-C", _HERE, "all", "refmpc"], check=True,
+            subprocess.run(["make", "-s", "-j8", "-C", _HERE, "all", "refmpc", "refwbc"], check=True,
                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         elif not os.path.exists(so):
             raise RuntimeError("oracle/libqr_oracle.so missing and /root/reference not available to build it")
@@ -263,8 +263,23 @@ def wbc_model_of(robot) -> WbcModel:
     return m
 
 
+_REFWBC = None
+
+
+def ref_wbc_available() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libqr_wbc_ref.so"))
+
+
+def _ref_wbc():
+    global _REFWBC
+    if _REFWBC is None:
+        _REFWBC = C.CDLL(os.path.join(_HERE, "_ref", "libqr_wbc_ref.so"))
+    return _REFWBC
+
+
 def wbc_step(model: WbcModel, state, cmd, contact, precision: str = "f64"):
-    """One WBC tick for one robot.  Returns dict(tau, fr, qdes, qddes, H, G, C, Jc, Jcdqd, pGC, vGC, qdd, rc)."""
+    """One WBC tick for one robot (precision f64 | f32 = the restatement, ref = the reference's own
+    classes compiled from /root/reference).  Returns dict(tau, fr, qdes, qddes, H, G, C, Jc, Jcdqd, pGC, vGC, qdd, rc)."""
     dt = np.float64 if precision == "f64" else np.float32
     ptr = _dp if precision == "f64" else _fp
     tau, fr, qdes, qddes = (np.zeros(12, dt) for _ in range(4))
@@ -272,7 +287,10 @@ def wbc_step(model: WbcModel, state, cmd, contact, precision: str = "f64"):
     state = np.ascontiguousarray(state, np.float32)
     cmd = np.ascontiguousarray(cmd, np.float32)
     contact = np.ascontiguousarray(contact, np.int32)
-    fn = lib().qro_wbc_step_f64 if precision == "f64" else lib().qro_wbc_step_f32
+    if precision == "ref":   # the reference's own WBC classes (oracle/_ref/libqr_wbc_ref.so), float32
+        fn = _ref_wbc().qr_ref_wbc_step
+    else:
+        fn = lib().qro_wbc_step_f64 if precision == "f64" else lib().qro_wbc_step_f32
     rc = fn(C.byref(model), _fp(state), _fp(cmd), _ip(contact), ptr(tau), ptr(fr), ptr(qdes), ptr(qddes), ptr(dbg))
     o = 0
     out = dict(tau=tau, fr=fr, qdes=qdes, qddes=qddes, rc=rc)

@@ -17,8 +17,10 @@
  * rounding (3e-7) with Eigen's Pade evaluation; tests/test_oracle.py holds both checks.  The rounding
  * of a true Eigen build is not reproducible here (Eigen is not installed) and stays UNPINNED; all
  * float32 products in the oracle are plain sequential sums without FMA contraction.  The WBC
- * restatement (wbc_oracle.cpp) has no compiled-reference counterpart: WBC parity is UNPINNED beyond
- * the reference's own QuadProg++ and the physics identities of tests/test_wbc.py.
+ * restatement (wbc_oracle.cpp) is pinned the same way: floating_base_model.cpp, qr_single_contact.cpp,
+ * qr_multitask_projection.cpp, qr_wholebody_impulse_ctrl.cpp and task_set/ of the reference compiled
+ * unmodified (oracle/_ref/libqr_wbc_ref.so, ref_wbc_shim.cpp) agree with it to float32 rounding
+ * (tests/test_wbc.py).
  */
 #ifndef QR_ORACLE_H
 #define QR_ORACLE_H

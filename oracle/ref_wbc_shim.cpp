@@ -1,0 +1,223 @@
+// ref_wbc_shim.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Drives the reference's OWN whole-body-control classes, compiled UNMODIFIED from where they lie under
+// /root/reference/quadruped (oracle/Makefile target `refwbc`, against oracle/mini_eigen):
+//   src/dynamics/floating_base_model.cpp                FloatingBaseModel<float>
+//   src/controllers/wbc/qr_single_contact.cpp           qrSingleContact<float>
+//   src/controllers/wbc/task_set/qr_task_*.cpp          body orientation / body position / link position
+//   src/controllers/wbc/qr_multitask_projection.cpp     qrMultitaskProjection<float>
+//   src/controllers/wbc/qr_wholebody_impulse_ctrl.cpp   qrWholeBodyImpulseCtrl<float> (+ QuadProg++)
+// What cannot be compiled here is the glue around them -- qrWbcLocomotionController and
+// qrRobot*::BuildDynamicModel need the robot / estimator / ROS / yaml classes -- so this file plays
+// that part: it feeds the model constants of src/robots/qr_robot_a1_sim.cpp:176-345 (Lite3 file
+// identical) to FloatingBaseModel's builder API and then issues the call sequence of
+// qr_wbc_locomotion_controller.cpp:29-73 (construction, gains), :138-168 (UpdateModel),
+// :172-201 (ContactTaskUpdate), :122-124 (FindConfiguration, MakeTorque).
+// Same C signature as qro_wbc_step_f32 (qr_oracle.h) so tests can hold the two side by side.
+#include "controllers/wbc/qr_multitask_projection.hpp"
+#include "controllers/wbc/qr_wholebody_impulse_ctrl.hpp"
+#include "controllers/wbc/task_set/qr_task_body_orientation.hpp"
+#include "controllers/wbc/task_set/qr_task_body_position.hpp"
+#include "controllers/wbc/task_set/qr_task_link_position.hpp"
+
+#include "qr_oracle.h"
+
+#include <cmath>
+#include <memory>
+
+using robotics::math::coordinateRotation;
+using robotics::math::CoordinateAxis;
+
+namespace {
+
+typedef SpatialInertia<float> SI;
+
+Vec3<float> signed_for_leg(const Vec3<float>& v, int leg) {   // qrRobot::WithLegSigns, qr_robot.cpp:89-104
+    const float sx = leg < 2 ? 1.f : -1.f, sy = (leg % 2 == 0) ? -1.f : 1.f;
+    return Vec3<float>(sx * v[0], sy * v[1], v[2]);
+}
+
+Mat3<float> micro(std::initializer_list<double> v) {   // `M << ...; M = M * 1e-6`
+    Mat3<float> m;
+    int i = 0;
+    for (double x : v) {
+        m(i / 3, i % 3) = x;
+        ++i;
+    }
+    return m * 1e-6;
+}
+
+void build_model(FloatingBaseModel<float>& model, const qro_wbc_model* cfg) {
+    const float hipLength = cfg->hip_len, upperLegLength = cfg->upper_len, lowerLegLength = cfg->lower_len;
+    Vec3<float> bodyDims(cfg->body_size[0], cfg->body_size[1], cfg->body_size[2]);
+
+    Mat3<float> rotorZ;
+    rotorZ.setIdentity();
+    float scale_ = 1e-2;
+    rotorZ = scale_ * 1e-6 * rotorZ;
+    Mat3<float> RY = coordinateRotation<float>(CoordinateAxis::Y, M_PI / 2);
+    Mat3<float> RX = coordinateRotation<float>(CoordinateAxis::X, M_PI / 2);
+    Mat3<float> rotorX = RY * rotorZ * RY.transpose();
+    Mat3<float> rotorY = RX * rotorZ * RX.transpose();
+
+    SI abad(0.696, Vec3<float>(-0.0033, 0, 0),
+            micro({469.2, -9.4, -0.342, -9.4, 807.5, -0.466, -0.342, -0.466, 552.9}));
+    SI hip(1.013, Vec3<float>(-0.003237, -0.022327, -0.027326),
+           micro({5529, 4.825, 343.9, 4.825, 5139.3, 22.4, 343.9, 22.4, 1367.8}));
+    SI knee(0.166, Vec3<float>(0.006435, 0, -0.107), micro({2998, 0, -141.2, 0, 3014, 0, -141.2, 0, 32.4}));
+    SI body(6, Vec3<float>(0, 0, 0), micro({15853, 0, 0, 0, 37799, 0, 0, 0, 45654}));
+    Vec3<float> origin(0, 0, 0);
+    float rotorMass = 1e-8;
+    SI rotX(rotorMass, origin, rotorX), rotY(rotorMass, origin, rotorY);
+
+    model.addBase(body);
+    model.addGroundContactBoxPoints(5, bodyDims);
+
+    const Mat3<float> I3 = Mat3<float>::Identity();
+    const Vec3<float> abadLoc(0.1805f, 0.047f, 0.f), abadRotorLoc(0.14f, 0.047f, 0.f), hipLoc(0, hipLength, 0),
+        hipRotorLoc(0, 0.04, 0), kneeLoc(0, 0, -upperLegLength);
+    const float kneeLinkY_offset = 0.004;
+    int id = 5;
+    for (int leg = 0; leg < 4; ++leg) {
+        const bool right = (leg % 2 == 0);   // sideSign < 0 in the reference loop
+        auto side = [&](SI s) { return right ? s.flipAlongAxis(CoordinateAxis::Y) : s; };
+        const int abadId = ++id;
+        model.addBody(side(abad), side(rotX), 1.f, 5, JointType::Revolute, CoordinateAxis::X,
+                      createSXform(I3, signed_for_leg(abadLoc, leg)), createSXform(I3, signed_for_leg(abadRotorLoc, leg)));
+        const int hipId = ++id;
+        model.addBody(side(hip), side(rotY), 1.f, abadId, JointType::Revolute, CoordinateAxis::Y,
+                      createSXform(I3, signed_for_leg(hipLoc, leg)),
+                      createSXform(coordinateRotation(CoordinateAxis::Z, float(M_PI)), signed_for_leg(hipRotorLoc, leg)));
+        model.addGroundContactPoint(hipId, Vec3<float>(0, 0, -upperLegLength));
+        const int kneeId = ++id;
+        model.addBody(knee, side(rotY), 1.f, hipId, JointType::Revolute, CoordinateAxis::Y, createSXform(I3, kneeLoc),
+                      createSXform(I3, origin));
+        model.addGroundContactPoint(kneeId, Vec3<float>(0, right ? kneeLinkY_offset : -kneeLinkY_offset, -lowerLegLength),
+                                    true);
+    }
+    Vec3<float> g(0, 0, -9.81);
+    model.setGravity(g);
+}
+
+}   // namespace
+
+extern "C" int qr_ref_wbc_step(const qro_wbc_model* cfg, const float* state, const float* cmd, const int* contact,
+                               float* tau, float* fr, float* qdes, float* qddes, float* dbg) {
+    const int FOOT[4] = {9, 11, 13, 15};   // Quadruped::linkID::FR, FL, HR, HL (config/qr_enum_types.h:35-45)
+    FloatingBaseModel<float> fb;
+    build_model(fb, cfg);
+
+    // construction + gains, qr_wbc_locomotion_controller.cpp:29-73
+    const size_t dimConfig = 18;
+    std::vector<qrTask<float>*> taskList;
+    std::vector<qrSingleContact<float>*> contactList;
+    qrMultitaskProjection<float> multitask(dimConfig);
+    qrWholeBodyImpulseCtrl<float> wbic(dimConfig, &contactList, &taskList);
+    qrWBICExtraData<float> extra;
+    extra.weightFb = DVec<float>::Constant(6, 0.1);
+    extra.weightFr = DVec<float>::Constant(12, 1);
+    qrTaskBodyOrientation<float> taskOri(&fb);
+    qrTaskBodyPosition<float> taskPos(&fb);
+    std::unique_ptr<qrSingleContact<float>> footContact[4];
+    std::unique_ptr<qrTaskLinkPosition<float>> taskFoot[4];
+    for (int l = 0; l < 4; ++l) {
+        footContact[l].reset(new qrSingleContact<float>(&fb, FOOT[l]));
+        taskFoot[l].reset(new qrTaskLinkPosition<float>(&fb, FOOT[l]));
+    }
+    for (int i = 0; i < 3; ++i) {
+        taskPos.Kp[i] = 100.;
+        taskPos.Kd[i] = 10.;
+        taskOri.Kp[i] = 100.;
+        taskOri.Kd[i] = 10.;
+        for (int l = 0; l < 4; ++l) {
+            taskFoot[l]->Kp[i] = 500;
+            taskFoot[l]->Kd[i] = 10.;
+        }
+    }
+
+    // UpdateModel, :138-168
+    FBModelState<float> ms;
+    ms.q = DVec<float>::Zero(12);
+    ms.qd = DVec<float>::Zero(12);
+    DVec<float> fullConfig(12 + 7);
+    fullConfig.setZero();
+    for (int i = 0; i < 4; ++i) ms.bodyOrientation[i] = state[i];
+    for (int i = 0; i < 3; ++i) ms.bodyPosition[i] = state[4 + i];
+    for (int i = 0; i < 6; ++i) ms.bodyVelocity[i] = state[7 + i];
+    for (int i = 0; i < 12; ++i) {
+        ms.q[i] = state[13 + i];
+        ms.qd[i] = state[25 + i];
+        fullConfig[i + 6] = ms.q[i];
+    }
+    fb.setState(ms);
+    fb.contactJacobians();
+    fb.massMatrix();
+    fb.generalizedGravityForce();
+    fb.generalizedCoriolisForce();
+    wbic.GetModelRes(fb);
+
+    // ContactTaskUpdate, :172-201.  The orientation task reads the desiredVel its PREVIOUS call stored
+    // (qr_task_body_orientation.cpp:68); a first call seeds that state with cmd[63..65].
+    const float *pBody_des = cmd, *vBody_des = cmd + 3, *aBody_des = cmd + 6, *rpy_des = cmd + 9, *vOri_des = cmd + 12,
+                *pFoot = cmd + 15, *vFoot = cmd + 27, *aFoot = cmd + 39, *Fr_des = cmd + 51, *prevOriVel = cmd + 63;
+    auto v3 = [](const float* p) { return Vec3<float>(p[0], p[1], p[2]); };
+    Vec3<float> zeroVec3;
+    zeroVec3.setZero();
+    Vec3<float> rpyDes = v3(rpy_des);
+    Quat<float> quatDes = robotics::math::rpyToQuat(rpyDes);
+    taskOri.UpdateTask(&quatDes, v3(prevOriVel), zeroVec3);
+    taskOri.UpdateTask(&quatDes, v3(vOri_des), zeroVec3);
+    Vec3<float> pBody = v3(pBody_des);
+    taskPos.UpdateTask(&pBody, v3(vBody_des), v3(aBody_des));
+    taskList.push_back(&taskOri);
+    taskList.push_back(&taskPos);
+    Vec3<float> pFootDes[4];
+    for (int leg = 0; leg < 4; ++leg) {
+        if (contact[leg]) {
+            footContact[leg]->SetDesiredFr((DVec<float>)(v3(Fr_des + 3 * leg)));
+            footContact[leg]->UpdateContactSpec();
+            contactList.push_back(footContact[leg].get());
+        } else {
+            pFootDes[leg] = v3(pFoot + 3 * leg);
+            taskFoot[leg]->UpdateTask(&pFootDes[leg], v3(vFoot + 3 * leg), v3(aFoot + 3 * leg));
+            taskList.push_back(taskFoot[leg].get());
+        }
+    }
+
+    // Run, :122-124
+    DVec<float> jointTorqueCmd(12), desiredJPos(12), desiredJVel(12);
+    multitask.FindConfiguration(fullConfig, taskList, contactList, desiredJPos, desiredJVel);
+    wbic.MakeTorque(jointTorqueCmd, &extra);
+
+    for (int i = 0; i < 12; ++i) {
+        tau[i] = jointTorqueCmd[i];
+        qdes[i] = desiredJPos[i];
+        qddes[i] = desiredJVel[i];
+        fr[i] = 0;
+    }
+    int k = 0;
+    for (int leg = 0; leg < 4; ++leg)
+        if (contact[leg]) {
+            for (int i = 0; i < 3; ++i) fr[3 * leg + i] = extra.optimalFr[3 * k + i];
+            ++k;
+        }
+    if (dbg) {   // H(324, row-major) G(18) C(18) Jc feet(4*54) Jcdqd(12) pGC(12) vGC(12) -- qdd(18) not exposed
+        float* o = dbg;
+        const DMat<float>& H = fb.getMassMatrix();
+        for (int i = 0; i < 18; ++i)
+            for (int j = 0; j < 18; ++j) *o++ = H(i, j);
+        for (int i = 0; i < 18; ++i) *o++ = fb.getGravityForce()[i];
+        for (int i = 0; i < 18; ++i) *o++ = fb.getCoriolisForce()[i];
+        for (int l = 0; l < 4; ++l)
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 18; ++j) *o++ = fb._Jc[FOOT[l]](i, j);
+        for (int l = 0; l < 4; ++l)
+            for (int i = 0; i < 3; ++i) *o++ = fb._Jcdqd[FOOT[l]][i];
+        for (int l = 0; l < 4; ++l)
+            for (int i = 0; i < 3; ++i) *o++ = fb._pGC[FOOT[l]][i];
+        for (int l = 0; l < 4; ++l)
+            for (int i = 0; i < 3; ++i) *o++ = fb._vGC[FOOT[l]][i];
+        for (int i = 0; i < 18; ++i) *o++ = 0.f;
+    }
+    return 0;
+}

@@ -103,6 +103,66 @@ def test_oracle_reproduces_wbc_golden(path, oracle, pkg):
 
 
 # ---------------------------------------------------------------------------------------------
+# PIN: the reference's own WBC classes compiled unmodified from /root/reference (oracle/_ref)
+# ---------------------------------------------------------------------------------------------
+def _relmax(a, b):
+    return np.abs(np.asarray(a, float) - np.asarray(b, float)).max() / max(np.abs(np.asarray(b, float)).max(), 1e-9)
+
+
+def _check_against_reference_build(oracle, M, state, cmd, contact, what):
+    """Float32 reference build vs the float64 restatement: agreement at float32 rounding level.  Measured
+    worst cases: dynamics 5e-7 of the largest entry, tau / fr 2e-6, qdes 3e-6, qddes 2e-5 (the kinematic
+    WBC chains four float32 pseudo-inverses)."""
+    ref = oracle.wbc_step(M, state, cmd, contact, "ref")
+    f64 = oracle.wbc_step(M, state, cmd, contact, "f64")
+    f32 = oracle.wbc_step(M, state, cmd, contact, "f32")
+    for f in ("H", "G", "C", "Jc", "Jcdqd", "pGC", "vGC"):
+        assert _relmax(ref[f], f64[f]) < 3e-6, (what, f, _relmax(ref[f], f64[f]))
+    for f, tol in (("tau", 2e-5), ("fr", 2e-5), ("qdes", 2e-5), ("qddes", 1e-4)):   # BASELINE form: rel + 1e-5 abs
+        r_ = ref[f].astype(float)
+        bound = tol * np.abs(r_).max() + 1e-5
+        assert np.abs(f64[f] - r_).max() <= bound, (what, f, np.abs(f64[f] - r_).max(), bound)
+        # the float32 restatement is as close to the reference build as float32 allows
+        assert np.abs(f32[f] - r_).max() <= bound, (what, f, "f32")
+    swing = np.repeat(np.asarray(contact) == 0, 3)
+    assert (ref["fr"][swing] == 0).all()
+    return ref
+
+
+@pytest.mark.parametrize("path", wbc_goldens(), ids=os.path.basename)
+def test_wbc_restatement_matches_reference_source_on_golden(path, oracle, pkg):
+    """FloatingBaseModel<float>, qrSingleContact, the three tasks, qrMultitaskProjection and
+    qrWholeBodyImpulseCtrl (with QuadProg++) of the reference, compiled from their own source files, on the
+    golden inputs; the committed golden torques are within the BASELINE tolerance of what the reference
+    build returns."""
+    if not oracle.ref_wbc_available():
+        pytest.skip("oracle/_ref/libqr_wbc_ref.so not built (needs /root/reference at build time)")
+    z, b = load_wbc_golden(path, pkg)
+    M = oracle.wbc_model_of(b["robot"])
+    for i in range(b["state"].shape[0]):
+        ref = _check_against_reference_build(oracle, M, b["state"][i], b["cmd"][i], b["contact"][i], (path, i))
+        t = ref["tau"].astype(float)
+        assert np.abs(z["tau_f64"][i] - t).max() <= 1e-4 * np.abs(t).max() + 1e-5
+
+
+def test_wbc_restatement_matches_reference_source_all_contact_patterns(oracle, pkg):
+    if not oracle.ref_wbc_available():
+        pytest.skip("oracle/_ref/libqr_wbc_ref.so not built (needs /root/reference at build time)")
+    for robot, seed in (("a1", 311), ("lite3", 312)):
+        b = pkg.synth.make_wbc_batch(robot, 32, seed=seed)
+        pats = [[0, 0, 0, 0], [1, 0, 0, 0], [0, 0, 1, 0], [1, 1, 0, 0], [1, 0, 0, 1], [0, 1, 1, 0], [1, 1, 1, 0], [1, 1, 1, 1]]
+        for i, p in enumerate(pats * 4):
+            b["contact"][i] = p
+            b["cmd"][i, 51:63] *= np.repeat(np.array(p, np.float32), 3)
+        # a quarter of the instances ask for forces far outside the friction pyramid (active QP constraints)
+        b["cmd"][24:, 51:63] *= np.float32(3.0)
+        b["cmd"][24:, 51:63:3] += np.float32(40.0) * (b["cmd"][24:, 53:63:3] != 0)
+        M = oracle.wbc_model_of(b["robot"])
+        for i in range(32):
+            _check_against_reference_build(oracle, M, b["state"][i], b["cmd"][i], b["contact"][i], (robot, i))
+
+
+# ---------------------------------------------------------------------------------------------
 # device sources on the CPU (host emulation)
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("path", wbc_goldens(), ids=os.path.basename)
