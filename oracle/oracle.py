@@ -116,6 +116,25 @@ def ref_mpc_solve(P: MpcParams, batch: dict, i: int):
     return H, g, ub, x
 
 
+def ref_mpc_time_batch(P: MpcParams, batch: dict, lo: int, hi: int, want_x: bool = False):
+    """Times the reference's own SolveMPCKernel + GetMPCSolution(0..11) (oracle/_ref/libqr_mpc_ref.so) on
+    problems [lo, hi) in this process, SetupProblem once.  Returns (seconds, lat, x12)."""
+    global _REF
+    if _REF is None:
+        _REF = C.CDLL(os.path.join(_HERE, "_ref", "libqr_mpc_ref.so"))
+    _REF.qr_ref_mpc_time_batch.restype = C.c_double
+    cnt = hi - lo
+    lat = np.empty(cnt)
+    x = np.empty((cnt, 12)) if want_x else None
+    params = np.array([P.dt, P.mu, P.f_max, P.mass, P.alpha], np.float64)
+    inertia = np.array(P.inertia[:], np.float32)
+    weights = np.array(P.weights[:], np.float32)
+    arrs = [np.ascontiguousarray(batch[k][lo:hi], np.float32) for k in ("p", "v", "quat", "w", "r_feet", "rpy", "traj", "gait")]
+    sec = _REF.qr_ref_mpc_time_batch(P.horizon, _dp(params), _fp(inertia), _fp(weights), cnt, *[_fp(a) for a in arrs],
+                                     _dp(x) if want_x else None, _dp(lat))
+    return sec, lat, x
+
+
 def mpc_qpoases(h: int, mu: float, H, g, ub, nWSR: int = 100000):
     """The reference's qpOASES call on float32 QP data.  Returns x, info(rval, nWSR), kkt, cstat."""
     n, m = 12 * h, 20 * h
