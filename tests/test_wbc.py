@@ -288,6 +288,24 @@ def test_gpu_wbc_batch_1024_vs_emulation_and_oracle(gpu, emul, oracle, pkg):
 
 
 @pytest.mark.gpu
+def test_gpu_wbc_vs_reference_source_build(gpu, oracle, pkg):
+    """The CUDA path against the reference's OWN WBC classes compiled from /root/reference
+    (oracle/_ref/libqr_wbc_ref.so travels to the GPU box): BASELINE tolerance 1e-4 rel / 1e-5 abs, norm-wise."""
+    if not oracle.ref_wbc_available():
+        pytest.skip("oracle/_ref/libqr_wbc_ref.so not built")
+    for robot, seed in (("a1", 321), ("lite3", 322)):
+        b = pkg.synth.make_wbc_batch(robot, 256, seed=seed)
+        r = gpu_wbc(gpu, b)
+        assert (r["status"] == 0).all()
+        M = oracle.wbc_model_of(b["robot"])
+        for i in range(0, 256, 5):
+            ref = oracle.wbc_step(M, b["state"][i], b["cmd"][i], b["contact"][i], "ref")
+            for f in FIELDS:
+                t = ref[f].astype(float)
+                assert np.abs(r[f][i] - t).max() <= 1e-4 * np.abs(t).max() + 1e-5, (robot, i, f)
+
+
+@pytest.mark.gpu
 def test_gpu_swing_parabola(gpu, oracle):
     import torch
     rng = np.random.default_rng(6)
