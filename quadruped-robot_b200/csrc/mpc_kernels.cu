@@ -41,14 +41,17 @@ __global__ void qr_mpc_classify_kernel(const QrMpcArgs A, int nclass, int* count
 
 // Fused SolveMPCKernel + GetMPCSolution.  Persistent CTAs; instances are handed out through an
 // atomic ticket so that the varying number of active-set rounds per instance balances out.
+// The workspace capacity (size class) is a template parameter: all shared-memory pointers of the solver
+// become compile-time offsets, which removes their re-computation from every inner loop.
+template <int CAP, bool HSG>
 __global__ void __launch_bounds__(QR_NT, 512 / QR_NT) qr_mpc_fused_kernel(const QrMpcArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_ticket;
     constexpr int NT = QR_NT;
     QrMpcSmem S;
-    qr_mpc_carve(S, smem, A.nfcap, A.P.horizon, A.scratch + (size_t)blockIdx.x * qr_fallback_doubles(A.nfcap),
-                 A.hs_global ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr);
-    qr_mpc_init_tables<NT>(S, A.nfcap);
+    qr_mpc_carve(S, smem, CAP, A.P.horizon, A.scratch + (size_t)blockIdx.x * qr_fallback_doubles(CAP),
+                 HSG ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(CAP) : nullptr);
+    qr_mpc_init_tables<NT>(S, CAP);
     const int total = A.count ? *A.count : A.batch;
     for (;;) {
         if (threadIdx.x == 0) s_ticket = atomicAdd(A.next, 1);
@@ -57,6 +60,24 @@ __global__ void __launch_bounds__(QR_NT, 512 / QR_NT) qr_mpc_fused_kernel(const 
         __syncthreads();
         if (k >= total) break;
         qr_mpc_solve_problem<NT>(A, A.list ? A.list[k] : k, S);
+    }
+}
+
+typedef void (*QrFusedKernel)(const QrMpcArgs);
+// Instantiated size classes (capacities in stance foot-steps); the Hessian moves to the L2-resident scratch
+// for the classes that do not fit two block-packed matrices in 227 KB of shared memory.
+constexpr int QR_HSG_FROM_CAP = 56;
+QrFusedKernel fused_kernel_for(int cap) {
+    switch (cap) {
+        case 8: return qr_mpc_fused_kernel<8, false>;
+        case 16: return qr_mpc_fused_kernel<16, false>;
+        case 24: return qr_mpc_fused_kernel<24, false>;
+        case 32: return qr_mpc_fused_kernel<32, false>;
+        case 40: return qr_mpc_fused_kernel<40, false>;
+        case 48: return qr_mpc_fused_kernel<48, false>;
+        case 56: return qr_mpc_fused_kernel<56, true>;
+        case 64: return qr_mpc_fused_kernel<64, true>;
+        default: return nullptr;
     }
 }
 
@@ -211,10 +232,7 @@ extern "C" void qr_gpu_shutdown(void) {
 }
 
 int num_classes(int horizon) { return (4 * horizon + QR_CLASS_STEP - 1) / QR_CLASS_STEP; }
-int class_cap(int c, int horizon) {
-    const int cap = QR_CLASS_STEP * (c + 1);
-    return cap < 4 * horizon ? cap : 4 * horizon;
-}
+int class_cap(int c, int /*horizon*/) { return QR_CLASS_STEP * (c + 1); }   // always one of the instantiated capacities
 
 int ensure_work(int nclass, int batch) {
     const size_t need = ((size_t)2 * nclass + (size_t)nclass * batch) * sizeof(int);
@@ -239,7 +257,7 @@ extern "C" int qr_gpu_mpc_occupancy(int horizon, int stance_footsteps, int* sm_c
     int grid = 0, occ = 0;
     size_t smem = 0;
     bool hsg = false;
-    int rc = launch_geometry(qr_mpc_fused_kernel, class_cap(c, horizon), horizon, 1 << 30, &grid, &smem, &occ, &hsg);
+    int rc = launch_geometry(fused_kernel_for(class_cap(c, horizon)), class_cap(c, horizon), horizon, 1 << 30, &grid, &smem, &occ, &hsg);
     if (rc) return rc;
     if (sm_count) *sm_count = g_ctx.sm_count;
     if (ctas_per_sm) *ctas_per_sm = occ;
@@ -273,8 +291,9 @@ extern "C" int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_option
     bool hsg[16];
     size_t scratch_need = 0;
     for (int c = 0; c < nclass; ++c) {
-        rc = launch_geometry(qr_mpc_fused_kernel, class_cap(c, h), h, batch, &grid[c], &smem[c], nullptr, &hsg[c]);
+        rc = launch_geometry(fused_kernel_for(class_cap(c, h)), class_cap(c, h), h, batch, &grid[c], &smem[c], nullptr, &hsg[c]);
         if (rc) return rc;
+        if (hsg[c] != (class_cap(c, h) >= QR_HSG_FROM_CAP)) return fail(QR_EINVAL, "unexpected shared-memory capacity for this size class");
         size_t need = (size_t)grid[c] * qr_fallback_doubles(class_cap(c, h));
         if (hsg[c]) need += (size_t)grid[c] * 9 * qr_ntri(class_cap(c, h));
         if (need > scratch_need) scratch_need = need;
@@ -303,15 +322,12 @@ extern "C" int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_option
     if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_classify_kernel", e);
     // largest workspaces first: their instances take longest
     for (int c = nclass - 1; c >= 0; --c) {
-        // the attribute is per function: re-assert this class's dynamic shared memory size
-        e = cudaFuncSetAttribute(qr_mpc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem[c]);
-        if (e != cudaSuccess) return fail(QR_ECUDA, "cudaFuncSetAttribute", e);
         A.nfcap = class_cap(c, h);
         A.hs_global = hsg[c] ? g_ctx.scratch + (size_t)grid[c] * qr_fallback_doubles(A.nfcap) : nullptr;
         A.list = lists + (size_t)c * batch;
         A.count = counts + c;
         A.next = tickets + c;
-        qr_mpc_fused_kernel<<<grid[c], QR_NT, smem[c], st>>>(A);
+        fused_kernel_for(A.nfcap)<<<grid[c], QR_NT, smem[c], st>>>(A);
         e = cudaGetLastError();
         if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_fused_kernel", e);
     }

@@ -46,7 +46,7 @@ QR_HD size_t qr_mpc_smem_bytes(int nfcap, int horizon, bool hs_in_smem = true) {
     bytes += (size_t)(9 + 9 + 6 * 3 + 1) * nfcap * sizeof(double) + 8 * sizeof(double);
     bytes += (size_t)(16 * horizon + 32) * sizeof(float);          // staged traj + gait + state rows
     bytes += (size_t)(3 * nfcap + (nfcap + 1) + 3 * nfcap + 2 * 4 * horizon + 8) * sizeof(int);
-    bytes += (size_t)qr_ntri(nfcap) * sizeof(unsigned short);
+    bytes += (size_t)((qr_ntri(nfcap) + 1) / 2) * sizeof(int);         // tri (unsigned short, padded to ints)
     return (bytes + 15) & ~(size_t)15;
 }
 
@@ -77,20 +77,24 @@ QR_DEV void qr_mpc_carve(QrMpcSmem& S, unsigned char* base, int nfcap, int horiz
     W.dx = d; d += n;
     W.ubz = d; d += nfcap;
     S.scal = d; d += 8;
-    float* f = reinterpret_cast<float*>(d);
-    S.traj = f; f += 12 * horizon;
-    S.gait = f; f += 4 * horizon;
-    S.state = f; f += 32;
-    int* ip = reinterpret_cast<int*>(f);
+    // fixed-size integer tables first, the horizon-dependent rows last: with a compile-time capacity every
+    // pointer of the solver is then a constant offset from the shared-memory base
+    int* ip = reinterpret_cast<int*>(d);
     W.act = ip; ip += nfcap;
     W.flag = ip; ip += nfcap;
     W.vert = ip; ip += nfcap;
     W.foff = ip; ip += nfcap + 1;
     W.rfoot = ip; ip += 3 * nfcap;
-    S.fs = ip; ip += 4 * horizon;
-    S.slot = ip; ip += 4 * horizon;
     S.misc = ip; ip += 8;
     W.tri = reinterpret_cast<unsigned short*>(ip);
+    ip += (qr_ntri(nfcap) + 1) / 2;
+    float* f = reinterpret_cast<float*>(ip);
+    S.state = f; f += 32;
+    S.traj = f; f += 12 * horizon;
+    S.gait = f; f += 4 * horizon;
+    ip = reinterpret_cast<int*>(f);
+    S.fs = ip; ip += 4 * horizon;
+    S.slot = ip; ip += 4 * horizon;
     // interior-point fallback vectors (global)
     double* gsc = fallback;
     W.x = gsc; gsc += n; W.dxa = gsc; gsc += n; W.rd = gsc; gsc += n; W.yv = gsc; gsc += n;

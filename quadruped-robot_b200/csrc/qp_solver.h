@@ -30,6 +30,10 @@
 #include "qr_team.h"
 #include "../../include/qr_gpu.h"
 
+#ifndef QR_TRACE_ROUND
+#define QR_TRACE_ROUND(round, nred, W) ((void)0)   // scratch analysis hook (host emulation only)
+#endif
+
 struct QrQpWork {
     int nf;             // stance foot-steps
     double mu_;         // 1/mu as the reference rounds it (float32 value)
@@ -113,6 +117,24 @@ QR_DEV double qr_sym_matvec_row_capped(const double* Hs, const double* p, const 
     return acc;
 }
 
+// 1/d for a positive normal d.  Device: hardware seed (rcp.approx, about 20 bits) refined by two Newton steps
+// to double precision -- a 60-cycle dependent chain instead of the ~130 of the IEEE division subroutine; it
+// sits on the critical path of every factorisation step.
+QR_DEV double qr_rcp_pos(double d) {
+#ifdef QR_ON_DEVICE
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / d;
+#endif
+}
+
 // Inverse of a symmetric positive definite 3x3 block [a b c; b d e; c e f] by its adjugate: one
 // reciprocal and no square root, so the dependent chain is short (cofactors -> determinant -> 1/det).
 // Written as a full symmetric 3x3 (row-major) to o[0..8].  A non-positive determinant is clamped
@@ -122,7 +144,7 @@ QR_DEV void qr_inv3_sym(double a, double b, double c, double d, double e, double
     const double c11 = a * f - c * c, c12 = b * c - a * e, c22 = a * d - b * b;
     double det = a * c00 + b * c01 + c * c02;
     if (!(det > 1e-300)) det = 1e-300;
-    const double r = 1.0 / det;
+    const double r = qr_rcp_pos(det);
     o[0] = c00 * r; o[1] = c01 * r; o[2] = c02 * r;
     o[3] = o[1];    o[4] = c11 * r; o[5] = c12 * r;
     o[6] = o[2];    o[7] = o[5];    o[8] = c22 * r;
@@ -226,10 +248,61 @@ QR_DEV void qr_ldl_forward(QrQpWork& W, int nb QR_PROF_ARG) {
 
 // Backward substitution: out = L'^{-1} D^{-1} W.wv, i.e. x_K = Dinv_K (y_K - sum_{I>K} W_IK' x_I).
 // In place on W.wv (a step reads block Kc and updates blocks J < Kc).
+//
+// On the device, systems of up to 32 blocks are solved by ONE warp without any CTA barrier: lane J keeps
+// block row J of the right-hand side in registers, the pivot row's solution travels by warp shuffle and
+// the next step's tile W_KJ is fetched while the current one is applied (one step is a dependent chain of
+// about 75 cycles instead of a shared-memory round trip plus a CTA barrier).
 template <int NT>
 QR_DEV void qr_ldl_backward(QrQpWork& W, int nb, double* out QR_PROF_ARG) {
     const double* K = W.K;
     double* y = W.wv;
+#ifdef QR_ON_DEVICE
+    if (NT >= 32 && nb <= 32) {
+#ifdef QR_EXP_REPEAT
+        for (int rep_ = 0; rep_ < QR_EXP_REPEAT; ++rep_)
+#endif
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            const int me = lane < nb ? lane : 0;
+            double y0 = y[3 * me], y1 = y[3 * me + 1], y2 = y[3 * me + 2];
+            const double* Di = W.Dinv + 9 * me;
+            const double d0 = Di[0], d1 = Di[1], d2 = Di[2], d4 = Di[4], d5 = Di[5], d8 = Di[8];
+            double b[9];
+            {
+                const double* blk = K + qr_blk(nb - 1, lane < nb - 1 ? lane : 0);
+#pragma unroll
+                for (int e = 0; e < 9; ++e) b[e] = blk[e];
+            }
+            for (int Kc = nb - 1; Kc >= 0; --Kc) {
+                // every lane forms Dinv*y of its own row; only lane Kc's is final and gets broadcast
+                const double x0 = d0 * y0 + d1 * y1 + d2 * y2;
+                const double x1 = d1 * y0 + d4 * y1 + d5 * y2;
+                const double x2 = d2 * y0 + d5 * y1 + d8 * y2;
+                double n[9];
+                if (Kc > 0) {
+                    const double* blk = K + qr_blk(Kc - 1, lane < Kc - 1 ? lane : 0);
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) n[e] = blk[e];
+                }
+                const double bx0 = __shfl_sync(0xffffffffu, x0, Kc);
+                const double bx1 = __shfl_sync(0xffffffffu, x1, Kc);
+                const double bx2 = __shfl_sync(0xffffffffu, x2, Kc);
+                if (lane == Kc) { out[3 * Kc] = bx0; out[3 * Kc + 1] = bx1; out[3 * Kc + 2] = bx2; }
+                if (lane < Kc) {
+                    y0 -= b[0] * bx0 + b[3] * bx1 + b[6] * bx2;
+                    y1 -= b[1] * bx0 + b[4] * bx1 + b[7] * bx2;
+                    y2 -= b[2] * bx0 + b[5] * bx1 + b[8] * bx2;
+                }
+#pragma unroll
+                for (int e = 0; e < 9; ++e) b[e] = n[e];
+            }
+        }
+        QR_SYNC();
+        QR_PROF(13);
+        return;
+    }
+#endif
     for (int Kc = nb - 1; Kc >= 0; --Kc) {
         const double* Di = W.Dinv + 9 * Kc;
         QR_FOR(idx, 3 * (Kc + 1)) {
@@ -340,6 +413,7 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
         QR_PROF(3);
         const int nred = W.foff[nf];
         const int nbr = (nred + 2) / 3;
+        QR_TRACE_ROUND(round, nred, W);
         // ---- reduced matrix (Z'HZ), padded to a multiple of 3 with identity; right-hand side
         QR_FOR(idx, 9 * ((nbr * (nbr + 1)) / 2)) {
             const int b = idx / 9, e = idx - 9 * b;

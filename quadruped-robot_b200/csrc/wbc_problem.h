@@ -673,7 +673,8 @@ QR_DEV int qr_wbc_qp_and_torque(const QrWbcModelDev& M, const qr_qp_options& opt
         Q.mu_ = 1.0 / M.mu;
         int it = 0, rounds = 0;
         const double* x = Q.xn;
-        status = qr_qp_solve<NT>(Q, opt, &it, &rounds, &x);
+        QR_PROF_DECL;
+        status = qr_qp_solve<NT>(Q, opt, &it, &rounds, &x QR_PROF_PASS);
         f = x;
     }
     // qdd[0:6] += da ; tau = (A qdd + C + G - JC' f)[6:18]
