@@ -26,14 +26,14 @@
 
 #define QR_HMAX QR_MAX_HORIZON
 
-// Shared-memory tables of one problem (about 6.5 KB).
+struct alignas(16) QrF4 { float x, y, z, w; };
+
+// Shared-memory tables of one problem (about 8 KB).
 struct QrCondenseTables {
-    float G02[QR_HMAX][3][12];   // rows 0..2 of G_k
-    float TG02[QR_HMAX][3][12];  // ... times 2*w[row]
+    QrF4 Gx[QR_HMAX][12];        // {G_k(0,c), G_k(1,c), G_k(2,c), G_k(3+a, 3b+a)}: rows 0..2 of column c, and gpos[k]
+    QrF4 TGx[QR_HMAX][12];       // the same times 2*w[row]: {TG02[k][0..2][c], tgpos[k][c % 3]}
     float G68[3][12];            // rows 6..8 of G_k (k independent) = dt * Iw^-1 [r]x
     float TG68[3][12];
-    float gpos[QR_HMAX];         // G_k(3+a, 3b+a)
-    float tgpos[QR_HMAX][3];
     float gvel;                  // G_k(9+a, 3b+a) = dt/m
     float tgvel[3];
     float e[QR_HMAX][12];        // (Aqp x0 - X_d), rows 0..11 of every step
@@ -149,17 +149,18 @@ QR_DEV void qr_condense_tables(const qr_mpc_params& P, const float* traj, QrCond
         s = QR_FADD(s, QR_FMUL(T.prot[k][3 * i + 0], T.G68[0][j]));
         s = QR_FADD(s, QR_FMUL(T.prot[k][3 * i + 1], T.G68[1][j]));
         s = QR_FADD(s, QR_FMUL(T.prot[k][3 * i + 2], T.G68[2][j]));
-        T.G02[k][i][j] = s;
-        T.TG02[k][i][j] = QR_FMUL(s, T.w2[i]);
+        (&T.Gx[k][j].x)[i] = s;
+        (&T.TGx[k][j].x)[i] = QR_FMUL(s, T.w2[i]);
     }
     QR_FOR(idx, 36) {
         const int i = idx / 12, j = idx % 12;
         T.TG68[i][j] = QR_FMUL(T.G68[i][j], T.w2[6 + i]);
     }
-    QR_FOR(k, h) {
+    QR_FOR(idx, h * 12) {
+        const int k = idx / 12, c = idx % 12;
         const float gp = QR_FADD(T.bpos, QR_FMUL(T.ppos[k], T.gvel));
-        T.gpos[k] = gp;
-        for (int a = 0; a < 3; ++a) T.tgpos[k][a] = QR_FMUL(gp, T.w2[3 + a]);
+        T.Gx[k][c].w = gp;
+        T.TGx[k][c].w = QR_FMUL(gp, T.w2[3 + c % 3]);
     }
     QR_FOR(a, 3) { T.tgvel[a] = QR_FMUL(T.gvel, T.w2[9 + a]); }
     // e = Aqp*x0 - X_d, rows 0..11 of step j use Adt^(j+1)   (:411-412, :382-385)
@@ -184,22 +185,30 @@ QR_DEV void qr_condense_tables(const qr_mpc_params& P, const float* traj, QrCond
     }
 }
 
-// One float32 entry of qH: row 12*i + 3*la + aa, column 12*j + 3*lb + ab  (:411).
+// One float32 entry of qH: row 12*i + 3*la + aa, column 12*j + 3*lb + ab  (:411).  The terms of rows 6..11
+// do not depend on r: their float32 products are formed once and added in the reference's position.
 QR_DEV float qr_condense_h_entry(const QrCondenseTables& T, int h, int i, int la, int aa, int j,
                                  int lb, int ab) {
     const int ca = 3 * la + aa, cb = 3 * lb + ab;
     const bool same_axis = (aa == ab);
+    const float p6 = QR_FMUL(T.TG68[0][ca], T.G68[0][cb]);
+    const float p7 = QR_FMUL(T.TG68[1][ca], T.G68[1][cb]);
+    const float p8 = QR_FMUL(T.TG68[2][ca], T.G68[2][cb]);
+    const float pv = QR_FMUL(T.tgvel[aa], T.gvel);
     float s = 0.f;
-    for (int r = (i > j ? i : j); r < h; ++r) {
-        const int ki = r - i, kj = r - j;
-        s = QR_FADD(s, QR_FMUL(T.TG02[ki][0][ca], T.G02[kj][0][cb]));
-        s = QR_FADD(s, QR_FMUL(T.TG02[ki][1][ca], T.G02[kj][1][cb]));
-        s = QR_FADD(s, QR_FMUL(T.TG02[ki][2][ca], T.G02[kj][2][cb]));
-        if (same_axis) s = QR_FADD(s, QR_FMUL(T.tgpos[ki][aa], T.gpos[kj]));
-        s = QR_FADD(s, QR_FMUL(T.TG68[0][ca], T.G68[0][cb]));
-        s = QR_FADD(s, QR_FMUL(T.TG68[1][ca], T.G68[1][cb]));
-        s = QR_FADD(s, QR_FMUL(T.TG68[2][ca], T.G68[2][cb]));
-        if (same_axis) s = QR_FADD(s, QR_FMUL(T.tgvel[aa], T.gvel));
+    const int r0 = (i > j ? i : j);
+    const QrF4* tg = &T.TGx[r0 - i][ca];
+    const QrF4* gg = &T.Gx[r0 - j][cb];
+    for (int r = r0; r < h; ++r, tg += 12, gg += 12) {
+        const QrF4 a = *tg, b = *gg;
+        s = QR_FADD(s, QR_FMUL(a.x, b.x));
+        s = QR_FADD(s, QR_FMUL(a.y, b.y));
+        s = QR_FADD(s, QR_FMUL(a.z, b.z));
+        if (same_axis) s = QR_FADD(s, QR_FMUL(a.w, b.w));
+        s = QR_FADD(s, p6);
+        s = QR_FADD(s, p7);
+        s = QR_FADD(s, p8);
+        if (same_axis) s = QR_FADD(s, pv);
     }
     if (i == j && ca == cb) s = QR_FADD(s, T.two_alpha);
     return s;
@@ -210,11 +219,11 @@ QR_DEV float qr_condense_g_entry(const QrCondenseTables& T, int h, int i, int la
     const int ca = 3 * la + aa;
     float s = 0.f;
     for (int j = i; j < h; ++j) {
-        const int k = j - i;
-        s = QR_FADD(s, QR_FMUL(T.TG02[k][0][ca], T.e[j][0]));
-        s = QR_FADD(s, QR_FMUL(T.TG02[k][1][ca], T.e[j][1]));
-        s = QR_FADD(s, QR_FMUL(T.TG02[k][2][ca], T.e[j][2]));
-        s = QR_FADD(s, QR_FMUL(T.tgpos[k][aa], T.e[j][3 + aa]));
+        const QrF4 a = T.TGx[j - i][ca];
+        s = QR_FADD(s, QR_FMUL(a.x, T.e[j][0]));
+        s = QR_FADD(s, QR_FMUL(a.y, T.e[j][1]));
+        s = QR_FADD(s, QR_FMUL(a.z, T.e[j][2]));
+        s = QR_FADD(s, QR_FMUL(a.w, T.e[j][3 + aa]));
         s = QR_FADD(s, QR_FMUL(T.TG68[0][ca], T.e[j][6]));
         s = QR_FADD(s, QR_FMUL(T.TG68[1][ca], T.e[j][7]));
         s = QR_FADD(s, QR_FMUL(T.TG68[2][ca], T.e[j][8]));

@@ -52,6 +52,10 @@ __global__ void __launch_bounds__(QR_NT, 512 / QR_NT) qr_mpc_fused_kernel(const 
     qr_mpc_carve(S, smem, CAP, A.P.horizon, A.scratch + (size_t)blockIdx.x * qr_fallback_doubles(CAP),
                  HSG ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(CAP) : nullptr);
     qr_mpc_init_tables<NT>(S, CAP);
+    if (!A.next) {   // small batches: one launch, instances strided over the grid, no work lists
+        for (int prob = blockIdx.x; prob < A.batch; prob += gridDim.x) qr_mpc_solve_problem<NT>(A, prob, S);
+        return;
+    }
     const int total = A.count ? *A.count : A.batch;
     for (;;) {
         if (threadIdx.x == 0) s_ticket = atomicAdd(A.next, 1);
@@ -116,6 +120,8 @@ struct Ctx {
     // staging buffers of the *_host entry point
     unsigned char* stage = nullptr;
     size_t stage_bytes = 0;
+    unsigned char* pin = nullptr;   // pinned host mirror of the staging buffer (small batches: one copy each way)
+    size_t pin_bytes = 0;
     cudaStream_t stream = nullptr;
     char err[256] = {0};
 };
@@ -143,9 +149,28 @@ qr_qp_options default_options() {
 // Launch geometry of one size class.  *hs_global is set when H does not fit in shared memory next to
 // the matrix under factorisation (capacities above ~44 foot-steps) and has to live in the L2-resident
 // global scratch instead.
+struct GeomEntry { const void* kern; int nfcap, horizon, occ; size_t bytes; bool hsg; };
+GeomEntry g_geom[64];
+int g_ngeom = 0;
+
 template <typename Kern>
 int launch_geometry(Kern kern, int nfcap, int horizon, int batch, int* grid, size_t* smem, int* per_sm,
                     bool* hs_global = nullptr) {
+    if (!kern) return fail(QR_EINVAL, "no kernel instantiated for this size class");
+    // attribute + occupancy queries cost microseconds each: remember them per (kernel, class, horizon)
+    for (int i = 0; i < g_ngeom; ++i) {
+        const GeomEntry& ge = g_geom[i];
+        if (ge.kern == (const void*)kern && ge.nfcap == nfcap && ge.horizon == horizon) {
+            if (hs_global) *hs_global = ge.hsg;
+            else if (ge.hsg) return fail(QR_EINVAL, "workspace does not fit in shared memory");
+            int g = g_ctx.sm_count * ge.occ;
+            if (g > batch) g = batch;
+            if (g < 1) g = 1;
+            *grid = g; *smem = ge.bytes;
+            if (per_sm) *per_sm = ge.occ;
+            return QR_OK;
+        }
+    }
     size_t bytes = qr_mpc_smem_bytes(nfcap, horizon, true);
     bool hsg = false;
     if (bytes + 1024 > g_ctx.smem_optin) {
@@ -155,12 +180,14 @@ int launch_geometry(Kern kern, int nfcap, int horizon, int batch, int* grid, siz
     if (hs_global) *hs_global = hsg;
     else if (hsg) return fail(QR_EINVAL, "workspace does not fit in shared memory");
     if (bytes > g_ctx.smem_optin) return fail(QR_EINVAL, "horizon needs more shared memory than one CTA may use");
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    // opt in to the device maximum once per kernel (the launch's own byte count decides the occupancy)
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_ctx.smem_optin - 256);
     if (e != cudaSuccess) return fail(QR_ECUDA, "cudaFuncSetAttribute", e);
     int occ = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, QR_NT, bytes);
     if (e != cudaSuccess) return fail(QR_ECUDA, "cudaOccupancyMaxActiveBlocksPerMultiprocessor", e);
     if (occ < 1) occ = 1;
+    if (g_ngeom < 64) g_geom[g_ngeom++] = GeomEntry{(const void*)kern, nfcap, horizon, occ, bytes, hsg};
     int g = g_ctx.sm_count * occ;
     if (g > batch) g = batch;
     if (g < 1) g = 1;
@@ -228,6 +255,8 @@ extern "C" void qr_gpu_shutdown(void) {
     if (g_ctx.work) cudaFree(g_ctx.work);
     if (g_ctx.stage) cudaFree(g_ctx.stage);
     if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
+    if (g_ctx.pin) cudaFreeHost(g_ctx.pin);
+    g_ngeom = 0;
     g_ctx = Ctx();
 }
 
@@ -280,6 +309,34 @@ extern "C" int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_option
         return fail(QR_EINVAL, "null input/output pointer");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int h = P->horizon, nclass = num_classes(h);
+    if (batch <= g_ctx.sm_count) {
+        // Latency path: the grid cannot fill the device anyway, so skip the classification and launch the
+        // largest size class once (its workspace holds any instance of this horizon).
+        const int cap = class_cap(nclass - 1, h);
+        int grid1 = 0;
+        size_t smem1 = 0;
+        bool hsg1 = false;
+        rc = launch_geometry(fused_kernel_for(cap), cap, h, batch, &grid1, &smem1, nullptr, &hsg1);
+        if (rc) return rc;
+        if (hsg1 != (cap >= QR_HSG_FROM_CAP)) return fail(QR_EINVAL, "unexpected shared-memory capacity for this size class");
+        rc = ensure_scratch(grid1, cap, hsg1);
+        if (rc) return rc;
+        QrMpcArgs A1;
+        memset(&A1, 0, sizeof(A1));
+        A1.P = *P;
+        A1.opt = opt ? *opt : default_options();
+        A1.batch = batch;
+        A1.nfcap = cap;
+        A1.p = p; A1.v = v; A1.quat = quat; A1.w = w; A1.r_feet = r_feet; A1.rpy = rpy; A1.traj = traj; A1.gait = gait;
+        A1.mu_i = mu_i; A1.fmax_i = fmax_i;
+        A1.grf_out = grf_out; A1.u_out = u_out; A1.status_out = status_out; A1.iters_out = iters_out;
+        A1.scratch = g_ctx.scratch;
+        A1.hs_global = hsg1 ? g_ctx.scratch + (size_t)grid1 * qr_fallback_doubles(cap) : nullptr;
+        fused_kernel_for(cap)<<<grid1, QR_NT, smem1, st>>>(A1);
+        cudaError_t e1 = cudaGetLastError();
+        if (e1 != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_fused_kernel", e1);
+        return QR_OK;
+    }
     rc = ensure_work(nclass, batch);
     if (rc) return rc;
     int* counts = g_ctx.work;
@@ -435,10 +492,21 @@ extern "C" int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_o
     cudaStream_t st = g_ctx.stream;
     float* d = reinterpret_cast<float*>(g_ctx.stage);
     cudaError_t e = cudaSuccess;
+    // Small batches (latency path): gather the rows into a pinned mirror of the staging buffer so that
+    // the whole call is one host->device and one device->host copy.
+    const bool packed = bytes <= (size_t)256 * 1024;
+    if (packed && !g_ctx.pin) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        e = cudaMallocHost(&g_ctx.pin, (size_t)256 * 1024);
+        if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMallocHost(pinned stage)", e);
+        g_ctx.pin_bytes = (size_t)256 * 1024;
+    }
+    float* hp = reinterpret_cast<float*>(g_ctx.pin);
     auto up = [&](const float* src, size_t cnt) -> float* {
         float* dst = d;
         d += cnt;
-        if (src && e == cudaSuccess) e = cudaMemcpyAsync(dst, src, cnt * sizeof(float), cudaMemcpyHostToDevice, st);
+        if (src && packed) memcpy(hp + (dst - reinterpret_cast<float*>(g_ctx.stage)), src, cnt * sizeof(float));
+        else if (src && e == cudaSuccess) e = cudaMemcpyAsync(dst, src, cnt * sizeof(float), cudaMemcpyHostToDevice, st);
         return src ? dst : nullptr;
     };
     float* dp = up(p, B * 3);
@@ -451,6 +519,8 @@ extern "C" int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_o
     float* dgait = up(gait, B * 4 * h);
     float* dmu = up(mu_i, B);
     float* dfm = up(fmax_i, B);
+    if (packed && e == cudaSuccess)
+        e = cudaMemcpyAsync(g_ctx.stage, g_ctx.pin, n_in * sizeof(float), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpyAsync H2D", e);
     float* dgrf = d; d += B * 12;
     float* du = nullptr;
@@ -460,6 +530,19 @@ extern "C" int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_o
     int rc = qr_gpu_mpc_solve_batch(P, opt, batch, dp, dv, dq, dw, dr, drpy, dtraj, dgait, dmu, dfm, dgrf, du,
                                     dstat, dit, st);
     if (rc) return rc;
+    if (packed) {
+        const size_t off = n_in * sizeof(float), nout = n_out * sizeof(float) + 3 * B * sizeof(int32_t);
+        e = cudaMemcpyAsync(g_ctx.pin + off, g_ctx.stage + off, nout, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpyAsync D2H", e);
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return fail(QR_ECUDA, "cudaStreamSynchronize", e);
+        const unsigned char* hb = g_ctx.pin;
+        memcpy(grf_out, hb + ((unsigned char*)dgrf - g_ctx.stage), B * 12 * sizeof(float));
+        if (u_out) memcpy(u_out, hb + ((unsigned char*)du - g_ctx.stage), B * 12 * h * sizeof(float));
+        if (status_out) memcpy(status_out, hb + ((unsigned char*)dstat - g_ctx.stage), B * sizeof(int32_t));
+        if (iters_out) memcpy(iters_out, hb + ((unsigned char*)dit - g_ctx.stage), 2 * B * sizeof(int32_t));
+        return QR_OK;
+    }
     e = cudaMemcpyAsync(grf_out, dgrf, B * 12 * sizeof(float), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && u_out) e = cudaMemcpyAsync(u_out, du, B * 12 * h * sizeof(float), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && status_out) e = cudaMemcpyAsync(status_out, dstat, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
