@@ -52,19 +52,29 @@ struct QrWbcWork {
     QrQpWork Q;
 };
 
-QR_HD size_t qr_wbc_smem_doubles() {
-    size_t d = 37 + 66 + 36 * (13 + 12 + 13 + 13 + 12 + 12) + 6 * (13 + 12 + 12 + 12 + 13 + 12 + 13 + 12 + 13 + 12) + 24;
-    d += 324 * 2 + 18 * 2 + 36 + 18;
-    d += 4 * 54 + 12 * 3;
-    d += 6 * 54 + 6 * 12;
-    d += 12 * 18 + 12 + 12;
-    d += 324 * 3;
-    d += 216 + 216 + 144 + 144 + 216;
-    d += 216 + 144 + 12;
+// Shared-memory plan (doubles).  The spatial-algebra temporaries of the dynamics phase (transforms, composite
+// inertias, body velocities...) are dead once H, C, G and the foot Jacobians exist; the task / projector / QP
+// workspace of the later phases is laid over them.  This is what sets the number of robots in flight per SM.
+QR_HD size_t qr_wbc_dyn_doubles() {
+    return 36 * (13 + 12 + 13 + 13 + 12 + 12) + 6 * (13 + 12 + 12 + 12 + 13 + 12 + 13 + 12 + 13 + 12) + 24;
+}
+QR_HD size_t qr_wbc_late_doubles() {
+    size_t d = 6 * 54 + 6 * 12;                       // tasks
+    d += 12 * 18 + 12 + 12;                           // stacked contacts
+    d += 324 * 3;                                     // N, N2, M1
+    d += 216 + 216 + 144 + 144 + 216;                 // weighted-inverse temporaries
+    d += 216 + 144 + 12;                              // Jacobi workspace
     d += 18 * 5 + 72 + 6 + 36;
-    // QP workspace for up to 4 contact blocks (all of it in shared memory, including the fallback vectors)
-    d += 90 + 90 + 36 + 36 + 12 * 6 + 4 + 12 * 4 + 20 * 6 + 16;
-    return d + 8;
+    // QP workspace for up to 4 contact blocks (its interior-point fallback vectors reuse the Jacobi workspace)
+    d += 90 + 90 + 36 + 36 + 12 * 6 + 4;
+    return d;
+}
+QR_HD size_t qr_wbc_smem_doubles() {
+    size_t d = 37 + 66;
+    d += 324 * 2 + 18 * 2 + 36 + 18;                  // H, Ainv, G, Cq, rowbuf, colbuf
+    d += 4 * 54 + 12 * 3;                             // foot Jacobians, Jdot qdot, positions, velocities
+    const size_t a = qr_wbc_dyn_doubles(), b = qr_wbc_late_doubles();
+    return d + (a > b ? a : b) + 8;
 }
 QR_HD size_t qr_wbc_smem_bytes() { return qr_wbc_smem_doubles() * sizeof(double) + (16 + 4 * 3 + 5 + 12 + 16) * sizeof(int) + 32; }
 
@@ -72,12 +82,16 @@ QR_DEV void qr_wbc_carve(QrWbcWork& W, unsigned char* base) {
     double* d = reinterpret_cast<double*>(base);
     auto take = [&](size_t n) { double* p = d; d += n; return p; };
     W.st = take(37); W.cmd = take(66);
+    W.H = take(324); W.Ainv = take(324); W.G = take(18); W.Cq = take(18); W.rowbuf = take(36); W.colbuf = take(18);
+    W.Jc = take(4 * 54); W.Jcd = take(12); W.pF = take(12); W.vF = take(12);
+    double* const overlay = d;
+    // ---- dynamics phase
     W.Xup = take(36 * 13); W.Xur = take(36 * 12); W.Xa = take(36 * 13); W.IC = take(36 * 13); W.T1 = take(36 * 12); W.T2 = take(36 * 12);
     W.v = take(6 * 13); W.vr = take(6 * 12); W.cj = take(6 * 12); W.cr = take(6 * 12); W.avp = take(6 * 13); W.avr = take(6 * 12);
     W.ag = take(6 * 13); W.agr = take(6 * 12); W.fvp = take(6 * 13); W.fvr = take(6 * 12);
     W.sq = take(12); W.cq = take(12);
-    W.H = take(324); W.Ainv = take(324); W.G = take(18); W.Cq = take(18); W.rowbuf = take(36); W.colbuf = take(18);
-    W.Jc = take(4 * 54); W.Jcd = take(12); W.pF = take(12); W.vF = take(12);
+    // ---- later phases, over the same memory
+    d = overlay;
     W.Jt = take(6 * 54); W.xdd = take(18); W.jdq = take(18); W.perr = take(18); W.dvel = take(18);
     W.JC = take(216); W.JCd = take(12); W.fdes = take(12);
     W.N = take(324); W.N2 = take(324); W.M1 = take(324);
@@ -88,9 +102,16 @@ QR_DEV void qr_wbc_carve(QrWbcWork& W, unsigned char* base) {
     Q.Hs = take(90); Q.K = take(90); Q.Dinv = take(36); Q.zv = take(36);
     Q.ps = take(12); Q.g = take(12); Q.xn = take(12); Q.q = take(12); Q.wv = take(12); Q.dx = take(12);
     Q.ubz = take(4);
-    Q.x = take(12); Q.dxa = take(12); Q.rd = take(12); Q.yv = take(12);
-    Q.s = take(20); Q.lam = take(20); Q.dsa = take(20); Q.dla = take(20); Q.rc = take(20); Q.dl = take(20);
-    Q.red = take(16);
+    {   // the interior-point fallback vectors of the QP reuse the Jacobi workspace (all pseudo-inverses are done by then)
+        double* f = W.svdB;
+        Q.x = f; f += 12; Q.dxa = f; f += 12; Q.rd = f; f += 12; Q.yv = f; f += 12;
+        Q.s = f; f += 20; Q.lam = f; f += 20; Q.dsa = f; f += 20; Q.dla = f; f += 20; Q.rc = f; f += 20; Q.dl = f; f += 20;
+        Q.red = f;   // 16 <= 216 - 184
+    }
+    {
+        const size_t a = qr_wbc_dyn_doubles(), b = qr_wbc_late_doubles();
+        d = overlay + (a > b ? a : b);
+    }
     d += 8;
     int* ip = reinterpret_cast<int*>(d);
     W.ints = ip; ip += 16;
@@ -119,14 +140,60 @@ template <int NT> QR_DEV void tm_copy(double* D, const double* S, int n) { QR_FO
 // (pseudoInverse, include/quadruped/utils/qr_algebra.h:119-140).  One-sided Jacobi on the columns of
 // B = J' (n x m): the m/2 disjoint column pairs of a round-robin round rotate on different lanes.
 // out = pinv(J), n x m.
+//
+// Fast path.  When every singular value is safely above the threshold nothing is dropped and
+// pinv(J) = J' (J J')^-1 (or J^-1 for the symmetric positive definite J of WeightedInverse): the Gram matrix is
+// inverted by Gauss-Jordan and the bound sigma_min^2 >= 1 / ||(J J')^-1||_F certifies the rank decision with a
+// 10x margin.  Anything closer to the threshold (or singular, or non-finite) takes the Jacobi SVD below, so the
+// thresholding semantics of the reference are kept exactly where they matter.  The SVD was 63 % of the kernel.
+template <int NT> QR_DEV void tm_inverse_spd(QrWbcWork& W, double* A, int n);
 template <int NT>
-QR_DEV void tm_pinv(QrWbcWork& W, double* out, const double* J, int m, int n, double thr) {
+QR_DEV void tm_pinv(QrWbcWork& W, double* out, const double* J, int m, int n, double thr, int sym_psd = 0) {
     double* B = W.svdB;   // n x m
     double* V = W.svdV;   // m x m
     if (m == 1 && n == 1) {   // the reference's scalar special case
         QR_THREADS(t) { if (t == 0) out[0] = J[0] > thr ? 1.0 / J[0] : 0.0; }
         QR_SYNC();
         return;
+    }
+    {
+        double* Gi = V;   // m x m
+        if (sym_psd) {
+            QR_FOR(idx, m * m) Gi[idx] = J[idx];
+        } else {
+            QR_FOR(idx, m * m) {
+                const int i = idx / m, j = idx - i * m;
+                double a = 0.0;
+                for (int l = 0; l < n; ++l) a += J[i * n + l] * J[j * n + l];
+                Gi[idx] = a;
+            }
+        }
+        QR_SYNC();
+        tm_inverse_spd<NT>(W, Gi, m);
+        int bad = 0;
+        double fro = 0.0;
+        QR_THREADS(t) {
+            if (t == 0) {
+                for (int idx = 0; idx < m * m; ++idx) fro += Gi[idx] * Gi[idx];
+                const double lam_min = 1.0 / sqrt(fro);           // <= smallest eigenvalue of the inverted matrix
+                const double need = sym_psd ? 10.0 * thr : 100.0 * thr * thr;
+                bad = !(lam_min > need) || !(fro < 1e300);
+            }
+        }
+        if (!QR_ANY(bad)) {
+            if (sym_psd) {
+                QR_FOR(idx, m * m) out[idx] = Gi[idx];
+            } else {
+                QR_FOR(idx, n * m) {
+                    const int i = idx / m, l = idx - i * m;
+                    double a = 0.0;
+                    for (int j = 0; j < m; ++j) a += J[j * n + i] * Gi[j * m + l];
+                    out[idx] = a;
+                }
+            }
+            QR_SYNC();
+            return;
+        }
     }
     QR_FOR(idx, n * m) { const int i = idx / m, j = idx - i * m; B[idx] = J[j * n + i]; }
     QR_FOR(idx, m * m) V[idx] = (idx / m == idx % m) ? 1.0 : 0.0;
@@ -197,7 +264,7 @@ template <int NT>
 QR_DEV void tm_weighted_inverse(QrWbcWork& W, double* Jbar, const double* J, int m) {
     tm_mul_nt<NT>(W.tmpA, W.Ainv, J, 18, 18, m);          // 18 x m
     tm_mul<NT>(W.Lam, J, W.tmpA, m, 18, m);               // m x m
-    tm_pinv<NT>(W, W.LamInv, W.Lam, m, m, 0.0001);
+    tm_pinv<NT>(W, W.LamInv, W.Lam, m, m, 0.0001, 1);
     tm_mul<NT>(Jbar, W.tmpA, W.LamInv, 18, m, m);
 }
 
