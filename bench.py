@@ -180,6 +180,76 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def _time_ms(torch, fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def bench_wbc_and_full_step(pkg, capi, torch, stream):
+    """Reported beside the headline metric: qr_wbc_kernel throughput (Lite3, batches 1024 and 65536) and one full
+    control tick of BASELINE configs[1] (Lite3 trot: contact table + reference trajectory -> MPC -> leg torques,
+    swing-foot parabola, WBIC with the MPC forces as Fr_des), batch 1024, all resident on the device."""
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    robot = pkg.robots.ROBOTS["lite3"]
+    M = capi.wbc_model_of(robot)
+    out = {"wbc": {"kernel": "qr_wbc_kernel", "robot": "lite3", "unit": "robots/s", "arith": "float64, one warp per robot"}}
+    for B in (1024, 65536):
+        wb = pkg.synth.make_wbc_batch("lite3", B, seed=6)
+        state, cmd, contact = dev(wb["state"]), dev(wb["cmd"]), dev(wb["contact"])
+        tau = torch.empty((B, 12), device="cuda")
+        st = torch.empty(B, dtype=torch.int32, device="cuda")
+        ms = _time_ms(torch, lambda: capi.wbc_solve_batch_device(M, state, cmd, contact, tau, stream, status=st), 10)
+        out["wbc"][f"batch_{B}"] = {"value": B / ms * 1e3, "ms_per_step": ms, "status_nonzero": int((st != 0).sum())}
+    # full tick, batch 1024
+    B, h, dt = 1024, 10, 0.03
+    mb = pkg.synth.make_mpc_batch("lite3", h, dt, B, seed=11, gait="trot")
+    wb = pkg.synth.make_wbc_batch("lite3", B, seed=12)
+    P = capi.params_of(robot, h, dt)
+    gt = pkg.robots.GAITS["trot"]
+    rng = np.random.default_rng(13)
+    progress = np.mod(rng.uniform(0, 1, (B, 1)) + np.array(gt["offsets"])[None, :], 1.0).astype(np.float32)
+    duty = np.full((B, 4), gt["duty"], np.float32)
+    traj_init = np.zeros((B, 12), np.float32)
+    traj_init[:, 2] = mb["rpy"][:, 2]; traj_init[:, 3:5] = mb["p"][:, :2]; traj_init[:, 5] = robot.body_height
+    traj_init[:, 9] = 0.5
+    d = {k: dev(mb[k]) for k in KEYS}
+    d_prog, d_duty, d_init, d_xy = dev(progress), dev(duty), dev(traj_init), dev(mb["p"][:, :2])
+    o = dict(grf=torch.empty((B, 12), device="cuda"), status=torch.empty(B, dtype=torch.int32, device="cuda"),
+             iters=torch.empty((B, 2), dtype=torch.int32, device="cuda"))
+    state, cmd, contact = dev(wb["state"]), dev(wb["cmd"]), dev(wb["contact"])
+    q = state[:, 13:25].contiguous()
+    tau_mpc = torch.empty((B, 12), device="cuda")
+    tau = torch.empty((B, 12), device="cuda")
+    st = torch.empty(B, dtype=torch.int32, device="cuda")
+    sw_start, sw_end = dev(rng.uniform(-0.1, 0.1, (4 * B, 3)).astype(np.float32)), dev(rng.uniform(-0.1, 0.1, (4 * B, 3)).astype(np.float32))
+    sw_h, sw_ph = dev(np.full(4 * B, 0.08, np.float32)), dev(rng.uniform(0, 1, 4 * B).astype(np.float32))
+    sw_pos = torch.empty((4 * B, 3), device="cuda")
+    nhl = pkg.synth.num_horizon_l(gt)
+
+    def tick():
+        capi.mpc_inputs_batch_device(h, nhl, dt, d_prog, d_duty, None, None, d_init, d_xy, d["gait"], d["traj"], stream)
+        capi.mpc_solve_batch_device(P, d, o, stream)
+        capi.mpc_leg_torque_batch_device(robot, d["quat"], q, o["grf"], None, tau_mpc, stream)
+        capi.swing_parabola_batch_device(sw_start, sw_end, sw_h, sw_ph, False, sw_pos, None, stream)
+        cmd[:, 51:63] = o["grf"]   # Fr_des of qrWbcCtrlData <- MPC forces (a torch copy kernel, not one of ours)
+        capi.wbc_solve_batch_device(M, state, cmd, contact, tau, stream, status=st)
+
+    ms = _time_ms(torch, tick, 20)
+    out["full_step"] = {"workload": "Lite3 trot h=10 dt=0.03: contact table + reference trajectory -> MPC -> leg torques, "
+                                    "swing parabola, WBIC (BASELINE configs[1]), batch 1024 on the device",
+                        "value": B / ms * 1e3, "unit": "robot ticks/s", "ms_per_step": ms,
+                        "mpc_not_converged": int((o["status"] != 0).sum()), "wbc_status_nonzero": int((st != 0).sum())}
+    return out
+
+
 def run_gpu(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -291,6 +361,12 @@ def run_gpu(args, rank, local_rank, world):
         ts = np.asarray(ts[100:]) * 1e6
         lat = {"batch": 1, "p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)), "reps": 1000}
 
+    # ---- the other half of the hot path (rank 0, N = 1): the WBC kernel alone and BASELINE configs[1], one full
+    # MPC + WBIC tick for a batch of robots, everything on the device
+    extra = None
+    if rank == 0 and world == 1:
+        extra = bench_wbc_and_full_step(pkg, capi, torch, stream)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -341,6 +417,7 @@ def run_gpu(args, rank, local_rank, world):
                           f"stock nWSR=100, {_kind_text(r['kind'])}, one pinned process per core"),
                "p50_ms": r["p50_ms"], "p99_ms": r["p99_ms"]}
 
+    n_size_classes = (4 * h + 7) // 8
     occ = capi.occupancy(h, int(round(float((sets_host[0]['gait'] > 0).sum(axis=1).mean()))))
     line = {
         "metric": METRIC, "value": value, "unit": "QP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -355,11 +432,13 @@ def run_gpu(args, rank, local_rank, world):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "QP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "qr_gpu_mpc_solve_batch_host (pinned host buffers, H2D + kernel + D2H + stream sync per step)"},
-        "gpu_launches": args.steps,
+        "gpu_launches": args.steps * (1 + n_size_classes),   # per step: qr_mpc_classify_kernel + one qr_mpc_fused_kernel per size class
         "roofline": roofline,
         "cpu_baseline": cpu,
         "latency": lat,
     }
+    if extra:
+        line.update(extra)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
