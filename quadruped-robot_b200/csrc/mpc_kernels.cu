@@ -52,17 +52,16 @@ __global__ void __launch_bounds__(QR_NT, 512 / QR_NT) qr_mpc_fused_kernel(const 
     qr_mpc_carve(S, smem, CAP, A.P.horizon, A.scratch + (size_t)blockIdx.x * qr_fallback_doubles(CAP),
                  HSG ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(CAP) : nullptr);
     qr_mpc_init_tables<NT>(S, CAP);
-    if (!A.next) {   // small batches: one launch, instances strided over the grid, no work lists
-        for (int prob = blockIdx.x; prob < A.batch; prob += gridDim.x) qr_mpc_solve_problem<NT>(A, prob, S);
-        return;
-    }
+    // A.next == null (small batches): one launch, instances strided over the grid, no work lists.
     const int total = A.count ? *A.count : A.batch;
+    int strided = blockIdx.x;
     for (;;) {
-        if (threadIdx.x == 0) s_ticket = atomicAdd(A.next, 1);
+        if (A.next && threadIdx.x == 0) s_ticket = atomicAdd(A.next, 1);
         __syncthreads();
-        const int k = s_ticket;
+        const int k = A.next ? s_ticket : strided;
         __syncthreads();
         if (k >= total) break;
+        strided += gridDim.x;
         qr_mpc_solve_problem<NT>(A, A.list ? A.list[k] : k, S);
     }
 }

@@ -177,7 +177,7 @@ QR_DEV void tm_pinv(QrWbcWork& W, double* out, const double* J, int m, int n, do
                 for (int idx = 0; idx < m * m; ++idx) fro += Gi[idx] * Gi[idx];
                 const double lam_min = 1.0 / sqrt(fro);           // <= smallest eigenvalue of the inverted matrix
                 const double need = sym_psd ? 10.0 * thr : 100.0 * thr * thr;
-                bad = !(lam_min > need) || !(fro < 1e300);
+                bad = !(lam_min > need) || !(fro < 1e300) || !(fro > 0.0);
             }
         }
         if (!QR_ANY(bad)) {
@@ -243,9 +243,21 @@ QR_DEV void tm_pinv(QrWbcWork& W, double* out, const double* J, int m, int n, do
 // (GetModelRes: Ainv = A.inverse(), qr_wholebody_impulse_ctrl.cpp:50-58).
 template <int NT>
 QR_DEV void tm_inverse_spd(QrWbcWork& W, double* A, int n) {
+    if (n == 3) {   // task-sized blocks: adjugate, one phase
+        double o[9];
+        QR_THREADS(t) {
+            if (t == 0) {
+                qr_inv3_sym(A[0], A[3], A[6], A[4], A[7], A[8], o);
+                for (int e = 0; e < 9; ++e) A[e] = o[e];
+            }
+        }
+        QR_SYNC();
+        return;
+    }
     for (int k = 0; k < n; ++k) {
         QR_FOR(c, n) {
-            const double piv = 1.0 / A[k * n + k];
+            const double akk = A[k * n + k];
+            const double piv = akk > 1e-300 ? qr_rcp_pos(akk) : 1.0 / akk;   // positive pivots: Newton reciprocal
             W.rowbuf[c] = (c == k ? 1.0 : A[k * n + c]) * piv;
             W.colbuf[c] = A[c * n + k];
         }
