@@ -194,6 +194,44 @@ int qr_gpu_swing_parabola_batch(int batch, const float* start, const float* end,
                                 const float* phase, int phase_module, float* pos_out, int32_t* valid_out,
                                 void* cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Force-balance stance controller
+ * ------------------------------------------------------------------------------------------------- */
+
+/* Parameters of Quadruped::ComputeContactForce
+ * (include/quadruped/controllers/balance_controller/qr_qp_torque_optimizer.h:145-153, 172-183; defaults there:
+ * regWeight 1e-4, frictionCoef 0.5 (control frame) / 0.45, fMinRatio 0.01, fMaxRatio 10). */
+typedef struct {
+    float mass;           /* robot->totalMass */
+    float inertia[9];     /* row-major 3x3, used when the per-robot `inertia` array is NULL */
+    float acc_weight[6];  /* accWeight */
+    float reg_weight;     /* regWeight */
+    float mu;             /* frictionCoef */
+    float fmin_ratio[4];  /* per leg (the control-frame overload passes one scalar: repeat it) */
+    float fmax_ratio[4];
+    int32_t world_frame;  /* 0: arithmetic of the control-frame overload (qr_qp_torque_optimizer.cpp:192-301),
+                             1: of the world-frame overload (:304-400); they differ in how lb is rounded */
+} qr_fb_params;
+
+/* qr_gpu_force_balance_batch -- replaces ComputeContactForce (qr_qp_torque_optimizer.cpp:192-400: ComputeMassMatrix,
+ * ComputeObjectiveMatrix, ComputeWeightMatrix, ComputeConstraintMatrix and the QuadProg++ solve :273-276 / :380-383),
+ * called by TorqueStanceLegController::GetAction (qr_torque_stance_leg_controller.cpp:496-500), for `batch` robots.
+ *   inertia  [batch][9] or NULL   the 3x3 matrix the reference inverts (Rcb I Rcb' resp. rotMat I rotMat')
+ *   foot     [batch][12]          footPositions.row(leg): foot positions in the frame of the computation
+ *   acc      [batch][6]           desiredAcc / desiredDdq
+ *   contact  [batch][4]           int32 0/1
+ *   gravity  [batch][3] or NULL   g.head(3) when the control frame is tilted (NULL: 0, 0, 9.8)
+ *   frame    [batch][9] or NULL   normal, tangent1, tangent2 (NULL: e_z, e_x, e_y -- the PLANE terrain)
+ *   force_out [batch][12]         X(leg, axis) = -x: the matrix the reference then rotates back ((X*Rcb)' resp.
+ *                                 RigidTransform); that frame change stays with the caller
+ *   status_out [batch] or NULL    0 optimal; 1 the solver met an infeasible row and the iterate at that point is
+ *                                 returned (what the reference does with QuadProg++'s result: a leg in swing asks for
+ *                                 n.x >= 1e-7 and -n.x >= 1e-7 at once); 2 iteration cap; 3 not solvable, forces zeroed
+ * Device pointers, asynchronous on the stream. */
+int qr_gpu_force_balance_batch(const qr_fb_params* P, int batch, const float* inertia, const float* foot,
+                               const float* acc, const int32_t* contact, const float* gravity, const float* frame,
+                               float* force_out, int32_t* status_out, int32_t* iters_out, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -337,3 +337,38 @@ def grf_to_torque(robot, quat, q, f_world):
     lib().qro_mpc_grf_to_torque(C.c_float(robot.hip_len), C.c_float(robot.upper_len), C.c_float(robot.lower_len),
                                 _fp(quat), _fp(q), _fp(f_world), _fp(ff), _fp(tau))
     return ff, tau
+
+
+# ------------------------------------------------------------------------------------------------
+# Force-balance stance QP
+# ------------------------------------------------------------------------------------------------
+class FbParams(C.Structure):
+    _fields_ = [("mass", C.c_float), ("inertia", C.c_float * 9), ("acc_weight", C.c_float * 6), ("reg_weight", C.c_float),
+                ("mu", C.c_float), ("fmin_ratio", C.c_float * 4), ("fmax_ratio", C.c_float * 4), ("world_frame", C.c_int)]
+
+
+def fb_params_of(p: dict) -> FbParams:
+    P = FbParams()
+    P.mass = p["mass"]
+    P.inertia[:] = [float(v) for v in np.asarray(p["inertia"], np.float32).reshape(9)]
+    P.acc_weight[:] = [float(v) for v in p["acc_weight"]]
+    P.reg_weight, P.mu = p["reg_weight"], p["mu"]
+    P.fmin_ratio[:] = [float(v) for v in p["fmin_ratio"]]
+    P.fmax_ratio[:] = [float(v) for v in p["fmax_ratio"]]
+    P.world_frame = int(p["world_frame"])
+    return P
+
+
+def force_balance(P: FbParams, foot, acc, contact, inertia=None, gravity=None, frame=None):
+    """One robot through the restated ComputeContactForce + the reference's QuadProg++.
+    Returns dict(force[12], status, cost, G[12,12], a[12], C[24,12], lb[24])."""
+    f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+    foot, acc, inertia, gravity, frame = f32(foot), f32(acc), f32(inertia), f32(gravity), f32(frame)
+    contact = np.ascontiguousarray(contact, np.int32)
+    force = np.zeros(12, np.float32)
+    G, a, Cm, lb = np.zeros((12, 12), np.float32), np.zeros(12, np.float32), np.zeros((24, 12), np.float32), np.zeros(24, np.float32)
+    cost = C.c_double()
+    opt = lambda a: None if a is None else _fp(a)
+    st = lib().qro_force_balance(C.byref(P), opt(inertia), _fp(foot), _fp(acc), _ip(contact), opt(gravity), opt(frame),
+                                 _fp(force), _fp(G), _fp(a), _fp(Cm), _fp(lb), C.byref(cost))
+    return dict(force=force, status=st, cost=cost.value, G=G, a=a, C=Cm, lb=lb)

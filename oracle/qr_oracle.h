@@ -130,6 +130,25 @@ int qro_wbc_step_f64(const qro_wbc_model* model, const float* state, const float
 int qro_swing_parabola(const float* start, const float* end, float height, float t, int phase_module,
                        float* pos);
 
+/* ------------------------------------------------------------------------------------------------
+ * Force-balance stance QP (fb_oracle.cpp): ComputeContactForce of qr_qp_torque_optimizer.cpp with the reference's
+ * QuadProg++.  force[12] = X(leg, axis) = -x.  Optional outputs: the float32 QP data G(144) a(12) C(24x12) lb(24)
+ * and QuadProg++'s return value (inf when it met an infeasible row).  Returns 0, 1 (infeasible row met, iterate
+ * kept -- what the reference does) or 3 (NaN: forces zeroed). */
+typedef struct {
+    float mass;
+    float inertia[9];
+    float acc_weight[6];
+    float reg_weight;
+    float mu;
+    float fmin_ratio[4];
+    float fmax_ratio[4];
+    int world_frame;
+} qro_fb_params;
+int qro_force_balance(const qro_fb_params* P, const float* inertia, const float* foot, const float* acc,
+                      const int* contact, const float* gravity, const float* frame, float* force,
+                      float* G_out, float* a_out, float* C_out, float* lb_out, double* cost_out);
+
 #ifdef __cplusplus
 }
 #endif

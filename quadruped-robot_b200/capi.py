@@ -36,7 +36,7 @@ def default_options() -> QpOptions:
 EXPORTS = ["qr_gpu_init", "qr_gpu_shutdown", "qr_gpu_last_error", "qr_gpu_mpc_occupancy",
            "qr_gpu_mpc_solve_batch", "qr_gpu_mpc_solve_batch_host", "qr_gpu_mpc_condense_batch",
            "qr_gpu_qp_solve_batch", "qr_gpu_wbc_solve_batch", "qr_gpu_wbc_solve_batch_f64",
-           "qr_gpu_swing_parabola_batch", "qr_gpu_mpc_inputs_batch", "qr_gpu_mpc_leg_torque_batch"]
+           "qr_gpu_swing_parabola_batch", "qr_gpu_mpc_inputs_batch", "qr_gpu_mpc_leg_torque_batch", "qr_gpu_force_balance_batch"]
 
 
 class WbcModel(C.Structure):
@@ -184,3 +184,30 @@ def mpc_leg_torque_batch_device(robot, quat, q, grf, f_ff, tau, stream_ptr: int)
     rc = lib().qr_gpu_mpc_leg_torque_batch(C.c_float(robot.hip_len), C.c_float(robot.upper_len), C.c_float(robot.lower_len),
                                            quat.shape[0], _vp(quat), _vp(q), _vp(grf), _vp(f_ff), _vp(tau), C.c_void_p(stream_ptr))
     _check(rc, "qr_gpu_mpc_leg_torque_batch")
+
+
+class FbParams(C.Structure):
+    """qr_fb_params of include/qr_gpu.h."""
+    _fields_ = [("mass", C.c_float), ("inertia", C.c_float * 9), ("acc_weight", C.c_float * 6), ("reg_weight", C.c_float),
+                ("mu", C.c_float), ("fmin_ratio", C.c_float * 4), ("fmax_ratio", C.c_float * 4), ("world_frame", C.c_int32)]
+
+
+def fb_params_of(p: dict) -> FbParams:
+    import numpy as np
+    P = FbParams()
+    P.mass = p["mass"]
+    P.inertia[:] = [float(v) for v in np.asarray(p["inertia"], np.float32).reshape(9)]
+    P.acc_weight[:] = [float(v) for v in p["acc_weight"]]
+    P.reg_weight, P.mu = p["reg_weight"], p["mu"]
+    P.fmin_ratio[:] = [float(v) for v in p["fmin_ratio"]]
+    P.fmax_ratio[:] = [float(v) for v in p["fmax_ratio"]]
+    P.world_frame = int(p["world_frame"])
+    return P
+
+
+def force_balance_batch_device(P: FbParams, foot, acc, contact, force, stream_ptr: int, inertia=None, gravity=None,
+                               frame=None, status=None, iters=None):
+    """torch CUDA tensors; asynchronous on the stream."""
+    rc = lib().qr_gpu_force_balance_batch(C.byref(P), foot.shape[0], _vp(inertia), _vp(foot), _vp(acc), _vp(contact),
+                                          _vp(gravity), _vp(frame), _vp(force), _vp(status), _vp(iters), C.c_void_p(stream_ptr))
+    _check(rc, "qr_gpu_force_balance_batch")

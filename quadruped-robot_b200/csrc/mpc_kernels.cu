@@ -733,3 +733,37 @@ extern "C" int qr_gpu_mpc_leg_torque_batch(float hip_len, float upper_len, float
     if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_leg_torque_kernel", e);
     return QR_OK;
 }
+
+// ==================================================================================================
+// Force-balance stance QP (one thread per robot)
+// ==================================================================================================
+#include "fb_problem.h"
+
+namespace {
+__global__ void __launch_bounds__(64) qr_force_balance_kernel(const QrFbArgs A) {
+    const int prob = blockIdx.x * blockDim.x + threadIdx.x;
+    if (prob < A.batch) qr_fb_problem(A, prob);
+}
+}  // namespace
+
+extern "C" int qr_gpu_force_balance_batch(const qr_fb_params* P, int batch, const float* inertia, const float* foot,
+                                          const float* acc, const int32_t* contact, const float* gravity,
+                                          const float* frame, float* force_out, int32_t* status_out, int32_t* iters_out,
+                                          void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
+    if (!P || batch < 0) return fail(QR_EINVAL, "null params or negative batch");
+    if (!(P->mass > 0.f) || !(P->mu > 0.f)) return fail(QR_EINVAL, "mass and mu must be positive");
+    if (batch == 0) return QR_OK;
+    if (!foot || !acc || !contact || !force_out) return fail(QR_EINVAL, "null pointer");
+    QrFbArgs A;
+    memset(&A, 0, sizeof(A));
+    A.P = *P;
+    A.batch = batch;
+    A.inertia = inertia; A.foot = foot; A.acc = acc; A.contact = contact; A.gravity = gravity; A.frame = frame;
+    A.force_out = force_out; A.status_out = status_out; A.iters_out = iters_out;
+    qr_force_balance_kernel<<<(batch + 63) / 64, 64, 0, (cudaStream_t)cuda_stream>>>(A);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_force_balance_kernel", e);
+    return QR_OK;
+}

@@ -222,3 +222,40 @@ def make_wbc_batch(robot: str | RobotMPC = "lite3", batch: int = 1024, seed: int
     ], 1)
     return dict(state=np.ascontiguousarray(state, F32), cmd=np.ascontiguousarray(cmd, F32),
                 contact=np.ascontiguousarray(contact, np.int32), rpy=rpy, robot=rb)
+
+
+# ------------------------------------------------------------------------------------------------
+# Force-balance stance controller workloads
+# ------------------------------------------------------------------------------------------------
+def make_fb_batch(robot: str | RobotMPC = "a1", batch: int = 256, seed: int = 0, world_frame: bool = False,
+                  tilted: bool = False) -> dict:
+    """Inputs of ComputeContactForce for `batch` robots: foot[B,12] (4x3 foot positions in the frame of the
+    computation), acc[B,6] desired acceleration, contact[B,4]; optional per-robot inertia[B,9], gravity[B,3] and
+    frame[B,9] (normal, tangent1, tangent2) for a tilted control frame.  acc_weight / ratios are the values of
+    config/a1_sim/stance_leg_controller.yaml and qr_torque_stance_leg_controller.cpp:98-108."""
+    rb = ROBOTS[robot] if isinstance(robot, str) else robot
+    rng = np.random.default_rng(seed)
+    B = batch
+    U = rng.uniform
+    hips = np.array(rb.hip_positions, float)
+    foot = hips[None] + np.array([0, 0, -rb.body_height]) + U(-0.05, 0.05, (B, 4, 3))
+    acc = np.concatenate([U(-2, 2, (B, 2)), U(-1.5, 1.5, (B, 1)), U(-4, 4, (B, 3))], 1)
+    patterns = np.array([[1, 0, 0, 1], [0, 1, 1, 0], [1, 1, 1, 1], [1, 1, 0, 1], [0, 1, 1, 1], [1, 0, 1, 1], [1, 1, 1, 0]], np.int32)
+    contact = patterns[rng.integers(0, len(patterns), B)]
+    params = dict(mass=rb.mass, inertia=np.diag(rb.inertia).astype(F32), acc_weight=(1.0, 1.0, 1.0, 10.0, 10.0, 1.0),
+                  reg_weight=1e-4, mu=0.45 if world_frame else 0.5, fmin_ratio=(0.01,) * 4, fmax_ratio=(10.0,) * 4,
+                  world_frame=int(world_frame))
+    out = dict(foot=np.ascontiguousarray(foot.reshape(B, 12), F32), acc=np.ascontiguousarray(acc, F32),
+               contact=np.ascontiguousarray(contact), params=params, robot=rb, inertia=None, gravity=None, frame=None)
+    if tilted:
+        pitch = U(-0.3, 0.3, B)
+        rpy = np.stack([U(-0.1, 0.1, B), pitch, np.zeros(B)], 1)
+        R = _rot_zyx(rpy)
+        I = np.diag(rb.inertia)
+        out["inertia"] = np.ascontiguousarray(np.einsum("bij,jk,blk->bil", R, I, R).reshape(B, 9), F32)
+        out["gravity"] = np.ascontiguousarray(np.einsum("bji,j->bi", R, np.array([0, 0, 9.8])), F32)
+        n = np.stack([-np.sin(pitch), np.zeros(B), np.cos(pitch)], 1)
+        t2 = np.tile(np.array([0.0, 1.0, 0.0]), (B, 1))
+        t1 = np.cross(t2, n)
+        out["frame"] = np.ascontiguousarray(np.concatenate([n, t1, t2], 1), F32)
+    return out

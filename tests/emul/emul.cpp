@@ -10,6 +10,7 @@
 #include "../../quadruped-robot_b200/csrc/mpc_problem.h"
 #include "../../quadruped-robot_b200/csrc/wbc_problem.h"
 #include "../../quadruped-robot_b200/csrc/mpc_io.h"
+#include "../../quadruped-robot_b200/csrc/fb_problem.h"
 
 static qr_qp_options emul_default_options() {
     qr_qp_options o;
@@ -117,4 +118,22 @@ extern "C" void qr_emul_mpc_reference_traj(int h, float dt, const float* init, c
 extern "C" void qr_emul_mpc_grf_to_torque(float hip, float up, float low, const float* quat, const float* q, const float* f,
                                           float* ff, float* tau) {
     qr_mpc_grf_to_torque(hip, up, low, quat, q, f, ff, tau);
+}
+
+extern "C" int qr_emul_force_balance_batch(const qr_fb_params* P, int batch, const float* inertia, const float* foot,
+                                           const float* acc, const int32_t* contact, const float* gravity,
+                                           const float* frame, float* force_out, int32_t* status_out, int32_t* iters_out) {
+    QrFbArgs A;
+    memset(&A, 0, sizeof(A));
+    A.P = *P; A.batch = batch;
+    A.inertia = inertia; A.foot = foot; A.acc = acc; A.contact = contact; A.gravity = gravity; A.frame = frame;
+    A.force_out = force_out; A.status_out = status_out; A.iters_out = iters_out;
+    for (int i = 0; i < batch; ++i) qr_fb_problem(A, i);
+    return 0;
+}
+// QP data exactly as handed to the solver (float32), for the bit-exactness test against the oracle
+extern "C" void qr_emul_fb_build(const qr_fb_params* P, const float* inertia, const float* foot, const float* acc,
+                                 const int32_t* contact, const float* gravity, const float* frame, float* G, float* a,
+                                 float* C, float* lb) {
+    qr_fb_build(*P, inertia ? inertia : P->inertia, foot, acc, contact, gravity, frame, G, a, C, lb);
 }

@@ -102,8 +102,32 @@ def swing_parabola(self, start, end, height, t, phase_module=False):
     return pos, bool(ok)
 
 
+def force_balance(self, P, batch):
+    """Host emulation of the force-balance device code: dict(force[B,12], status, iters)."""
+    B = batch["foot"].shape[0]
+    force = np.zeros((B, 12), np.float32)
+    st, it = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    self.lib.qr_emul_force_balance_batch(C.byref(P), B, self._fp(batch.get("inertia")), self._fp(batch["foot"]),
+                                         self._fp(batch["acc"]), ip(batch["contact"]), self._fp(batch.get("gravity")),
+                                         self._fp(batch.get("frame")), self._fp(force), ip(st), ip(it))
+    return dict(force=force, status=st, iters=it)
+
+
+def fb_build(self, P, batch, i):
+    """float32 QP data of robot i as the device code builds them: G[12,12], a[12], C[24,12], lb[24]."""
+    G, a, Cm, lb = np.zeros((12, 12), np.float32), np.zeros(12, np.float32), np.zeros((24, 12), np.float32), np.zeros(24, np.float32)
+    row = lambda k: None if batch.get(k) is None else np.ascontiguousarray(batch[k][i])
+    self.lib.qr_emul_fb_build(C.byref(P), self._fp(row("inertia")), self._fp(row("foot")), self._fp(row("acc")),
+                              row("contact").ctypes.data_as(C.POINTER(C.c_int)), self._fp(row("gravity")),
+                              self._fp(row("frame")), self._fp(G), self._fp(a), self._fp(Cm), self._fp(lb))
+    return G, a, Cm, lb
+
+
 Emul.wbc_solve = wbc_solve
 Emul.swing_parabola = swing_parabola
+Emul.force_balance = force_balance
+Emul.fb_build = fb_build
 
 
 def load():
