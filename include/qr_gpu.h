@@ -179,6 +179,13 @@ int qr_gpu_wbc_solve_batch(const qr_wbc_model* model, int batch, const float* st
                            const int32_t* contact, float* tau_out, float* fr_out, float* qdes_out,
                            float* qddes_out, int32_t* status_out, void* cuda_stream);
 
+/* Same call with HOST buffers (what the reference-side controller holds for its one robot): inputs are copied
+ * host->device, the kernel runs, tau / fr / qdes / qddes / status come back, and the call returns after the
+ * stream has drained.  Any output pointer except tau_out may be NULL. */
+int qr_gpu_wbc_solve_batch_host(const qr_wbc_model* model, int batch, const float* state, const float* cmd,
+                                const int32_t* contact, float* tau_out, float* fr_out, float* qdes_out,
+                                float* qddes_out, int32_t* status_out);
+
 /* Same with float64 outputs and the intermediate model quantities (tests): dbg [batch][630] =
  * H(324) G(18) Cqd(18) Jc of the four feet (216) Jcdqd(12) pFoot(12) vFoot(12) qddot(18); any may be NULL. */
 int qr_gpu_wbc_solve_batch_f64(const qr_wbc_model* model, int batch, const float* state, const float* cmd,

@@ -36,7 +36,7 @@ def default_options() -> QpOptions:
 EXPORTS = ["qr_gpu_init", "qr_gpu_shutdown", "qr_gpu_last_error", "qr_gpu_mpc_occupancy",
            "qr_gpu_mpc_solve_batch", "qr_gpu_mpc_solve_batch_host", "qr_gpu_mpc_condense_batch",
            "qr_gpu_qp_solve_batch", "qr_gpu_wbc_solve_batch", "qr_gpu_wbc_solve_batch_f64",
-           "qr_gpu_swing_parabola_batch", "qr_gpu_mpc_inputs_batch", "qr_gpu_mpc_leg_torque_batch", "qr_gpu_force_balance_batch"]
+           "qr_gpu_swing_parabola_batch", "qr_gpu_mpc_inputs_batch", "qr_gpu_mpc_leg_torque_batch", "qr_gpu_force_balance_batch", "qr_gpu_wbc_solve_batch_host"]
 
 
 class WbcModel(C.Structure):
@@ -211,3 +211,19 @@ def force_balance_batch_device(P: FbParams, foot, acc, contact, force, stream_pt
     rc = lib().qr_gpu_force_balance_batch(C.byref(P), foot.shape[0], _vp(inertia), _vp(foot), _vp(acc), _vp(contact),
                                           _vp(gravity), _vp(frame), _vp(force), _vp(status), _vp(iters), C.c_void_p(stream_ptr))
     _check(rc, "qr_gpu_force_balance_batch")
+
+
+def wbc_solve_batch_host(model: WbcModel, state, cmd, contact):
+    """numpy in / numpy out through the host-buffer entry point: dict(tau, fr, qdes, qddes, status)."""
+    import numpy as np
+    B = state.shape[0]
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    state, cmd, contact = f(state), f(cmd), np.ascontiguousarray(contact, np.int32)
+    out = {k: np.zeros((B, 12), np.float32) for k in ("tau", "fr", "qdes", "qddes")}
+    st = np.zeros(B, np.int32)
+    fp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib().qr_gpu_wbc_solve_batch_host(C.byref(model), B, fp(state), fp(cmd), fp(contact), fp(out["tau"]), fp(out["fr"]),
+                                           fp(out["qdes"]), fp(out["qddes"]), fp(st))
+    _check(rc, "qr_gpu_wbc_solve_batch_host")
+    out["status"] = st
+    return out

@@ -646,6 +646,52 @@ extern "C" int qr_gpu_wbc_solve_batch(const qr_wbc_model* model, int batch, cons
     return wbc_launch(model, batch, state, cmd, contact, A, cuda_stream);
 }
 
+extern "C" int qr_gpu_wbc_solve_batch_host(const qr_wbc_model* model, int batch, const float* state, const float* cmd,
+                                           const int32_t* contact, float* tau_out, float* fr_out, float* qdes_out,
+                                           float* qddes_out, int32_t* status_out) {
+    if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
+    if (!model || batch < 0) return fail(QR_EINVAL, "null model or negative batch");
+    if (batch == 0) return QR_OK;
+    if (!state || !cmd || !contact || !tau_out) return fail(QR_EINVAL, "null pointer");
+    const size_t B = (size_t)batch;
+    const size_t bytes = B * ((37 + 66 + 4 * 12) * sizeof(float) + 5 * sizeof(int32_t)) + 256;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (bytes > g_ctx.stage_bytes) {
+            if (g_ctx.stage) cudaFree(g_ctx.stage);
+            g_ctx.stage = nullptr;
+            g_ctx.stage_bytes = 0;
+            cudaError_t e = cudaMalloc(&g_ctx.stage, bytes);
+            if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMalloc(stage)", e);
+            g_ctx.stage_bytes = bytes;
+        }
+    }
+    cudaStream_t st = g_ctx.stream;
+    float* d_state = reinterpret_cast<float*>(g_ctx.stage);
+    float* d_cmd = d_state + B * 37;
+    float* d_tau = d_cmd + B * 66;
+    float* d_fr = d_tau + B * 12;
+    float* d_qdes = d_fr + B * 12;
+    float* d_qddes = d_qdes + B * 12;
+    int32_t* d_contact = reinterpret_cast<int32_t*>(d_qddes + B * 12);
+    int32_t* d_status = d_contact + B * 4;
+    cudaError_t e = cudaMemcpyAsync(d_state, state, B * 37 * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_cmd, cmd, B * 66 * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_contact, contact, B * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpyAsync H2D", e);
+    int rc = qr_gpu_wbc_solve_batch(model, batch, d_state, d_cmd, d_contact, d_tau, d_fr, d_qdes, d_qddes, d_status, st);
+    if (rc) return rc;
+    e = cudaMemcpyAsync(tau_out, d_tau, B * 12 * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && fr_out) e = cudaMemcpyAsync(fr_out, d_fr, B * 12 * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && qdes_out) e = cudaMemcpyAsync(qdes_out, d_qdes, B * 12 * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && qddes_out) e = cudaMemcpyAsync(qddes_out, d_qddes, B * 12 * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && status_out) e = cudaMemcpyAsync(status_out, d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpyAsync D2H", e);
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(QR_ECUDA, "cudaStreamSynchronize", e);
+    return QR_OK;
+}
+
 extern "C" int qr_gpu_wbc_solve_batch_f64(const qr_wbc_model* model, int batch, const float* state, const float* cmd,
                                           const int32_t* contact, double* tau_out, double* fr_out, double* qdes_out,
                                           double* qddes_out, double* dbg_out, int32_t* status_out, void* cuda_stream) {
