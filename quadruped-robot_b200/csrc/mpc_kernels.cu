@@ -43,8 +43,14 @@ __global__ void qr_mpc_classify_kernel(const QrMpcArgs A, int nclass, int* count
 // atomic ticket so that the varying number of active-set rounds per instance balances out.
 // The workspace capacity (size class) is a template parameter: all shared-memory pointers of the solver
 // become compile-time offsets, which removes their re-computation from every inner loop.
+#ifndef QR_FUSED_MIN_CTAS
+#define QR_FUSED_MIN_CTAS (512 / QR_NT)
+#endif
+#ifndef QR_HSG_FROM
+#define QR_HSG_FROM 56
+#endif
 template <int CAP, bool HSG>
-__global__ void __launch_bounds__(QR_NT, 512 / QR_NT) qr_mpc_fused_kernel(const QrMpcArgs A) {
+__global__ void __launch_bounds__(QR_NT, QR_FUSED_MIN_CTAS) qr_mpc_fused_kernel(const QrMpcArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_ticket;
     constexpr int NT = QR_NT;
@@ -69,17 +75,17 @@ __global__ void __launch_bounds__(QR_NT, 512 / QR_NT) qr_mpc_fused_kernel(const 
 typedef void (*QrFusedKernel)(const QrMpcArgs);
 // Instantiated size classes (capacities in stance foot-steps); the Hessian moves to the L2-resident scratch
 // for the classes that do not fit two block-packed matrices in 227 KB of shared memory.
-constexpr int QR_HSG_FROM_CAP = 56;
+constexpr int QR_HSG_FROM_CAP = QR_HSG_FROM;
 QrFusedKernel fused_kernel_for(int cap) {
     switch (cap) {
-        case 8: return qr_mpc_fused_kernel<8, false>;
-        case 16: return qr_mpc_fused_kernel<16, false>;
-        case 24: return qr_mpc_fused_kernel<24, false>;
-        case 32: return qr_mpc_fused_kernel<32, false>;
-        case 40: return qr_mpc_fused_kernel<40, false>;
-        case 48: return qr_mpc_fused_kernel<48, false>;
-        case 56: return qr_mpc_fused_kernel<56, true>;
-        case 64: return qr_mpc_fused_kernel<64, true>;
+        case 8: return qr_mpc_fused_kernel<8, (8 >= QR_HSG_FROM)>;
+        case 16: return qr_mpc_fused_kernel<16, (16 >= QR_HSG_FROM)>;
+        case 24: return qr_mpc_fused_kernel<24, (24 >= QR_HSG_FROM)>;
+        case 32: return qr_mpc_fused_kernel<32, (32 >= QR_HSG_FROM)>;
+        case 40: return qr_mpc_fused_kernel<40, (40 >= QR_HSG_FROM)>;
+        case 48: return qr_mpc_fused_kernel<48, (48 >= QR_HSG_FROM)>;
+        case 56: return qr_mpc_fused_kernel<56, (56 >= QR_HSG_FROM)>;
+        case 64: return qr_mpc_fused_kernel<64, (64 >= QR_HSG_FROM)>;
         default: return nullptr;
     }
 }
@@ -172,7 +178,7 @@ int launch_geometry(Kern kern, int nfcap, int horizon, int batch, int* grid, siz
     }
     size_t bytes = qr_mpc_smem_bytes(nfcap, horizon, true);
     bool hsg = false;
-    if (bytes + 1024 > g_ctx.smem_optin) {
+    if (bytes + 1024 > g_ctx.smem_optin || (hs_global && *hs_global)) {   // *hs_global preset: the caller asks for H in the scratch
         bytes = qr_mpc_smem_bytes(nfcap, horizon, false);
         hsg = true;
     }
@@ -284,7 +290,7 @@ extern "C" int qr_gpu_mpc_occupancy(int horizon, int stance_footsteps, int* sm_c
     if (c < 0) c = 0;
     int grid = 0, occ = 0;
     size_t smem = 0;
-    bool hsg = false;
+    bool hsg = class_cap(c, horizon) >= QR_HSG_FROM_CAP;
     int rc = launch_geometry(fused_kernel_for(class_cap(c, horizon)), class_cap(c, horizon), horizon, 1 << 30, &grid, &smem, &occ, &hsg);
     if (rc) return rc;
     if (sm_count) *sm_count = g_ctx.sm_count;
@@ -314,7 +320,7 @@ extern "C" int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_option
         const int cap = class_cap(nclass - 1, h);
         int grid1 = 0;
         size_t smem1 = 0;
-        bool hsg1 = false;
+        bool hsg1 = cap >= QR_HSG_FROM_CAP;
         rc = launch_geometry(fused_kernel_for(cap), cap, h, batch, &grid1, &smem1, nullptr, &hsg1);
         if (rc) return rc;
         if (hsg1 != (cap >= QR_HSG_FROM_CAP)) return fail(QR_EINVAL, "unexpected shared-memory capacity for this size class");
@@ -347,6 +353,7 @@ extern "C" int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_option
     bool hsg[16];
     size_t scratch_need = 0;
     for (int c = 0; c < nclass; ++c) {
+        hsg[c] = class_cap(c, h) >= QR_HSG_FROM_CAP;
         rc = launch_geometry(fused_kernel_for(class_cap(c, h)), class_cap(c, h), h, batch, &grid[c], &smem[c], nullptr, &hsg[c]);
         if (rc) return rc;
         if (hsg[c] != (class_cap(c, h) >= QR_HSG_FROM_CAP)) return fail(QR_EINVAL, "unexpected shared-memory capacity for this size class");

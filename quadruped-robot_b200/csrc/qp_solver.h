@@ -61,6 +61,13 @@ struct QrQpWork {
 };
 
 QR_DEV int qr_blk(int S, int T) { return 9 * ((S * (S + 1)) / 2 + T); }
+// The matrix under LDL' factorisation (the reduced system) is packed by COLUMNS instead: block (I,J), I >= J, of an
+// nb x nb block matrix at 9*(J*nb - J(J-1)/2 + I - J).  The trailing sub-matrix of every elimination step is then
+// one contiguous run of blocks, so the 32 lanes of a warp update 32 consecutive tiles: their 64-bit accesses fall
+// on distinct banks (with the row-packed layout the gaps between rows cost 27-41 % extra shared-memory
+// wavefronts in this loop -- the shared-memory pipe is the unit that limits the kernel's throughput).
+QR_DEV int qr_kcol(int nb, int J) { return J * nb - (J * (J - 1)) / 2; }
+QR_DEV int qr_kblk(int nb, int I, int J) { return 9 * (qr_kcol(nb, J) + (I - J)); }
 
 // Decode a lower-triangular linear index idx -> (I, J), I >= J (used once per launch to fill W.tri).
 QR_DEV void qr_tri_decode(int idx, int& I, int& J) {
@@ -176,16 +183,17 @@ QR_DEV void qr_ldl_factor(QrQpWork& W, int nb, int with_rhs QR_PROF_ARG) {
     for (int Kc = 0; Kc < nb; ++Kc) {
         const int nrem = nb - Kc - 1;
         const int ntile = (nrem * (nrem + 1)) / 2;
+        const int kc0 = qr_kcol(nb, Kc), kc1 = qr_kcol(nb, Kc + 1);
         const double* Di = W.Dinv + 9 * Kc;
         QR_FOR(idx, ntile + (with_rhs ? nrem : 0)) {
             const double d0 = Di[0], d1 = Di[1], d2 = Di[2], d4 = Di[4], d5 = Di[5], d8 = Di[8];
             if (idx < ntile) {
-                const int code = W.tri[idx];
-                const int I = (code >> 8) + Kc + 1, J = (code & 255) + Kc + 1;
-                const int rowI = (I * (I + 1)) / 2;
-                const double* wi = K + 9 * (rowI + Kc);
-                const double* wj = K + qr_blk(J, Kc);
-                double* a = K + 9 * (rowI + J);
+                // tiles in memory order: idx-th block of the (contiguous) trailing columns Kc+1 .. nb-1
+                const int code = W.tri[ntile - 1 - idx];
+                const int I = nb - 1 - (code & 255), J = nb - 1 - (code >> 8);
+                const double* wi = K + 9 * (kc0 + (I - Kc));
+                const double* wj = K + 9 * (kc0 + (J - Kc));
+                double* a = K + 9 * (kc1 + idx);
                 double m[9], t[9], r[9];
 #pragma unroll
                 for (int e = 0; e < 9; ++e) { m[e] = wj[e]; r[e] = a[e]; }
@@ -213,7 +221,7 @@ QR_DEV void qr_ldl_factor(QrQpWork& W, int nb, int with_rhs QR_PROF_ARG) {
                 const double t0 = d0 * y0 + d1 * y1 + d2 * y2;
                 const double t1 = d1 * y0 + d4 * y1 + d5 * y2;
                 const double t2 = d2 * y0 + d5 * y1 + d8 * y2;
-                const double* wj = K + qr_blk(J, Kc);
+                const double* wj = K + 9 * (kc0 + (J - Kc));
                 y[3 * J] -= wj[0] * t0 + wj[1] * t1 + wj[2] * t2;
                 y[3 * J + 1] -= wj[3] * t0 + wj[4] * t1 + wj[5] * t2;
                 y[3 * J + 2] -= wj[6] * t0 + wj[7] * t1 + wj[8] * t2;
@@ -238,7 +246,7 @@ QR_DEV void qr_ldl_forward(QrQpWork& W, int nb QR_PROF_ARG) {
             const double t0 = Di[0] * y0 + Di[1] * y1 + Di[2] * y2;
             const double t1 = Di[3] * y0 + Di[4] * y1 + Di[5] * y2;
             const double t2 = Di[6] * y0 + Di[7] * y1 + Di[8] * y2;
-            const double* r = K + qr_blk(I, Kc) + 3 * a;
+            const double* r = K + qr_kblk(nb, I, Kc) + 3 * a;
             y[3 * I + a] -= r[0] * t0 + r[1] * t1 + r[2] * t2;
         }
         QR_SYNC();
@@ -270,7 +278,7 @@ QR_DEV void qr_ldl_backward(QrQpWork& W, int nb, double* out QR_PROF_ARG) {
             const double d0 = Di[0], d1 = Di[1], d2 = Di[2], d4 = Di[4], d5 = Di[5], d8 = Di[8];
             double b[9];
             {
-                const double* blk = K + qr_blk(nb - 1, lane < nb - 1 ? lane : 0);
+                const double* blk = K + qr_kblk(nb, nb - 1, lane < nb - 1 ? lane : 0);
 #pragma unroll
                 for (int e = 0; e < 9; ++e) b[e] = blk[e];
             }
@@ -281,7 +289,7 @@ QR_DEV void qr_ldl_backward(QrQpWork& W, int nb, double* out QR_PROF_ARG) {
                 const double x2 = d2 * y0 + d5 * y1 + d8 * y2;
                 double n[9];
                 if (Kc > 0) {
-                    const double* blk = K + qr_blk(Kc - 1, lane < Kc - 1 ? lane : 0);
+                    const double* blk = K + qr_kblk(nb, Kc - 1, lane < Kc - 1 ? lane : 0);
 #pragma unroll
                     for (int e = 0; e < 9; ++e) n[e] = blk[e];
                 }
@@ -314,7 +322,7 @@ QR_DEV void qr_ldl_backward(QrQpWork& W, int nb, double* out QR_PROF_ARG) {
             if (J == Kc) {
                 out[3 * Kc + a] = (a == 0 ? x0 : (a == 1 ? x1 : x2));
             } else {
-                const double* blk = K + qr_blk(Kc, J);   // W_KJ, column a of it
+                const double* blk = K + qr_kblk(nb, Kc, J);   // W_KJ, column a of it
                 y[3 * J + a] -= blk[a] * x0 + blk[3 + a] * x1 + blk[6 + a] * x2;
             }
         }
@@ -415,10 +423,11 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
         const int nbr = (nred + 2) / 3;
         QR_TRACE_ROUND(round, nred, W);
         // ---- reduced matrix (Z'HZ), padded to a multiple of 3 with identity; right-hand side
-        QR_FOR(idx, 9 * ((nbr * (nbr + 1)) / 2)) {
+        const int nkb = (nbr * (nbr + 1)) / 2;
+        QR_FOR(idx, 9 * nkb) {
             const int b = idx / 9, e = idx - 9 * b;
-            const int code = W.tri[b];
-            const int r1 = 3 * (code >> 8) + e / 3, r2 = 3 * (code & 255) + e % 3;
+            const int code = W.tri[nkb - 1 - b];   // b-th block of the column-packed matrix (see qr_kblk)
+            const int r1 = 3 * (nbr - 1 - (code & 255)) + e / 3, r2 = 3 * (nbr - 1 - (code >> 8)) + e % 3;
             const int f1 = W.rfoot[r1], f2 = W.rfoot[r2];
             double val;
             if (f1 < 0 || f2 < 0) {
