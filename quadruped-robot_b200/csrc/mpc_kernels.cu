@@ -43,11 +43,15 @@ __global__ void qr_mpc_classify_kernel(const QrMpcArgs A, int nclass, int* count
 // atomic ticket so that the varying number of active-set rounds per instance balances out.
 // The workspace capacity (size class) is a template parameter: all shared-memory pointers of the solver
 // become compile-time offsets, which removes their re-computation from every inner loop.
+// Occupancy.  With both block-packed matrices in shared memory (52.8 KB at capacity 24) and 128 registers the
+// kernel stops at 4 CTAs per SM.  Measured on B200 (A1 trot, 65536 instances): Hessian in the L2-resident scratch
+// and a 96-register cap -> 5 CTAs per SM, +5 % QP/s (3.11 -> 3.27 M); 80 registers / 6 CTAs: +2.5 % (spills);
+// the Hessian in the scratch at unchanged occupancy costs nothing (its reads are three streaming passes per round).
 #ifndef QR_FUSED_MIN_CTAS
-#define QR_FUSED_MIN_CTAS (512 / QR_NT)
+#define QR_FUSED_MIN_CTAS 5
 #endif
 #ifndef QR_HSG_FROM
-#define QR_HSG_FROM 56
+#define QR_HSG_FROM 8     // smallest capacity that keeps the Hessian in the global scratch (8: every class)
 #endif
 template <int CAP, bool HSG>
 __global__ void __launch_bounds__(QR_NT, QR_FUSED_MIN_CTAS) qr_mpc_fused_kernel(const QrMpcArgs A) {
@@ -70,6 +74,18 @@ __global__ void __launch_bounds__(QR_NT, QR_FUSED_MIN_CTAS) qr_mpc_fused_kernel(
         strided += gridDim.x;
         qr_mpc_solve_problem<NT>(A, A.list ? A.list[k] : k, S);
     }
+}
+
+// Latency path (batches that cannot fill the device): one instantiation with the capacity as a runtime value, both
+// matrices in shared memory whenever they fit and no register cap -- per-instance latency matters here, not occupancy.
+__global__ void __launch_bounds__(QR_NT, 1) qr_mpc_fused_latency_kernel(const QrMpcArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NT = QR_NT;
+    QrMpcSmem S;
+    qr_mpc_carve(S, smem, A.nfcap, A.P.horizon, A.scratch + (size_t)blockIdx.x * qr_fallback_doubles(A.nfcap),
+                 A.hs_global ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr);
+    qr_mpc_init_tables<NT>(S, A.nfcap);
+    for (int prob = blockIdx.x; prob < A.batch; prob += gridDim.x) qr_mpc_solve_problem<NT>(A, prob, S);
 }
 
 typedef void (*QrFusedKernel)(const QrMpcArgs);
@@ -320,10 +336,9 @@ extern "C" int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_option
         const int cap = class_cap(nclass - 1, h);
         int grid1 = 0;
         size_t smem1 = 0;
-        bool hsg1 = cap >= QR_HSG_FROM_CAP;
-        rc = launch_geometry(fused_kernel_for(cap), cap, h, batch, &grid1, &smem1, nullptr, &hsg1);
+        bool hsg1 = false;
+        rc = launch_geometry(qr_mpc_fused_latency_kernel, cap, h, batch, &grid1, &smem1, nullptr, &hsg1);
         if (rc) return rc;
-        if (hsg1 != (cap >= QR_HSG_FROM_CAP)) return fail(QR_EINVAL, "unexpected shared-memory capacity for this size class");
         rc = ensure_scratch(grid1, cap, hsg1);
         if (rc) return rc;
         QrMpcArgs A1;
@@ -337,9 +352,9 @@ extern "C" int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_option
         A1.grf_out = grf_out; A1.u_out = u_out; A1.status_out = status_out; A1.iters_out = iters_out;
         A1.scratch = g_ctx.scratch;
         A1.hs_global = hsg1 ? g_ctx.scratch + (size_t)grid1 * qr_fallback_doubles(cap) : nullptr;
-        fused_kernel_for(cap)<<<grid1, QR_NT, smem1, st>>>(A1);
+        qr_mpc_fused_latency_kernel<<<grid1, QR_NT, smem1, st>>>(A1);
         cudaError_t e1 = cudaGetLastError();
-        if (e1 != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_fused_kernel", e1);
+        if (e1 != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_fused_latency_kernel", e1);
         return QR_OK;
     }
     rc = ensure_work(nclass, batch);
