@@ -247,6 +247,19 @@ def bench_wbc_and_full_step(pkg, capi, torch, stream):
                                     "swing parabola, WBIC (BASELINE configs[1]), batch 1024 on the device",
                         "value": B / ms * 1e3, "unit": "robot ticks/s", "ms_per_step": ms,
                         "mpc_not_converged": int((o["status"] != 0).sum()), "wbc_status_nonzero": int((st != 0).sum())}
+    # BASELINE configs[4]: horizon-30 long-preview MPC (360 variables), batch 4096, A1 trot
+    B, h, dt = 4096, 30, 0.03
+    mb = pkg.synth.make_mpc_batch("a1", h, dt, B, seed=14, gait="trot")
+    P30 = capi.params_of(pkg.robots.ROBOTS["a1"], h, dt)
+    d30 = {k: dev(mb[k]) for k in KEYS}
+    o30 = dict(grf=torch.empty((B, 12), device="cuda"), status=torch.empty(B, dtype=torch.int32, device="cuda"),
+               iters=torch.empty((B, 2), dtype=torch.int32, device="cuda"))
+    ms = _time_ms(torch, lambda: capi.mpc_solve_batch_device(P30, d30, o30, stream), 3, warm=1)
+    out["horizon30"] = {"workload": "A1 trot convex MPC h=30 dt=0.03 (360 variables, 72 stance foot-steps), batch 4096 "
+                                    "(BASELINE configs[4]); beyond the reference's own K_MAX_GAIT_SEGMENTS = 16",
+                        "value": B / ms * 1e3, "unit": "QP/s", "ms_per_step": ms,
+                        "not_converged": int((o30["status"] != 0).sum()),
+                        "rounds_mean": float(o30["iters"][:, 1].float().mean())}
     return out
 
 

@@ -28,7 +28,9 @@ extern "C" {
 #define QR_ECUDA (-5)
 #define QR_ENOMEM (-12)
 
-#define QR_MAX_HORIZON 16 /* K_MAX_GAIT_SEGMENTS, controllers/mpc/qr_mpc_interface.h:33 */
+/* The reference's arrays stop at K_MAX_GAIT_SEGMENTS = 16 (controllers/mpc/qr_mpc_interface.h:33); the engine
+ * goes to 32 so that the long-preview configuration of BASELINE.json (horizon 30, 360 variables) runs too. */
+#define QR_MAX_HORIZON 32
 
 /* Replaces Quadruped::ProblemConfig + the inertia/mass SetupProblem stores in MPCRobotState
  * (include/quadruped/controllers/mpc/qr_mpc_interface.h:107-144; SetupProblem :157,

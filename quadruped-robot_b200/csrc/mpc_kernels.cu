@@ -20,7 +20,16 @@
 
 namespace {
 
-constexpr int QR_CLASS_STEP = 8;   // size classes: workspace capacities 8, 16, 24, ... stance foot-steps
+// Size classes: workspace capacities in stance foot-steps.  8 .. 72 in steps of 8 keep the matrix under factorisation
+// in shared memory; 96 and 128 (long horizons with most legs in stance) keep it in the L2-resident scratch.
+constexpr int QR_CLASS_STEP = 8;
+constexpr int QR_NCLASS_MAX = 11;
+__host__ __device__ inline int qr_class_cap(int c) { return c < 9 ? QR_CLASS_STEP * (c + 1) : (c == 9 ? 96 : 128); }
+__host__ __device__ inline int qr_class_of(int nf) {
+    if (nf <= 72) { const int c = (nf + QR_CLASS_STEP - 1) / QR_CLASS_STEP - 1; return c < 0 ? 0 : c; }
+    return nf <= 96 ? 9 : 10;
+}
+constexpr int QR_KG_FROM_CAP = 96;   // smallest capacity whose matrix under factorisation lives in the global scratch
 
 // Size classification: one thread per instance counts its stance foot-steps (gait * f_max > 0, the
 // rows SolveMPC would give a non-zero upper bound, qr_mpc_interface.cpp:387) and appends the instance
@@ -33,8 +42,8 @@ __global__ void qr_mpc_classify_kernel(const QrMpcArgs A, int nclass, int* count
     const float* g = A.gait + (size_t)prob * h4;
     int nf = 0;
     for (int k = 0; k < h4; ++k) nf += (__fmul_rn(g[k], fmax) > 0.f) ? 1 : 0;
-    int c = (nf + QR_CLASS_STEP - 1) / QR_CLASS_STEP - 1;
-    c = c < 0 ? 0 : (c >= nclass ? nclass - 1 : c);
+    int c = qr_class_of(nf);
+    c = c >= nclass ? nclass - 1 : c;
     const int slot = atomicAdd(&counts[c], 1);
     lists[(size_t)c * A.batch + slot] = prob;
 }
@@ -53,14 +62,15 @@ __global__ void qr_mpc_classify_kernel(const QrMpcArgs A, int nclass, int* count
 #ifndef QR_HSG_FROM
 #define QR_HSG_FROM 8     // smallest capacity that keeps the Hessian in the global scratch (8: every class)
 #endif
-template <int CAP, bool HSG>
+template <int CAP, bool HSG, bool KG>
 __global__ void __launch_bounds__(QR_NT, QR_FUSED_MIN_CTAS) qr_mpc_fused_kernel(const QrMpcArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_ticket;
     constexpr int NT = QR_NT;
     QrMpcSmem S;
     qr_mpc_carve(S, smem, CAP, A.P.horizon, A.scratch + (size_t)blockIdx.x * qr_fallback_doubles(CAP),
-                 HSG ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(CAP) : nullptr);
+                 HSG ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(CAP) : nullptr,
+                 KG ? A.k_global + (size_t)blockIdx.x * 9 * qr_ntri(CAP) : nullptr);
     qr_mpc_init_tables<NT>(S, CAP);
     // A.next == null (small batches): one launch, instances strided over the grid, no work lists.
     const int total = A.count ? *A.count : A.batch;
@@ -83,7 +93,8 @@ __global__ void __launch_bounds__(QR_NT, 1) qr_mpc_fused_latency_kernel(const Qr
     constexpr int NT = QR_NT;
     QrMpcSmem S;
     qr_mpc_carve(S, smem, A.nfcap, A.P.horizon, A.scratch + (size_t)blockIdx.x * qr_fallback_doubles(A.nfcap),
-                 A.hs_global ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr);
+                 A.hs_global ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr,
+                 A.k_global ? A.k_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr);
     qr_mpc_init_tables<NT>(S, A.nfcap);
     for (int prob = blockIdx.x; prob < A.batch; prob += gridDim.x) qr_mpc_solve_problem<NT>(A, prob, S);
 }
@@ -94,14 +105,10 @@ typedef void (*QrFusedKernel)(const QrMpcArgs);
 constexpr int QR_HSG_FROM_CAP = QR_HSG_FROM;
 QrFusedKernel fused_kernel_for(int cap) {
     switch (cap) {
-        case 8: return qr_mpc_fused_kernel<8, (8 >= QR_HSG_FROM)>;
-        case 16: return qr_mpc_fused_kernel<16, (16 >= QR_HSG_FROM)>;
-        case 24: return qr_mpc_fused_kernel<24, (24 >= QR_HSG_FROM)>;
-        case 32: return qr_mpc_fused_kernel<32, (32 >= QR_HSG_FROM)>;
-        case 40: return qr_mpc_fused_kernel<40, (40 >= QR_HSG_FROM)>;
-        case 48: return qr_mpc_fused_kernel<48, (48 >= QR_HSG_FROM)>;
-        case 56: return qr_mpc_fused_kernel<56, (56 >= QR_HSG_FROM)>;
-        case 64: return qr_mpc_fused_kernel<64, (64 >= QR_HSG_FROM)>;
+#define QR_CASE(C) case C: return qr_mpc_fused_kernel<C, (C >= QR_HSG_FROM), (C >= QR_KG_FROM_CAP)>;
+        QR_CASE(8) QR_CASE(16) QR_CASE(24) QR_CASE(32) QR_CASE(40) QR_CASE(48) QR_CASE(56) QR_CASE(64) QR_CASE(72)
+        QR_CASE(96) QR_CASE(128)
+#undef QR_CASE
         default: return nullptr;
     }
 }
@@ -120,7 +127,8 @@ __global__ void __launch_bounds__(QR_NT) qr_qp_solve_kernel(const QrMpcArgs A) {
     constexpr int NT = QR_NT;
     QrMpcSmem S;
     qr_mpc_carve(S, smem, A.nfcap, A.P.horizon, A.scratch + (size_t)blockIdx.x * qr_fallback_doubles(A.nfcap),
-                 A.hs_global ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr);
+                 A.hs_global ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr,
+                 A.k_global ? A.k_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr);
     qr_mpc_init_tables<NT>(S, A.nfcap);
     for (int prob = blockIdx.x; prob < A.batch; prob += gridDim.x)
         qr_qp_solve_problem<NT>(A, prob, S);
@@ -170,58 +178,65 @@ qr_qp_options default_options() {
 // Launch geometry of one size class.  *hs_global is set when H does not fit in shared memory next to
 // the matrix under factorisation (capacities above ~44 foot-steps) and has to live in the L2-resident
 // global scratch instead.
-struct GeomEntry { const void* kern; int nfcap, horizon, occ; size_t bytes; bool hsg; };
-GeomEntry g_geom[64];
+// Launch plan of one kernel for one workspace capacity: where the two block-packed matrices live, dynamic shared
+// memory, resident CTAs per SM.  hsg / kg are requests on input (true: keep that matrix in the global scratch) and
+// are forced to true when the workspace would not fit in shared memory otherwise.
+struct Plan {
+    int grid = 0, occ = 0;
+    size_t smem = 0;
+    bool hsg = false, kg = false;
+    size_t scratch_doubles(int nfcap) const {   // per launch: [grid][fallback] [grid][Hs] [grid][K]
+        size_t d = (size_t)grid * qr_fallback_doubles(nfcap);
+        if (hsg) d += (size_t)grid * 9 * qr_ntri(nfcap);
+        if (kg) d += (size_t)grid * 9 * qr_ntri(nfcap);
+        return d;
+    }
+};
+struct GeomEntry { const void* kern; int nfcap, horizon; bool want_hsg, want_kg; Plan plan; };
+GeomEntry g_geom[96];
 int g_ngeom = 0;
 
 template <typename Kern>
-int launch_geometry(Kern kern, int nfcap, int horizon, int batch, int* grid, size_t* smem, int* per_sm,
-                    bool* hs_global = nullptr) {
+int launch_geometry(Kern kern, int nfcap, int horizon, int batch, Plan* out, bool want_hsg = false, bool want_kg = false) {
     if (!kern) return fail(QR_EINVAL, "no kernel instantiated for this size class");
-    // attribute + occupancy queries cost microseconds each: remember them per (kernel, class, horizon)
-    for (int i = 0; i < g_ngeom; ++i) {
+    Plan pl;
+    bool found = false;
+    // attribute + occupancy queries cost microseconds each: remember them per (kernel, class, horizon, request)
+    for (int i = 0; i < g_ngeom && !found; ++i) {
         const GeomEntry& ge = g_geom[i];
-        if (ge.kern == (const void*)kern && ge.nfcap == nfcap && ge.horizon == horizon) {
-            if (hs_global) *hs_global = ge.hsg;
-            else if (ge.hsg) return fail(QR_EINVAL, "workspace does not fit in shared memory");
-            int g = g_ctx.sm_count * ge.occ;
-            if (g > batch) g = batch;
-            if (g < 1) g = 1;
-            *grid = g; *smem = ge.bytes;
-            if (per_sm) *per_sm = ge.occ;
-            return QR_OK;
+        if (ge.kern == (const void*)kern && ge.nfcap == nfcap && ge.horizon == horizon && ge.want_hsg == want_hsg &&
+            ge.want_kg == want_kg) {
+            pl = ge.plan;
+            found = true;
         }
     }
-    size_t bytes = qr_mpc_smem_bytes(nfcap, horizon, true);
-    bool hsg = false;
-    if (bytes + 1024 > g_ctx.smem_optin || (hs_global && *hs_global)) {   // *hs_global preset: the caller asks for H in the scratch
-        bytes = qr_mpc_smem_bytes(nfcap, horizon, false);
-        hsg = true;
+    if (!found) {
+        pl.hsg = want_hsg;
+        pl.kg = want_kg;
+        size_t bytes = qr_mpc_smem_bytes(nfcap, horizon, !pl.hsg, !pl.kg);
+        if (bytes + 1024 > g_ctx.smem_optin && !pl.hsg) { pl.hsg = true; bytes = qr_mpc_smem_bytes(nfcap, horizon, false, !pl.kg); }
+        if (bytes + 1024 > g_ctx.smem_optin && !pl.kg) { pl.kg = true; bytes = qr_mpc_smem_bytes(nfcap, horizon, false, false); }
+        if (bytes + 1024 > g_ctx.smem_optin) return fail(QR_EINVAL, "horizon needs more shared memory than one CTA may use");
+        // opt in to the device maximum once per kernel (the launch's own byte count decides the occupancy)
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_ctx.smem_optin - 256);
+        if (e != cudaSuccess) return fail(QR_ECUDA, "cudaFuncSetAttribute", e);
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, QR_NT, bytes);
+        if (e != cudaSuccess) return fail(QR_ECUDA, "cudaOccupancyMaxActiveBlocksPerMultiprocessor", e);
+        pl.occ = occ < 1 ? 1 : occ;
+        pl.smem = bytes;
+        if (g_ngeom < 96) g_geom[g_ngeom++] = GeomEntry{(const void*)kern, nfcap, horizon, want_hsg, want_kg, pl};
     }
-    if (hs_global) *hs_global = hsg;
-    else if (hsg) return fail(QR_EINVAL, "workspace does not fit in shared memory");
-    if (bytes > g_ctx.smem_optin) return fail(QR_EINVAL, "horizon needs more shared memory than one CTA may use");
-    // opt in to the device maximum once per kernel (the launch's own byte count decides the occupancy)
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_ctx.smem_optin - 256);
-    if (e != cudaSuccess) return fail(QR_ECUDA, "cudaFuncSetAttribute", e);
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, QR_NT, bytes);
-    if (e != cudaSuccess) return fail(QR_ECUDA, "cudaOccupancyMaxActiveBlocksPerMultiprocessor", e);
-    if (occ < 1) occ = 1;
-    if (g_ngeom < 64) g_geom[g_ngeom++] = GeomEntry{(const void*)kern, nfcap, horizon, occ, bytes, hsg};
-    int g = g_ctx.sm_count * occ;
+    int g = g_ctx.sm_count * pl.occ;
     if (g > batch) g = batch;
     if (g < 1) g = 1;
-    *grid = g;
-    *smem = bytes;
-    if (per_sm) *per_sm = occ;
+    pl.grid = g;
+    *out = pl;
     return QR_OK;
 }
 
-// scratch layout: [grid][fallback vectors] followed by [grid][Hessian blocks] (the latter only when needed)
-int ensure_scratch(int grid, int nfcap, bool hs_global = false) {
-    size_t need = (size_t)grid * qr_fallback_doubles(nfcap) * sizeof(double);
-    if (hs_global) need += (size_t)grid * 9 * qr_ntri(nfcap) * sizeof(double);
+int ensure_scratch_doubles(size_t doubles) {
+    const size_t need = doubles * sizeof(double);
     if (need <= g_ctx.scratch_bytes) return QR_OK;
     if (g_ctx.scratch) cudaFree(g_ctx.scratch);
     g_ctx.scratch = nullptr;
@@ -230,6 +245,17 @@ int ensure_scratch(int grid, int nfcap, bool hs_global = false) {
     if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMalloc(scratch)", e);
     g_ctx.scratch_bytes = need;
     return QR_OK;
+}
+
+// Point the kernel arguments at this launch's slices of the scratch.
+void bind_scratch(QrMpcArgs& A, const Plan& pl, int nfcap) {
+    double* s = g_ctx.scratch;
+    A.scratch = s;
+    s += (size_t)pl.grid * qr_fallback_doubles(nfcap);
+    A.hs_global = nullptr;
+    A.k_global = nullptr;
+    if (pl.hsg) { A.hs_global = s; s += (size_t)pl.grid * 9 * qr_ntri(nfcap); }
+    if (pl.kg) A.k_global = s;
 }
 
 int check_params(const qr_mpc_params* P, int batch) {
@@ -281,8 +307,10 @@ extern "C" void qr_gpu_shutdown(void) {
     g_ctx = Ctx();
 }
 
-int num_classes(int horizon) { return (4 * horizon + QR_CLASS_STEP - 1) / QR_CLASS_STEP; }
-int class_cap(int c, int /*horizon*/) { return QR_CLASS_STEP * (c + 1); }   // always one of the instantiated capacities
+int num_classes(int horizon) { return qr_class_of(4 * horizon) + 1; }
+int class_cap(int c, int /*horizon*/) { return qr_class_cap(c); }   // always one of the instantiated capacities
+bool class_hsg(int cap) { return cap >= QR_HSG_FROM_CAP; }
+bool class_kg(int cap) { return cap >= QR_KG_FROM_CAP; }
 
 int ensure_work(int nclass, int batch) {
     const size_t need = ((size_t)2 * nclass + (size_t)nclass * batch) * sizeof(int);
@@ -302,17 +330,14 @@ extern "C" int qr_gpu_mpc_occupancy(int horizon, int stance_footsteps, int* sm_c
     if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
     if (horizon < 1 || horizon > QR_MAX_HORIZON) return fail(QR_EINVAL, "horizon out of range");
     if (stance_footsteps < 0 || stance_footsteps > 4 * horizon) return fail(QR_EINVAL, "stance count out of range");
-    int c = (stance_footsteps + QR_CLASS_STEP - 1) / QR_CLASS_STEP - 1;
-    if (c < 0) c = 0;
-    int grid = 0, occ = 0;
-    size_t smem = 0;
-    bool hsg = class_cap(c, horizon) >= QR_HSG_FROM_CAP;
-    int rc = launch_geometry(fused_kernel_for(class_cap(c, horizon)), class_cap(c, horizon), horizon, 1 << 30, &grid, &smem, &occ, &hsg);
+    const int cap = class_cap(qr_class_of(stance_footsteps), horizon);
+    Plan pl;
+    int rc = launch_geometry(fused_kernel_for(cap), cap, horizon, 1 << 30, &pl, class_hsg(cap), class_kg(cap));
     if (rc) return rc;
     if (sm_count) *sm_count = g_ctx.sm_count;
-    if (ctas_per_sm) *ctas_per_sm = occ;
+    if (ctas_per_sm) *ctas_per_sm = pl.occ;
     if (threads_per_cta) *threads_per_cta = QR_NT;
-    if (smem_bytes) *smem_bytes = (int)smem;
+    if (smem_bytes) *smem_bytes = (int)pl.smem;
     return QR_OK;
 }
 
@@ -330,29 +355,26 @@ extern "C" int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_option
         return fail(QR_EINVAL, "null input/output pointer");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int h = P->horizon, nclass = num_classes(h);
+    QrMpcArgs A;
+    memset(&A, 0, sizeof(A));
+    A.P = *P;
+    A.opt = opt ? *opt : default_options();
+    A.batch = batch;
+    A.p = p; A.v = v; A.quat = quat; A.w = w; A.r_feet = r_feet; A.rpy = rpy; A.traj = traj; A.gait = gait;
+    A.mu_i = mu_i; A.fmax_i = fmax_i;
+    A.grf_out = grf_out; A.u_out = u_out; A.status_out = status_out; A.iters_out = iters_out;
     if (batch <= g_ctx.sm_count) {
         // Latency path: the grid cannot fill the device anyway, so skip the classification and launch the
         // largest size class once (its workspace holds any instance of this horizon).
         const int cap = class_cap(nclass - 1, h);
-        int grid1 = 0;
-        size_t smem1 = 0;
-        bool hsg1 = false;
-        rc = launch_geometry(qr_mpc_fused_latency_kernel, cap, h, batch, &grid1, &smem1, nullptr, &hsg1);
+        Plan pl;
+        rc = launch_geometry(qr_mpc_fused_latency_kernel, cap, h, batch, &pl);
         if (rc) return rc;
-        rc = ensure_scratch(grid1, cap, hsg1);
+        rc = ensure_scratch_doubles(pl.scratch_doubles(cap));
         if (rc) return rc;
-        QrMpcArgs A1;
-        memset(&A1, 0, sizeof(A1));
-        A1.P = *P;
-        A1.opt = opt ? *opt : default_options();
-        A1.batch = batch;
-        A1.nfcap = cap;
-        A1.p = p; A1.v = v; A1.quat = quat; A1.w = w; A1.r_feet = r_feet; A1.rpy = rpy; A1.traj = traj; A1.gait = gait;
-        A1.mu_i = mu_i; A1.fmax_i = fmax_i;
-        A1.grf_out = grf_out; A1.u_out = u_out; A1.status_out = status_out; A1.iters_out = iters_out;
-        A1.scratch = g_ctx.scratch;
-        A1.hs_global = hsg1 ? g_ctx.scratch + (size_t)grid1 * qr_fallback_doubles(cap) : nullptr;
-        qr_mpc_fused_latency_kernel<<<grid1, QR_NT, smem1, st>>>(A1);
+        A.nfcap = cap;
+        bind_scratch(A, pl, cap);
+        qr_mpc_fused_latency_kernel<<<pl.grid, QR_NT, pl.smem, st>>>(A);
         cudaError_t e1 = cudaGetLastError();
         if (e1 != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_fused_latency_kernel", e1);
         return QR_OK;
@@ -362,50 +384,34 @@ extern "C" int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_option
     int* counts = g_ctx.work;
     int* tickets = g_ctx.work + nclass;
     int* lists = g_ctx.work + 2 * nclass;
-    // geometry of every class first (so that the scratch is sized once, before any launch)
-    int grid[16];
-    size_t smem[16];
-    bool hsg[16];
+    // plan of every class first (so that the scratch is sized once, before any launch)
+    Plan plan[QR_NCLASS_MAX];
     size_t scratch_need = 0;
     for (int c = 0; c < nclass; ++c) {
-        hsg[c] = class_cap(c, h) >= QR_HSG_FROM_CAP;
-        rc = launch_geometry(fused_kernel_for(class_cap(c, h)), class_cap(c, h), h, batch, &grid[c], &smem[c], nullptr, &hsg[c]);
+        const int cap = class_cap(c, h);
+        rc = launch_geometry(fused_kernel_for(cap), cap, h, batch, &plan[c], class_hsg(cap), class_kg(cap));
         if (rc) return rc;
-        if (hsg[c] != (class_cap(c, h) >= QR_HSG_FROM_CAP)) return fail(QR_EINVAL, "unexpected shared-memory capacity for this size class");
-        size_t need = (size_t)grid[c] * qr_fallback_doubles(class_cap(c, h));
-        if (hsg[c]) need += (size_t)grid[c] * 9 * qr_ntri(class_cap(c, h));
+        if (plan[c].hsg != class_hsg(cap) || plan[c].kg != class_kg(cap))
+            return fail(QR_EINVAL, "unexpected shared-memory capacity for this size class");
+        const size_t need = plan[c].scratch_doubles(cap);
         if (need > scratch_need) scratch_need = need;
     }
-    if (scratch_need * sizeof(double) > g_ctx.scratch_bytes) {
-        if (g_ctx.scratch) cudaFree(g_ctx.scratch);
-        g_ctx.scratch = nullptr;
-        g_ctx.scratch_bytes = 0;
-        cudaError_t e = cudaMalloc(&g_ctx.scratch, scratch_need * sizeof(double));
-        if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMalloc(scratch)", e);
-        g_ctx.scratch_bytes = scratch_need * sizeof(double);
-    }
-    QrMpcArgs A;
-    memset(&A, 0, sizeof(A));
-    A.P = *P;
-    A.opt = opt ? *opt : default_options();
-    A.batch = batch;
-    A.p = p; A.v = v; A.quat = quat; A.w = w; A.r_feet = r_feet; A.rpy = rpy; A.traj = traj; A.gait = gait;
-    A.mu_i = mu_i; A.fmax_i = fmax_i;
-    A.grf_out = grf_out; A.u_out = u_out; A.status_out = status_out; A.iters_out = iters_out;
-    A.scratch = g_ctx.scratch;
+    rc = ensure_scratch_doubles(scratch_need);
+    if (rc) return rc;
     cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)2 * nclass * sizeof(int), st);
     if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemsetAsync(work counters)", e);
     qr_mpc_classify_kernel<<<(batch + 255) / 256, 256, 0, st>>>(A, nclass, counts, lists);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_classify_kernel", e);
-    // largest workspaces first: their instances take longest
+    // largest workspaces first: their instances take longest.  The classes share the scratch; they run one after
+    // the other on the stream.
     for (int c = nclass - 1; c >= 0; --c) {
         A.nfcap = class_cap(c, h);
-        A.hs_global = hsg[c] ? g_ctx.scratch + (size_t)grid[c] * qr_fallback_doubles(A.nfcap) : nullptr;
+        bind_scratch(A, plan[c], A.nfcap);
         A.list = lists + (size_t)c * batch;
         A.count = counts + c;
         A.next = tickets + c;
-        fused_kernel_for(A.nfcap)<<<grid[c], QR_NT, smem[c], st>>>(A);
+        fused_kernel_for(A.nfcap)<<<plan[c].grid, QR_NT, plan[c].smem, st>>>(A);
         e = cudaGetLastError();
         if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_fused_kernel", e);
     }
@@ -423,11 +429,11 @@ extern "C" int qr_gpu_mpc_condense_batch(const qr_mpc_params* P, int batch, cons
     if (batch == 0) return QR_OK;
     if (!p || !v || !quat || !w || !r_feet || !rpy || !traj || !gait || !H_out || !g_out || !ub_out)
         return fail(QR_EINVAL, "null input/output pointer");
-    int grid = 0;
-    size_t smem = 0;
     // the condense-only kernel needs the tables and the staged rows, not the QP workspace
-    rc = launch_geometry(qr_mpc_condense_kernel, QR_CLASS_STEP, P->horizon, batch, &grid, &smem, nullptr);
+    Plan pl;
+    rc = launch_geometry(qr_mpc_condense_kernel, QR_CLASS_STEP, P->horizon, batch, &pl);
     if (rc) return rc;
+    if (pl.hsg || pl.kg) return fail(QR_EINVAL, "workspace does not fit in shared memory");
     QrMpcArgs A;
     memset(&A, 0, sizeof(A));
     A.P = *P;
@@ -437,7 +443,7 @@ extern "C" int qr_gpu_mpc_condense_batch(const qr_mpc_params* P, int batch, cons
     A.p = p; A.v = v; A.quat = quat; A.w = w; A.r_feet = r_feet; A.rpy = rpy; A.traj = traj; A.gait = gait;
     A.fmax_i = fmax_i;
     A.H_out = H_out; A.g_out = g_out; A.ub_out = ub_out;
-    qr_mpc_condense_kernel<<<grid, QR_NT, smem, (cudaStream_t)cuda_stream>>>(A);
+    qr_mpc_condense_kernel<<<pl.grid, QR_NT, pl.smem, (cudaStream_t)cuda_stream>>>(A);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_condense_kernel", e);
     return QR_OK;
@@ -455,12 +461,10 @@ extern "C" int qr_gpu_qp_solve_batch(int horizon, float mu, const qr_qp_options*
     if (rc) return rc;
     if (batch == 0) return QR_OK;
     if (!H || !g || !ub || (!x_out && !x_out_f64)) return fail(QR_EINVAL, "null input/output pointer");
-    int grid = 0;
-    size_t smem = 0;
-    bool hsg = false;
-    rc = launch_geometry(qr_qp_solve_kernel, 4 * horizon, horizon, batch, &grid, &smem, nullptr, &hsg);
+    Plan pl;
+    rc = launch_geometry(qr_qp_solve_kernel, 4 * horizon, horizon, batch, &pl);
     if (rc) return rc;
-    rc = ensure_scratch(grid, 4 * horizon, hsg);
+    rc = ensure_scratch_doubles(pl.scratch_doubles(4 * horizon));
     if (rc) return rc;
     QrMpcArgs A;
     memset(&A, 0, sizeof(A));
@@ -471,9 +475,8 @@ extern "C" int qr_gpu_qp_solve_batch(int horizon, float mu, const qr_qp_options*
     A.mu_i = mu_i;
     A.H_in = H; A.g_in = g; A.ub_in = ub;
     A.x_out = x_out; A.x_out_f64 = x_out_f64; A.status_out = status_out; A.iters_out = iters_out;
-    A.scratch = g_ctx.scratch;
-    A.hs_global = hsg ? g_ctx.scratch + (size_t)grid * qr_fallback_doubles(A.nfcap) : nullptr;
-    qr_qp_solve_kernel<<<grid, QR_NT, smem, (cudaStream_t)cuda_stream>>>(A);
+    bind_scratch(A, pl, A.nfcap);
+    qr_qp_solve_kernel<<<pl.grid, QR_NT, pl.smem, (cudaStream_t)cuda_stream>>>(A);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_qp_solve_kernel", e);
     return QR_OK;

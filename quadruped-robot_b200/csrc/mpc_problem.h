@@ -18,7 +18,8 @@ struct QrMpcArgs {
     int32_t* status_out;     // [batch] or null
     int32_t* iters_out;      // [batch][2] or null
     double* scratch;         // [teams][qr_fallback_doubles(nfcap)] vectors of the interior-point fallback
-    double* hs_global;       // [teams][9*ntri(nfcap)] Hessian blocks when they do not fit in shared memory, else null
+    double* hs_global;       // [teams][9*ntri(nfcap)] Hessian blocks when they are kept out of shared memory, else null
+    double* k_global;        // [teams][9*ntri(nfcap)] matrix under factorisation when it does not fit in shared memory, else null
     // work list of this launch (size class): problems list[0 .. *count), handed out through *next.
     // list == null: problems 0 .. batch-1.
     const int* list;
@@ -40,9 +41,10 @@ QR_HD size_t qr_kbytes(int nfcap) {
 }
 
 // Shared-memory footprint in bytes for a workspace able to hold nfcap stance foot-steps.
-QR_HD size_t qr_mpc_smem_bytes(int nfcap, int horizon, bool hs_in_smem = true) {
+QR_HD size_t qr_mpc_smem_bytes(int nfcap, int horizon, bool hs_in_smem = true, bool k_in_smem = true) {
     size_t bytes = hs_in_smem ? (size_t)9 * qr_ntri(nfcap) * sizeof(double) : 0;   // Hs
-    bytes += qr_kbytes(nfcap);                                     // K (aliased by the condense tables)
+    bytes += k_in_smem ? qr_kbytes(nfcap)                          // K (aliased by the condense tables)
+                       : ((sizeof(QrCondenseTables) + 15) & ~(size_t)15);   // the tables alone
     bytes += (size_t)(9 + 9 + 6 * 3 + 1) * nfcap * sizeof(double) + 8 * sizeof(double);
     bytes += (size_t)(16 * horizon + 32) * sizeof(float);          // staged traj + gait + state rows
     bytes += (size_t)(3 * nfcap + (nfcap + 1) + 3 * nfcap + 2 * 4 * horizon + 8) * sizeof(int);
@@ -63,14 +65,20 @@ struct QrMpcSmem {
 };
 
 QR_DEV void qr_mpc_carve(QrMpcSmem& S, unsigned char* base, int nfcap, int horizon, double* fallback,
-                         double* hs_global = nullptr) {
+                         double* hs_global = nullptr, double* k_global = nullptr) {
     double* d = reinterpret_cast<double*>(base);
     QrQpWork& W = S.W;
     const int n = 3 * nfcap, m = 5 * nfcap;
     if (hs_global) W.Hs = hs_global;
     else { W.Hs = d; d += 9 * qr_ntri(nfcap); }
-    W.K = d; d = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d) + qr_kbytes(nfcap));
-    S.T = reinterpret_cast<QrCondenseTables*>(W.K);
+    if (k_global) {
+        W.K = k_global;
+        S.T = reinterpret_cast<QrCondenseTables*>(d);
+        d = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d) + ((sizeof(QrCondenseTables) + 15) & ~(size_t)15));
+    } else {
+        W.K = d; d = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d) + qr_kbytes(nfcap));
+        S.T = reinterpret_cast<QrCondenseTables*>(W.K);
+    }
     W.Dinv = d; d += 9 * nfcap;
     W.zv = d; d += 9 * nfcap;
     W.ps = d; d += n; W.g = d; d += n; W.xn = d; d += n; W.q = d; d += n; W.wv = d; d += n;

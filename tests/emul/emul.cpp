@@ -33,8 +33,9 @@ struct EmulTeam {
 static int class_cap_of(const float* gait, float fmax, int horizon) {
     int nf = 0;
     for (int k = 0; k < 4 * horizon; ++k) nf += (gait[k] * fmax > 0.f) ? 1 : 0;
-    int cap = ((nf + 7) / 8) * 8;
-    return cap < 8 ? 8 : cap;   // capacities are multiples of 8, as the instantiated CUDA size classes
+    // the instantiated CUDA size classes: 8 .. 72 in steps of 8, then 96 and 128
+    if (nf <= 72) { const int cap = ((nf + 7) / 8) * 8; return cap < 8 ? 8 : cap; }
+    return nf <= 96 ? 96 : 128;
 }
 
 extern "C" int qr_emul_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_options* opt, int batch,

@@ -29,13 +29,20 @@ CONFIGS = [
     dict(name="a1_h10_musweep", robot="a1", h=10, dt=0.03, gait="trot", seed=102, B=6, mu_sweep=True),
     dict(name="aliengo_h10_mixed", robot="aliengo", h=10, dt=0.03, gait="mixed", seed=103, B=6, mu_sweep=False),
     dict(name="a1_h16_stand", robot="a1", h=16, dt=0.03, gait="stand", seed=104, B=2, mu_sweep=False),
+    # BASELINE.json configs[4]: long-preview MPC, 360 variables.  Beyond the reference's own K_MAX_GAIT_SEGMENTS = 16
+    # (its arrays would overflow), so these are checked against the oracle's restatement + qpOASES only.
+    dict(name="a1_h30_trot", robot="a1", h=30, dt=0.03, gait="trot", seed=105, B=2, mu_sweep=False),
+    dict(name="a1_h30_stand", robot="a1", h=30, dt=0.03, gait="stand", seed=106, B=1, mu_sweep=False),
 ]
 KEYS = ("p", "v", "quat", "w", "r_feet", "rpy", "traj", "gait", "mu", "f_max")
 
 
 def main():
     O.build()
+    only = sys.argv[1:]
     for cfg in CONFIGS:
+        if only and cfg["name"] not in only:
+            continue
         b = pkg.synth.make_mpc_batch(cfg["robot"], cfg["h"], cfg["dt"], cfg["B"], seed=cfg["seed"],
                                      gait=cfg["gait"], mu_sweep=cfg["mu_sweep"])
         h, B = cfg["h"], cfg["B"]

@@ -16,8 +16,11 @@ RTOL, ATOL = 1e-4, 1e-5
 KEYS = ("p", "v", "quat", "w", "r_feet", "rpy", "traj", "gait", "mu", "f_max")
 
 
-def golden_files():
-    return sorted(glob.glob(os.path.join(HERE, "golden", "mpc_*.npz")))
+def golden_files(reference_runnable=False):
+    """All MPC fixtures; reference_runnable=True leaves out the horizon-30 ones (BASELINE configs[4]): the reference's
+    own arrays stop at K_MAX_GAIT_SEGMENTS = 16, so its source build cannot be run on them."""
+    files = sorted(glob.glob(os.path.join(HERE, "golden", "mpc_*.npz")))
+    return [f for f in files if "_h30_" not in f] if reference_runnable else files
 
 
 def load_golden(path, pkg):

@@ -171,7 +171,7 @@ def test_edge_cases(gpu, pkg):
     one = {k: (np.ascontiguousarray(v[3:4]) if isinstance(v, np.ndarray) else v) for k, v in b.items()}
     assert np.array_equal(gpu.mpc_solve_batch_host(P, one, want_u=True)["u"][0], r["u"][3])
     # API errors are codes, not crashes
-    bad = gpu.params_of(b["robot"], 17, dt)
+    bad = gpu.params_of(b["robot"], 33, dt)
     with pytest.raises(gpu.QrGpuError):
         gpu.mpc_solve_batch_host(bad, one)
 

@@ -62,7 +62,7 @@ def _ref_or_skip(oracle):
         pytest.skip("oracle/_ref/libqr_mpc_ref.so not built (needs /root/reference at build time)")
 
 
-@pytest.mark.parametrize("path", parity.golden_files(), ids=os.path.basename)
+@pytest.mark.parametrize("path", parity.golden_files(reference_runnable=True), ids=os.path.basename)
 def test_restatement_matches_reference_source(path, oracle, pkg, monkeypatch):
     """PIN: the reference's own qr_mpc_interface.cpp, compiled UNMODIFIED from /root/reference against
     oracle/mini_eigen (oracle/_ref/libqr_mpc_ref.so), run through its public SetupProblem /
