@@ -203,6 +203,44 @@ int qr_gpu_swing_parabola_batch(int batch, const float* start, const float* end,
                                 const float* phase, int phase_module, float* pos_out, int32_t* valid_out,
                                 void* cuda_stream);
 
+/* qr_gpu_swing_bspline_batch -- replaces qrFootBSplinePatternGenerator (the WALK-mode swing trajectory):
+ * SetParameters + UpdateSpline + GenerateTrajectory (src/controllers/qr_foot_trajectory_generator.cpp:53-163) with
+ * tinynurbs::curveDerivatives (extern/tinynurbs/include/tinynurbs/core/evaluate.h:66-100, core/basis.h:25-66, 163-272)
+ * for `batch` feet.  initial_pos, target_pos [batch][3]; height, duration, initial_time, time [batch];
+ * pos_out, vel_out [batch][3] (metres, metres per unit of spline parameter); valid_out [batch] or NULL (0 where
+ * GenerateTrajectory returns false and the outputs are left untouched). */
+int qr_gpu_swing_bspline_batch(int batch, const float* initial_pos, const float* target_pos, const float* height,
+                               const float* duration, const float* initial_time, const float* time, float* pos_out,
+                               float* vel_out, int32_t* valid_out, void* cuda_stream);
+
+/* Robot constants the foothold planner reads: qrRobot::hipOffset, GetDefaultHipPosition() (3x4, column-major:
+ * m[3*leg + axis]), hipLength, and the planner's swingKp. */
+typedef struct {
+    float hip_offset[12];
+    float hip_pos[12];
+    float hip_len;
+    float swing_kp[3];
+} qr_foothold_params;
+
+/* qr_gpu_foothold_heuristic_batch -- replaces qrFootholdPlanner::ComputeHeuristicFootHold
+ * (src/planner/qr_foothold_planner.cpp:112-240) for `batch` robots.  Rows:
+ *   com_vel [batch][3]  GetBaseVelocityInBaseFrame();  rpy_rate [batch][3]  GetBaseRollPitchYawRate()
+ *   dR, base_R [batch][9] row-major  stateDataFlow.baseRInControlFrame, baseRMat;  rpy [batch][3]
+ *   foot_base [batch][12]  GetFootPositionsInBaseFrame() (3x4 column-major)
+ *   des_speed [batch][3] = stateDes.segment(6,3), des_twist [batch] = stateDes(11),
+ *   des_height [batch] = stateDes(2) - footClearance
+ *   swing_remain, norm_phase [batch][4]  gaitGenerator->swingTimeRemaining / normalizedPhase
+ *   allow_switch, swing_mask [batch][4] int32  allowSwitchLegState; 1 for the legs in swingFootIds
+ *   foothold_io [batch][12]  desiredFootholds (3x4 column-major, base frame): columns of swing legs are overwritten
+ *   phase_io [batch][4]      planner phase of the swing legs
+ * (The reference's footTargetPosition(0,2) / (0,3) writes at :219-222 index a 3-vector out of range and are not
+ * mirrored.) */
+int qr_gpu_foothold_heuristic_batch(const qr_foothold_params* P, int batch, const float* com_vel, const float* rpy_rate,
+                                    const float* dR, const float* base_R, const float* rpy, const float* foot_base,
+                                    const float* des_speed, const float* des_twist, const float* des_height,
+                                    const float* swing_remain, const float* norm_phase, const int32_t* allow_switch,
+                                    const int32_t* swing_mask, float* foothold_io, float* phase_io, void* cuda_stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Force-balance stance controller
  * ------------------------------------------------------------------------------------------------- */

@@ -372,3 +372,38 @@ def force_balance(P: FbParams, foot, acc, contact, inertia=None, gravity=None, f
     st = lib().qro_force_balance(C.byref(P), opt(inertia), _fp(foot), _fp(acc), _ip(contact), opt(gravity), opt(frame),
                                  _fp(force), _fp(G), _fp(a), _fp(Cm), _fp(lb), C.byref(cost))
     return dict(force=force, status=st, cost=cost.value, G=G, a=a, C=Cm, lb=lb)
+
+
+# ------------------------------------------------------------------------------------------------
+# WALK-mode swing trajectory (B-spline via the reference's tinynurbs) and heuristic foothold
+# ------------------------------------------------------------------------------------------------
+class FootholdParams(C.Structure):
+    _fields_ = [("hip_offset", C.c_float * 12), ("hip_pos", C.c_float * 12), ("hip_len", C.c_float), ("swing_kp", C.c_float * 3)]
+
+
+def foothold_params_of(p: dict) -> FootholdParams:
+    P = FootholdParams()
+    P.hip_offset[:] = [float(v) for v in np.asarray(p["hip_offset"], np.float32).reshape(12)]
+    P.hip_pos[:] = [float(v) for v in np.asarray(p["hip_pos"], np.float32).reshape(12)]
+    P.hip_len = p["hip_len"]
+    P.swing_kp[:] = [float(v) for v in p["swing_kp"]]
+    return P
+
+
+def swing_bspline(initial_pos, target_pos, height, duration, initial_time, time):
+    ip, tp = np.ascontiguousarray(initial_pos, np.float32), np.ascontiguousarray(target_pos, np.float32)
+    pos, vel = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    ok = lib().qro_swing_bspline(_fp(ip), _fp(tp), C.c_float(height), C.c_float(duration), C.c_float(initial_time),
+                                 C.c_float(time), _fp(pos), _fp(vel))
+    return pos, vel, bool(ok)
+
+
+def foothold(P: FootholdParams, leg, b: dict, i: int):
+    """Robot i, one leg, of a make_foothold_batch dict: (foothold[3], phase)."""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    fh, ph = np.zeros(12, np.float32), C.c_float()
+    lib().qro_foothold(C.byref(P), int(leg), _fp(f32(b["com_vel"][i])), _fp(f32(b["rpy_rate"][i])), _fp(f32(b["dR"][i])),
+                       _fp(f32(b["base_R"][i])), _fp(f32(b["rpy"][i])), _fp(f32(b["foot_base"][i])), _fp(f32(b["des_speed"][i])),
+                       C.c_float(b["des_twist"][i]), C.c_float(b["des_height"][i]), C.c_float(b["swing_remain"][i, leg]),
+                       int(b["allow_switch"][i, leg]), C.c_float(b["norm_phase"][i, leg]), _fp(fh), C.byref(ph))
+    return fh[3 * leg:3 * leg + 3].copy(), ph.value

@@ -149,6 +149,21 @@ int qro_force_balance(const qro_fb_params* P, const float* inertia, const float*
                       const int* contact, const float* gravity, const float* frame, float* force,
                       float* G_out, float* a_out, float* C_out, float* lb_out, double* cost_out);
 
+/* WALK-mode swing trajectory (cubic B-spline through the reference's vendored tinynurbs) and heuristic foothold
+ * (swing_oracle.cpp).  qro_swing_bspline returns 0 when GenerateTrajectory rejects the time. */
+int qro_swing_bspline(const float* initial_pos, const float* target_pos, float height, float duration,
+                      float initial_time, float time, float* pos, float* vel);
+typedef struct {
+    float hip_offset[12];
+    float hip_pos[12];
+    float hip_len;
+    float swing_kp[3];
+} qro_foothold_params;
+void qro_foothold(const qro_foothold_params* P, int legId, const float* com_vel, const float* w, const float* dR,
+                  const float* base_R, const float* rpy, const float* foot_base, const float* des_speed,
+                  float des_twist, float des_height, float swing_remain, int allow_switch, float norm_phase,
+                  float* foothold, float* phase);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,7 +36,8 @@ def default_options() -> QpOptions:
 EXPORTS = ["qr_gpu_init", "qr_gpu_shutdown", "qr_gpu_last_error", "qr_gpu_mpc_occupancy",
            "qr_gpu_mpc_solve_batch", "qr_gpu_mpc_solve_batch_host", "qr_gpu_mpc_condense_batch",
            "qr_gpu_qp_solve_batch", "qr_gpu_wbc_solve_batch", "qr_gpu_wbc_solve_batch_f64",
-           "qr_gpu_swing_parabola_batch", "qr_gpu_mpc_inputs_batch", "qr_gpu_mpc_leg_torque_batch", "qr_gpu_force_balance_batch", "qr_gpu_wbc_solve_batch_host"]
+           "qr_gpu_swing_parabola_batch", "qr_gpu_mpc_inputs_batch", "qr_gpu_mpc_leg_torque_batch", "qr_gpu_force_balance_batch", "qr_gpu_wbc_solve_batch_host", "qr_gpu_swing_bspline_batch",
+           "qr_gpu_foothold_heuristic_batch"]
 
 
 class WbcModel(C.Structure):
@@ -227,3 +228,33 @@ def wbc_solve_batch_host(model: WbcModel, state, cmd, contact):
     _check(rc, "qr_gpu_wbc_solve_batch_host")
     out["status"] = st
     return out
+
+
+class FootholdParams(C.Structure):
+    """qr_foothold_params of include/qr_gpu.h."""
+    _fields_ = [("hip_offset", C.c_float * 12), ("hip_pos", C.c_float * 12), ("hip_len", C.c_float), ("swing_kp", C.c_float * 3)]
+
+
+def foothold_params_of(p: dict) -> FootholdParams:
+    import numpy as np
+    P = FootholdParams()
+    P.hip_offset[:] = [float(v) for v in np.asarray(p["hip_offset"], np.float32).reshape(12)]
+    P.hip_pos[:] = [float(v) for v in np.asarray(p["hip_pos"], np.float32).reshape(12)]
+    P.hip_len = p["hip_len"]
+    P.swing_kp[:] = [float(v) for v in p["swing_kp"]]
+    return P
+
+
+def swing_bspline_batch_device(initial_pos, target_pos, height, duration, initial_time, time, pos, vel, valid, stream_ptr: int):
+    rc = lib().qr_gpu_swing_bspline_batch(initial_pos.shape[0], _vp(initial_pos), _vp(target_pos), _vp(height), _vp(duration),
+                                          _vp(initial_time), _vp(time), _vp(pos), _vp(vel), _vp(valid), C.c_void_p(stream_ptr))
+    _check(rc, "qr_gpu_swing_bspline_batch")
+
+
+def foothold_heuristic_batch_device(P: FootholdParams, d: dict, foothold, phase, stream_ptr: int):
+    """d: torch CUDA tensors named like make_foothold_batch's keys."""
+    rc = lib().qr_gpu_foothold_heuristic_batch(
+        C.byref(P), d["com_vel"].shape[0], _vp(d["com_vel"]), _vp(d["rpy_rate"]), _vp(d["dR"]), _vp(d["base_R"]), _vp(d["rpy"]),
+        _vp(d["foot_base"]), _vp(d["des_speed"]), _vp(d["des_twist"]), _vp(d["des_height"]), _vp(d["swing_remain"]),
+        _vp(d["norm_phase"]), _vp(d["allow_switch"]), _vp(d["swing_mask"]), _vp(foothold), _vp(phase), C.c_void_p(stream_ptr))
+    _check(rc, "qr_gpu_foothold_heuristic_batch")

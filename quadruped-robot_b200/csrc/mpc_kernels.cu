@@ -838,3 +838,76 @@ extern "C" int qr_gpu_force_balance_batch(const qr_fb_params* P, int batch, cons
     if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_force_balance_kernel", e);
     return QR_OK;
 }
+
+// ==================================================================================================
+// Swing-leg targets: cubic B-spline trajectory and heuristic foothold (one thread per foot)
+// ==================================================================================================
+#include "swing_extra.h"
+
+namespace {
+__global__ void qr_swing_bspline_kernel(int batch, const float* ip, const float* tp, const float* height, const float* duration,
+                                        const float* t0, const float* t, float* pos, float* vel, int32_t* valid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    float p[3], v[3];
+    const int ok = qr_swing_bspline(ip + 3 * (size_t)i, tp + 3 * (size_t)i, height[i], duration[i], t0[i], t[i], p, v);
+    if (ok) {
+        for (int k = 0; k < 3; ++k) { pos[3 * (size_t)i + k] = p[k]; vel[3 * (size_t)i + k] = v[k]; }
+    }
+    if (valid) valid[i] = ok;
+}
+
+struct QrFootholdRows {
+    const float *com_vel, *w, *dR, *base_R, *rpy, *foot_base, *des_speed, *des_twist, *des_height, *swing_remain, *norm_phase;
+    const int32_t *allow_switch, *swing_mask;
+    float *foothold, *phase;
+};
+__global__ void qr_foothold_kernel(const QrFootholdParams P, int batch, const QrFootholdRows R) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = idx >> 2, leg = idx & 3;
+    if (i >= batch || !R.swing_mask[4 * (size_t)i + leg]) return;
+    qr_foothold_heuristic(P, leg, R.com_vel + 3 * (size_t)i, R.w + 3 * (size_t)i, R.dR + 9 * (size_t)i, R.base_R + 9 * (size_t)i,
+                          R.rpy + 3 * (size_t)i, R.foot_base + 12 * (size_t)i, R.des_speed + 3 * (size_t)i, R.des_twist[i],
+                          R.des_height[i], R.swing_remain[4 * (size_t)i + leg], R.allow_switch[4 * (size_t)i + leg],
+                          R.norm_phase[4 * (size_t)i + leg], R.foothold + 12 * (size_t)i, R.phase + 4 * (size_t)i + leg);
+}
+}  // namespace
+
+extern "C" int qr_gpu_swing_bspline_batch(int batch, const float* initial_pos, const float* target_pos, const float* height,
+                                          const float* duration, const float* initial_time, const float* time,
+                                          float* pos_out, float* vel_out, int32_t* valid_out, void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
+    if (batch < 0) return fail(QR_EINVAL, "negative batch");
+    if (batch == 0) return QR_OK;
+    if (!initial_pos || !target_pos || !height || !duration || !initial_time || !time || !pos_out || !vel_out)
+        return fail(QR_EINVAL, "null pointer");
+    qr_swing_bspline_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(batch, initial_pos, target_pos, height, duration,
+                                                                                       initial_time, time, pos_out, vel_out, valid_out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_swing_bspline_kernel", e);
+    return QR_OK;
+}
+
+extern "C" int qr_gpu_foothold_heuristic_batch(const qr_foothold_params* P, int batch, const float* com_vel, const float* rpy_rate,
+                                               const float* dR, const float* base_R, const float* rpy, const float* foot_base,
+                                               const float* des_speed, const float* des_twist, const float* des_height,
+                                               const float* swing_remain, const float* norm_phase, const int32_t* allow_switch,
+                                               const int32_t* swing_mask, float* foothold_io, float* phase_io, void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
+    if (!P || batch < 0) return fail(QR_EINVAL, "null params or negative batch");
+    if (batch == 0) return QR_OK;
+    if (!com_vel || !rpy_rate || !dR || !base_R || !rpy || !foot_base || !des_speed || !des_twist || !des_height ||
+        !swing_remain || !norm_phase || !allow_switch || !swing_mask || !foothold_io || !phase_io)
+        return fail(QR_EINVAL, "null pointer");
+    QrFootholdParams Q;
+    static_assert(sizeof(QrFootholdParams) == sizeof(qr_foothold_params), "layout");
+    memcpy(&Q, P, sizeof(Q));
+    QrFootholdRows R{com_vel, rpy_rate, dR, base_R, rpy, foot_base, des_speed, des_twist, des_height, swing_remain, norm_phase,
+                     allow_switch, swing_mask, foothold_io, phase_io};
+    qr_foothold_kernel<<<(4 * batch + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(Q, batch, R);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_foothold_kernel", e);
+    return QR_OK;
+}

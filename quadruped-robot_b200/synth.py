@@ -259,3 +259,46 @@ def make_fb_batch(robot: str | RobotMPC = "a1", batch: int = 256, seed: int = 0,
         t1 = np.cross(t2, n)
         out["frame"] = np.ascontiguousarray(np.concatenate([n, t1, t2], 1), F32)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Swing-leg workloads
+# ------------------------------------------------------------------------------------------------
+def make_swing_batch(batch: int = 256, seed: int = 0) -> dict:
+    """Feet for the B-spline generator: start / target positions (steps up and down), apex height, duration 1 (the
+    generator is driven with the swing phase), sample times inside and just outside [0, duration]."""
+    rng = np.random.default_rng(seed)
+    B = batch
+    U = rng.uniform
+    ip = np.stack([U(-0.3, 0.3, B), U(-0.2, 0.2, B), U(-0.32, -0.25, B)], 1)
+    tp = ip + np.stack([U(-0.15, 0.25, B), U(-0.08, 0.08, B), U(-0.06, 0.06, B)], 1)
+    tp[: B // 8, :2] = ip[: B // 8, :2]          # purely vertical steps (atan2(0, 0))
+    t = U(-0.002, 1.002, B)
+    t[:8] = [0.0, 1.0, 0.5, 0.05, -0.0015, 1.0015, -0.0005, 1.0005]   # incl. two samples the generator rejects
+    return dict(initial_pos=ip.astype(F32), target_pos=tp.astype(F32), height=U(0.04, 0.12, B).astype(F32),
+                duration=np.ones(B, F32), initial_time=np.zeros(B, F32), time=t.astype(F32))
+
+
+def make_foothold_batch(robot: str | RobotMPC = "a1", batch: int = 256, seed: int = 0) -> dict:
+    """Inputs of ComputeHeuristicFootHold for `batch` robots (see qr_gpu_foothold_heuristic_batch)."""
+    rb = ROBOTS[robot] if isinstance(robot, str) else robot
+    rng = np.random.default_rng(seed)
+    B = batch
+    U = rng.uniform
+    rpy = np.stack([U(-0.15, 0.15, B), U(-0.15, 0.15, B), U(-np.pi, np.pi, B)], 1)
+    base_R = _rot_zyx(rpy)
+    dR = _rot_zyx(np.stack([rpy[:, 0], rpy[:, 1], np.zeros(B)], 1))
+    hips = np.array(rb.hip_positions, float)                       # [4,3]
+    abad = hips.copy(); abad[:, 1] -= np.sign(hips[:, 1]) * rb.hip_len
+    foot_base = hips[None] + np.array([0, 0, -rb.body_height]) + U(-0.06, 0.06, (B, 4, 3))
+    swing = rng.integers(0, 2, (B, 4)).astype(np.int32)
+    swing[:, 0] = 1
+    params = dict(hip_offset=abad.astype(F32).reshape(12), hip_pos=hips.astype(F32).reshape(12), hip_len=rb.hip_len,
+                  swing_kp=(0.03, 0.03, 0.03))
+    return dict(com_vel=U(-0.6, 1.0, (B, 3)).astype(F32), rpy_rate=U(-0.8, 0.8, (B, 3)).astype(F32),
+                dR=np.ascontiguousarray(dR.reshape(B, 9), F32), base_R=np.ascontiguousarray(base_R.reshape(B, 9), F32),
+                rpy=rpy.astype(F32), foot_base=np.ascontiguousarray(foot_base.reshape(B, 12), F32),
+                des_speed=np.stack([U(-0.5, 1.0, B), U(-0.3, 0.3, B), np.zeros(B)], 1).astype(F32),
+                des_twist=U(-0.6, 0.6, B).astype(F32), des_height=np.full(B, rb.body_height - 0.01, F32),
+                swing_remain=U(0.0, 0.25, (B, 4)).astype(F32), norm_phase=U(0, 1, (B, 4)).astype(F32),
+                allow_switch=rng.integers(0, 2, (B, 4)).astype(np.int32), swing_mask=swing, params=params, robot=rb)

@@ -11,6 +11,7 @@
 #include "../../quadruped-robot_b200/csrc/wbc_problem.h"
 #include "../../quadruped-robot_b200/csrc/mpc_io.h"
 #include "../../quadruped-robot_b200/csrc/fb_problem.h"
+#include "../../quadruped-robot_b200/csrc/swing_extra.h"
 
 static qr_qp_options emul_default_options() {
     qr_qp_options o;
@@ -137,4 +138,18 @@ extern "C" void qr_emul_fb_build(const qr_fb_params* P, const float* inertia, co
                                  const int32_t* contact, const float* gravity, const float* frame, float* G, float* a,
                                  float* C, float* lb) {
     qr_fb_build(*P, inertia ? inertia : P->inertia, foot, acc, contact, gravity, frame, G, a, C, lb);
+}
+
+extern "C" int qr_emul_swing_bspline(const float* ip, const float* tp, float height, float duration, float t0, float t,
+                                     float* pos, float* vel) {
+    return qr_swing_bspline(ip, tp, height, duration, t0, t, pos, vel);
+}
+extern "C" void qr_emul_foothold(const qr_foothold_params* P, int leg, const float* com_vel, const float* w, const float* dR,
+                                 const float* base_R, const float* rpy, const float* foot_base, const float* des_speed,
+                                 float des_twist, float des_height, float swing_remain, int allow_switch, float norm_phase,
+                                 float* foothold, float* phase) {
+    QrFootholdParams Q;
+    memcpy(&Q, P, sizeof(Q));
+    qr_foothold_heuristic(Q, leg, com_vel, w, dR, base_R, rpy, foot_base, des_speed, des_twist, des_height, swing_remain,
+                          allow_switch, norm_phase, foothold, phase);
 }

@@ -124,6 +124,27 @@ def fb_build(self, P, batch, i):
     return G, a, Cm, lb
 
 
+def swing_bspline(self, ip, tp, height, duration, t0, t):
+    ip, tp = np.ascontiguousarray(ip, np.float32), np.ascontiguousarray(tp, np.float32)
+    pos, vel = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    ok = self.lib.qr_emul_swing_bspline(self._fp(ip), self._fp(tp), C.c_float(height), C.c_float(duration), C.c_float(t0),
+                                        C.c_float(t), self._fp(pos), self._fp(vel))
+    return pos, vel, bool(ok)
+
+
+def foothold(self, P, leg, b, i):
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    fh, ph = np.zeros(12, np.float32), C.c_float()
+    self.lib.qr_emul_foothold(C.byref(P), int(leg), self._fp(f32(b["com_vel"][i])), self._fp(f32(b["rpy_rate"][i])),
+                              self._fp(f32(b["dR"][i])), self._fp(f32(b["base_R"][i])), self._fp(f32(b["rpy"][i])),
+                              self._fp(f32(b["foot_base"][i])), self._fp(f32(b["des_speed"][i])), C.c_float(b["des_twist"][i]),
+                              C.c_float(b["des_height"][i]), C.c_float(b["swing_remain"][i, leg]), int(b["allow_switch"][i, leg]),
+                              C.c_float(b["norm_phase"][i, leg]), self._fp(fh), C.byref(ph))
+    return fh[3 * leg:3 * leg + 3].copy(), ph.value
+
+
+Emul.swing_bspline = swing_bspline
+Emul.foothold = foothold
 Emul.wbc_solve = wbc_solve
 Emul.swing_parabola = swing_parabola
 Emul.force_balance = force_balance
