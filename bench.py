@@ -247,6 +247,21 @@ def bench_wbc_and_full_step(pkg, capi, torch, stream):
                                     "swing parabola, WBIC (BASELINE configs[1]), batch 1024 on the device",
                         "value": B / ms * 1e3, "unit": "robot ticks/s", "ms_per_step": ms,
                         "mpc_not_converged": int((o["status"] != 0).sum()), "wbc_status_nonzero": int((st != 0).sum())}
+    # BASELINE configs[3]: Aliengo, gait drawn per instance (trot / walk / gallop: different contact masks and numbers of
+    # eliminated swing variables -> several size classes in one call), batch 16384
+    B, h, dt = 16384, 10, 0.03
+    mb = pkg.synth.make_mpc_batch("aliengo", h, dt, B, seed=15, gait="mixed")
+    Pm = capi.params_of(pkg.robots.ROBOTS["aliengo"], h, dt)
+    dm = {k: dev(mb[k]) for k in KEYS}
+    om = dict(grf=torch.empty((B, 12), device="cuda"), status=torch.empty(B, dtype=torch.int32, device="cuda"),
+              iters=torch.empty((B, 2), dtype=torch.int32, device="cuda"))
+    ms = _time_ms(torch, lambda: capi.mpc_solve_batch_device(Pm, dm, om, stream), 5, warm=2)
+    nf = (mb["gait"] > 0).sum(1)
+    out["mixed_gait"] = {"workload": "Aliengo convex MPC h=10, gait drawn per instance (trot / walk / gallop), batch 16384 "
+                                     "(BASELINE configs[3])", "value": B / ms * 1e3, "unit": "QP/s", "ms_per_step": ms,
+                         "not_converged": int((om["status"] != 0).sum()),
+                         "stance_footsteps_min_mean_max": [int(nf.min()), float(nf.mean()), int(nf.max())],
+                         "rounds_mean": float(om["iters"][:, 1].float().mean())}
     # BASELINE configs[4]: horizon-30 long-preview MPC (360 variables), batch 4096, A1 trot
     B, h, dt = 4096, 30, 0.03
     mb = pkg.synth.make_mpc_batch("a1", h, dt, B, seed=14, gait="trot")
