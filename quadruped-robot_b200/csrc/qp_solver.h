@@ -267,9 +267,6 @@ QR_DEV void qr_ldl_backward(QrQpWork& W, int nb, double* out QR_PROF_ARG) {
     double* y = W.wv;
 #ifdef QR_ON_DEVICE
     if (NT >= 32 && nb <= 32) {
-#ifdef QR_EXP_REPEAT
-        for (int rep_ = 0; rep_ < QR_EXP_REPEAT; ++rep_)
-#endif
         if (threadIdx.x < 32) {
             const int lane = threadIdx.x;
             const int me = lane < nb ? lane : 0;
