@@ -135,3 +135,15 @@ extern "C" int qro_force_balance(const qro_fb_params* P, const float* inertia, c
     for (int i = 0; i < 12; ++i) force[i] = invalid ? 0.f : -float(x[i]);
     return invalid ? 3 : (std::isinf(cost) ? 1 : 0);
 }
+
+// Generic inequality-constrained QP through the reference's QuadProg++: min 1/2 x'Gx + g0'x  s.t. C[i].x + c0[i] >= 0.
+// G n x n row-major (symmetric), C m rows of n.  Returns QuadProg++'s cost (inf when it reports infeasibility).
+extern "C" double qro_quadprog_ineq(int n, int m, const double* G, const double* g0, const double* C, const double* c0, double* x) {
+    quadprogpp::Matrix<double> GG(n, n), CI(n, m), CE(n, 0);
+    quadprogpp::Vector<double> gg(n), ci(m), ce(0), xx(n);
+    for (int i = 0; i < n; ++i) { gg[i] = g0[i]; for (int j = 0; j < n; ++j) GG[i][j] = G[i * n + j]; }
+    for (int i = 0; i < m; ++i) { ci[i] = c0[i]; for (int k = 0; k < n; ++k) CI[k][i] = C[i * n + k]; }
+    const double cost = quadprogpp::solve_quadprog(GG, gg, CE, ce, CI, ci, xx);
+    for (int i = 0; i < n; ++i) x[i] = xx[i];
+    return cost;
+}

@@ -407,3 +407,14 @@ def foothold(P: FootholdParams, leg, b: dict, i: int):
                        C.c_float(b["des_twist"][i]), C.c_float(b["des_height"][i]), C.c_float(b["swing_remain"][i, leg]),
                        int(b["allow_switch"][i, leg]), C.c_float(b["norm_phase"][i, leg]), _fp(fh), C.byref(ph))
     return fh[3 * leg:3 * leg + 3].copy(), ph.value
+
+
+def quadprog_ineq(G, g0, Cm, c0):
+    """min 1/2 x'Gx + g0'x s.t. Cm x + c0 >= 0 through the reference's QuadProg++: (x, cost)."""
+    G, g0, Cm, c0 = (np.ascontiguousarray(a, np.float64) for a in (G, g0, Cm, c0))
+    n, m = G.shape[0], Cm.shape[0]
+    x = np.zeros(n)
+    f = lib().qro_quadprog_ineq
+    f.restype = C.c_double
+    cost = f(n, m, _dp(G), _dp(g0), _dp(Cm), _dp(c0), _dp(x))
+    return x, cost

@@ -149,6 +149,8 @@ int qro_force_balance(const qro_fb_params* P, const float* inertia, const float*
                       const int* contact, const float* gravity, const float* frame, float* force,
                       float* G_out, float* a_out, float* C_out, float* lb_out, double* cost_out);
 
+double qro_quadprog_ineq(int n, int m, const double* G, const double* g0, const double* C, const double* c0, double* x);
+
 /* WALK-mode swing trajectory (cubic B-spline through the reference's vendored tinynurbs) and heuristic foothold
  * (swing_oracle.cpp).  qro_swing_bspline returns 0 when GenerateTrajectory rejects the time. */
 int qro_swing_bspline(const float* initial_pos, const float* target_pos, float height, float duration,

@@ -153,3 +153,9 @@ extern "C" void qr_emul_foothold(const qr_foothold_params* P, int leg, const flo
     qr_foothold_heuristic(Q, leg, com_vel, w, dR, base_R, rpy, foot_base, des_speed, des_twist, des_height, swing_remain,
                           allow_switch, norm_phase, foothold, phase);
 }
+
+extern "C" int qr_emul_small_qp(int n, int m, const double* G, const double* g0, const double* C, const double* c0, double* x,
+                                int* iters) {
+    QrSmallQpWork W;
+    return qr_small_qp_solve(n, m, G, g0, C, c0, x, W, iters);
+}

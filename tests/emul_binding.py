@@ -143,6 +143,17 @@ def foothold(self, P, leg, b, i):
     return fh[3 * leg:3 * leg + 3].copy(), ph.value
 
 
+def small_qp(self, G, g0, Cm, c0):
+    G, g0, Cm, c0 = (np.ascontiguousarray(a, np.float64) for a in (G, g0, Cm, c0))
+    n, m = G.shape[0], Cm.shape[0]
+    x = np.zeros(n)
+    it = C.c_int()
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    st = self.lib.qr_emul_small_qp(n, m, dp(G), dp(g0), dp(Cm), dp(c0), dp(x), C.byref(it))
+    return x, st, it.value
+
+
+Emul.small_qp = small_qp
 Emul.swing_bspline = swing_bspline
 Emul.foothold = foothold
 Emul.wbc_solve = wbc_solve

@@ -92,3 +92,36 @@ def test_gpu_matches_oracle(robot, world, tilted, seed, pkg, gpu, oracle, emul):
     e = emul.force_balance(P, b)
     assert np.abs(f - e["force"]).max() < 2e-5
     assert (st.cpu().numpy() != 3).all()
+
+
+def test_small_qp_solver_against_quadprog(emul, oracle):
+    """csrc/small_qp.h alone against the reference's QuadProg++ on random strictly convex QPs: generic, heavily
+    constrained, with duplicated / parallel rows (linearly dependent candidates) and with infeasible row pairs."""
+    rng = np.random.default_rng(71)
+    n_inf = 0
+    for trial in range(300):
+        n = int(rng.integers(2, 13))
+        m = int(rng.integers(1, 25))
+        M = rng.normal(size=(n, n))
+        G = M @ M.T + 0.05 * np.eye(n)
+        g0 = rng.normal(size=n) * 3
+        Cm = rng.normal(size=(m, n))
+        c0 = rng.normal(size=m) + (0.5 if trial % 3 else -0.5)
+        kind = trial % 5
+        if kind == 1 and m >= 4:      # duplicated and scaled rows
+            Cm[1] = Cm[0]; c0[1] = c0[0]
+            Cm[3] = 2.0 * Cm[2]; c0[3] = 2.0 * c0[2] + 0.1
+        if kind == 2 and m >= 2:      # parallel rows forming a slab (feasible)
+            Cm[1] = -Cm[0]; c0[1] = -c0[0] + 1.0
+        if kind == 3 and m >= 2:      # contradictory pair (infeasible)
+            Cm[1] = -Cm[0]; c0[0] = -1.0; c0[1] = -1.0
+        xo, cost = oracle.quadprog_ineq(G, g0, Cm, c0)
+        xe, st, it = emul.small_qp(G, g0, Cm, c0)
+        if np.isinf(cost):
+            n_inf += 1
+            assert st == 1, (trial, st)
+            continue
+        assert st == 0, (trial, st, cost)
+        assert np.abs(xe - xo).max() <= 1e-7 * (1 + np.abs(xo).max()), (trial, np.abs(xe - xo).max())
+        assert (Cm @ xe + c0 >= -1e-8).all()
+    assert n_inf >= 40
