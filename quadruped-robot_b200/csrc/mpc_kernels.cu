@@ -88,9 +88,12 @@ __global__ void __launch_bounds__(QR_NT, QR_FUSED_MIN_CTAS) qr_mpc_fused_kernel(
 
 // Latency path (batches that cannot fill the device): one instantiation with the capacity as a runtime value, both
 // matrices in shared memory whenever they fit and no register cap -- per-instance latency matters here, not occupancy.
-__global__ void __launch_bounds__(QR_NT, 1) qr_mpc_fused_latency_kernel(const QrMpcArgs A) {
+#ifndef QR_LAT_NT
+#define QR_LAT_NT 256   // a wider team shortens the phases with plenty of parallel work (condensing, early LDL' steps)
+#endif
+__global__ void __launch_bounds__(QR_LAT_NT, 1) qr_mpc_fused_latency_kernel(const QrMpcArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int NT = QR_NT;
+    constexpr int NT = QR_LAT_NT;
     QrMpcSmem S;
     qr_mpc_carve(S, smem, A.nfcap, A.P.horizon, A.scratch + (size_t)blockIdx.x * qr_fallback_doubles(A.nfcap),
                  A.hs_global ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr,
@@ -374,7 +377,7 @@ extern "C" int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_option
         if (rc) return rc;
         A.nfcap = cap;
         bind_scratch(A, pl, cap);
-        qr_mpc_fused_latency_kernel<<<pl.grid, QR_NT, pl.smem, st>>>(A);
+        qr_mpc_fused_latency_kernel<<<pl.grid, QR_LAT_NT, pl.smem, st>>>(A);
         cudaError_t e1 = cudaGetLastError();
         if (e1 != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_fused_latency_kernel", e1);
         return QR_OK;
