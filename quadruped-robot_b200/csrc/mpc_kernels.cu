@@ -56,17 +56,34 @@ __global__ void qr_mpc_classify_kernel(const QrMpcArgs A, int nclass, int* count
 // kernel stops at 4 CTAs per SM.  Measured on B200 (A1 trot, 65536 instances): Hessian in the L2-resident scratch
 // and a 96-register cap -> 5 CTAs per SM, +5 % QP/s (3.11 -> 3.27 M); 80 registers / 6 CTAs: +2.5 % (spills);
 // the Hessian in the scratch at unchanged occupancy costs nothing (its reads are three streaming passes per round).
-#ifndef QR_FUSED_MIN_CTAS
-#define QR_FUSED_MIN_CTAS 5
+// Team size and resident CTAs per size class.  The classes up to 24 foot-steps (the trot / walk gaits at h = 10) are
+// bound by the instruction count of their busiest warp and by the SM's register file: 96 threads x 6 CTAs per SM
+// measured +2.9 % QP/s over 128 x 5 (64 x 7: -3 %; 96 x 7 at 80 registers: spills, +-0).  From 32 foot-steps on,
+// shared memory alone limits the SM to 4, 3, 2 and then 1 CTA: no register cap is needed there, and the classes left
+// with one CTA per SM get a 256-thread team (the early steps of their factorisations have hundreds of tiles).
+#ifndef QR_NT_SMALL
+#define QR_NT_SMALL 96
+#endif
+#ifndef QR_CTAS_SMALL
+#define QR_CTAS_SMALL 6
+#endif
+#ifndef QR_NT_LARGE
+#define QR_NT_LARGE 256
 #endif
 #ifndef QR_HSG_FROM
 #define QR_HSG_FROM 8     // smallest capacity that keeps the Hessian in the global scratch (8: every class)
 #endif
+__host__ __device__ constexpr int qr_fused_nt(int cap) {
+    return cap <= 24 ? QR_NT_SMALL : (cap >= 56 && cap <= 72 ? QR_NT_LARGE : QR_NT);
+}
+__host__ __device__ constexpr int qr_fused_min_ctas(int cap) {
+    return cap <= 24 ? QR_CTAS_SMALL : (cap == 32 ? 4 : (cap == 40 ? 3 : (cap == 48 ? 2 : (cap <= 72 ? 1 : 5))));
+}
 template <int CAP, bool HSG, bool KG>
-__global__ void __launch_bounds__(QR_NT, QR_FUSED_MIN_CTAS) qr_mpc_fused_kernel(const QrMpcArgs A) {
+__global__ void __launch_bounds__(qr_fused_nt(CAP), qr_fused_min_ctas(CAP)) qr_mpc_fused_kernel(const QrMpcArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_ticket;
-    constexpr int NT = QR_NT;
+    constexpr int NT = qr_fused_nt(CAP);
     QrMpcSmem S;
     qr_mpc_carve(S, smem, CAP, A.P.horizon, A.scratch + (size_t)blockIdx.x * qr_fallback_doubles(CAP),
                  HSG ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(CAP) : nullptr,
@@ -145,10 +162,14 @@ struct Ctx {
     int device = 0;
     int sm_count = 0;
     size_t smem_optin = 0;
-    double* scratch = nullptr;
-    size_t scratch_bytes = 0;
-    int* work = nullptr;          // [2*nclass] counters (counts, tickets) followed by [nclass][batch] lists
-    size_t work_bytes = 0;
+    // Per-launch device buffers exist twice ("lanes"): the *_host entry point solves a large batch as two chunks
+    // on two streams, so that the second chunk's upload runs under the first chunk's kernels and its CTAs move in
+    // as the first chunk's CTAs retire.  Everything else uses lane 0.
+    double* scratch_[2] = {nullptr, nullptr};
+    size_t scratch_bytes_[2] = {0, 0};
+    int* work_[2] = {nullptr, nullptr};   // [2*nclass] counters (counts, tickets) followed by [nclass][batch] lists
+    size_t work_bytes_[2] = {0, 0};
+    cudaStream_t stream2 = nullptr;       // lane 1 of the *_host entry point
     // staging buffers of the *_host entry point
     unsigned char* stage = nullptr;
     size_t stage_bytes = 0;
@@ -200,7 +221,8 @@ GeomEntry g_geom[96];
 int g_ngeom = 0;
 
 template <typename Kern>
-int launch_geometry(Kern kern, int nfcap, int horizon, int batch, Plan* out, bool want_hsg = false, bool want_kg = false) {
+int launch_geometry(Kern kern, int nfcap, int horizon, int batch, Plan* out, bool want_hsg = false, bool want_kg = false,
+                    int nt = QR_NT) {
     if (!kern) return fail(QR_EINVAL, "no kernel instantiated for this size class");
     Plan pl;
     bool found = false;
@@ -224,7 +246,7 @@ int launch_geometry(Kern kern, int nfcap, int horizon, int batch, Plan* out, boo
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_ctx.smem_optin - 256);
         if (e != cudaSuccess) return fail(QR_ECUDA, "cudaFuncSetAttribute", e);
         int occ = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, QR_NT, bytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, bytes);
         if (e != cudaSuccess) return fail(QR_ECUDA, "cudaOccupancyMaxActiveBlocksPerMultiprocessor", e);
         pl.occ = occ < 1 ? 1 : occ;
         pl.smem = bytes;
@@ -238,21 +260,21 @@ int launch_geometry(Kern kern, int nfcap, int horizon, int batch, Plan* out, boo
     return QR_OK;
 }
 
-int ensure_scratch_doubles(size_t doubles) {
+int ensure_scratch_doubles(size_t doubles, int lane = 0) {
     const size_t need = doubles * sizeof(double);
-    if (need <= g_ctx.scratch_bytes) return QR_OK;
-    if (g_ctx.scratch) cudaFree(g_ctx.scratch);
-    g_ctx.scratch = nullptr;
-    g_ctx.scratch_bytes = 0;
-    cudaError_t e = cudaMalloc(&g_ctx.scratch, need);
+    if (need <= g_ctx.scratch_bytes_[lane]) return QR_OK;
+    if (g_ctx.scratch_[lane]) cudaFree(g_ctx.scratch_[lane]);
+    g_ctx.scratch_[lane] = nullptr;
+    g_ctx.scratch_bytes_[lane] = 0;
+    cudaError_t e = cudaMalloc(&g_ctx.scratch_[lane], need);
     if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMalloc(scratch)", e);
-    g_ctx.scratch_bytes = need;
+    g_ctx.scratch_bytes_[lane] = need;
     return QR_OK;
 }
 
 // Point the kernel arguments at this launch's slices of the scratch.
-void bind_scratch(QrMpcArgs& A, const Plan& pl, int nfcap) {
-    double* s = g_ctx.scratch;
+void bind_scratch(QrMpcArgs& A, const Plan& pl, int nfcap, int lane = 0) {
+    double* s = g_ctx.scratch_[lane];
     A.scratch = s;
     s += (size_t)pl.grid * qr_fallback_doubles(nfcap);
     A.hs_global = nullptr;
@@ -301,8 +323,11 @@ extern "C" int qr_gpu_init(int device) {
 
 extern "C" void qr_gpu_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_ctx.scratch) cudaFree(g_ctx.scratch);
-    if (g_ctx.work) cudaFree(g_ctx.work);
+    for (int l = 0; l < 2; ++l) {
+        if (g_ctx.scratch_[l]) cudaFree(g_ctx.scratch_[l]);
+        if (g_ctx.work_[l]) cudaFree(g_ctx.work_[l]);
+    }
+    if (g_ctx.stream2) cudaStreamDestroy(g_ctx.stream2);
     if (g_ctx.stage) cudaFree(g_ctx.stage);
     if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
     if (g_ctx.pin) cudaFreeHost(g_ctx.pin);
@@ -315,15 +340,15 @@ int class_cap(int c, int /*horizon*/) { return qr_class_cap(c); }   // always on
 bool class_hsg(int cap) { return cap >= QR_HSG_FROM_CAP; }
 bool class_kg(int cap) { return cap >= QR_KG_FROM_CAP; }
 
-int ensure_work(int nclass, int batch) {
+int ensure_work(int nclass, int batch, int lane = 0) {
     const size_t need = ((size_t)2 * nclass + (size_t)nclass * batch) * sizeof(int);
-    if (need <= g_ctx.work_bytes) return QR_OK;
-    if (g_ctx.work) cudaFree(g_ctx.work);
-    g_ctx.work = nullptr;
-    g_ctx.work_bytes = 0;
-    cudaError_t e = cudaMalloc(&g_ctx.work, need);
+    if (need <= g_ctx.work_bytes_[lane]) return QR_OK;
+    if (g_ctx.work_[lane]) cudaFree(g_ctx.work_[lane]);
+    g_ctx.work_[lane] = nullptr;
+    g_ctx.work_bytes_[lane] = 0;
+    cudaError_t e = cudaMalloc(&g_ctx.work_[lane], need);
     if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMalloc(work lists)", e);
-    g_ctx.work_bytes = need;
+    g_ctx.work_bytes_[lane] = need;
     return QR_OK;
 }
 
@@ -335,21 +360,21 @@ extern "C" int qr_gpu_mpc_occupancy(int horizon, int stance_footsteps, int* sm_c
     if (stance_footsteps < 0 || stance_footsteps > 4 * horizon) return fail(QR_EINVAL, "stance count out of range");
     const int cap = class_cap(qr_class_of(stance_footsteps), horizon);
     Plan pl;
-    int rc = launch_geometry(fused_kernel_for(cap), cap, horizon, 1 << 30, &pl, class_hsg(cap), class_kg(cap));
+    int rc = launch_geometry(fused_kernel_for(cap), cap, horizon, 1 << 30, &pl, class_hsg(cap), class_kg(cap), qr_fused_nt(cap));
     if (rc) return rc;
     if (sm_count) *sm_count = g_ctx.sm_count;
     if (ctas_per_sm) *ctas_per_sm = pl.occ;
-    if (threads_per_cta) *threads_per_cta = QR_NT;
+    if (threads_per_cta) *threads_per_cta = qr_fused_nt(cap);
     if (smem_bytes) *smem_bytes = (int)pl.smem;
     return QR_OK;
 }
 
-extern "C" int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_options* opt, int batch,
-                                      const float* p, const float* v, const float* quat,
-                                      const float* w, const float* r_feet, const float* rpy,
-                                      const float* traj, const float* gait, const float* mu_i,
-                                      const float* fmax_i, float* grf_out, float* u_out,
-                                      int32_t* status_out, int32_t* iters_out, void* cuda_stream) {
+static int mpc_solve_batch_lane(int lane, const qr_mpc_params* P, const qr_qp_options* opt, int batch,
+                                const float* p, const float* v, const float* quat,
+                                const float* w, const float* r_feet, const float* rpy,
+                                const float* traj, const float* gait, const float* mu_i,
+                                const float* fmax_i, float* grf_out, float* u_out,
+                                int32_t* status_out, int32_t* iters_out, void* cuda_stream) {
     std::lock_guard<std::mutex> lk(g_mu);
     int rc = check_params(P, batch);
     if (rc) return rc;
@@ -371,35 +396,35 @@ extern "C" int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_option
         // largest size class once (its workspace holds any instance of this horizon).
         const int cap = class_cap(nclass - 1, h);
         Plan pl;
-        rc = launch_geometry(qr_mpc_fused_latency_kernel, cap, h, batch, &pl);
+        rc = launch_geometry(qr_mpc_fused_latency_kernel, cap, h, batch, &pl, false, false, QR_LAT_NT);
         if (rc) return rc;
-        rc = ensure_scratch_doubles(pl.scratch_doubles(cap));
+        rc = ensure_scratch_doubles(pl.scratch_doubles(cap), lane);
         if (rc) return rc;
         A.nfcap = cap;
-        bind_scratch(A, pl, cap);
+        bind_scratch(A, pl, cap, lane);
         qr_mpc_fused_latency_kernel<<<pl.grid, QR_LAT_NT, pl.smem, st>>>(A);
         cudaError_t e1 = cudaGetLastError();
         if (e1 != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_fused_latency_kernel", e1);
         return QR_OK;
     }
-    rc = ensure_work(nclass, batch);
+    rc = ensure_work(nclass, batch, lane);
     if (rc) return rc;
-    int* counts = g_ctx.work;
-    int* tickets = g_ctx.work + nclass;
-    int* lists = g_ctx.work + 2 * nclass;
+    int* counts = g_ctx.work_[lane];
+    int* tickets = g_ctx.work_[lane] + nclass;
+    int* lists = g_ctx.work_[lane] + 2 * nclass;
     // plan of every class first (so that the scratch is sized once, before any launch)
     Plan plan[QR_NCLASS_MAX];
     size_t scratch_need = 0;
     for (int c = 0; c < nclass; ++c) {
         const int cap = class_cap(c, h);
-        rc = launch_geometry(fused_kernel_for(cap), cap, h, batch, &plan[c], class_hsg(cap), class_kg(cap));
+        rc = launch_geometry(fused_kernel_for(cap), cap, h, batch, &plan[c], class_hsg(cap), class_kg(cap), qr_fused_nt(cap));
         if (rc) return rc;
         if (plan[c].hsg != class_hsg(cap) || plan[c].kg != class_kg(cap))
             return fail(QR_EINVAL, "unexpected shared-memory capacity for this size class");
         const size_t need = plan[c].scratch_doubles(cap);
         if (need > scratch_need) scratch_need = need;
     }
-    rc = ensure_scratch_doubles(scratch_need);
+    rc = ensure_scratch_doubles(scratch_need, lane);
     if (rc) return rc;
     cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)2 * nclass * sizeof(int), st);
     if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemsetAsync(work counters)", e);
@@ -410,15 +435,25 @@ extern "C" int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_option
     // the other on the stream.
     for (int c = nclass - 1; c >= 0; --c) {
         A.nfcap = class_cap(c, h);
-        bind_scratch(A, plan[c], A.nfcap);
+        bind_scratch(A, plan[c], A.nfcap, lane);
         A.list = lists + (size_t)c * batch;
         A.count = counts + c;
         A.next = tickets + c;
-        fused_kernel_for(A.nfcap)<<<plan[c].grid, QR_NT, plan[c].smem, st>>>(A);
+        fused_kernel_for(A.nfcap)<<<plan[c].grid, qr_fused_nt(A.nfcap), plan[c].smem, st>>>(A);
         e = cudaGetLastError();
         if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_fused_kernel", e);
     }
     return QR_OK;
+}
+
+extern "C" int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_options* opt, int batch,
+                                      const float* p, const float* v, const float* quat,
+                                      const float* w, const float* r_feet, const float* rpy,
+                                      const float* traj, const float* gait, const float* mu_i,
+                                      const float* fmax_i, float* grf_out, float* u_out,
+                                      int32_t* status_out, int32_t* iters_out, void* cuda_stream) {
+    return mpc_solve_batch_lane(0, P, opt, batch, p, v, quat, w, r_feet, rpy, traj, gait, mu_i, fmax_i, grf_out, u_out,
+                                status_out, iters_out, cuda_stream);
 }
 
 extern "C" int qr_gpu_mpc_condense_batch(const qr_mpc_params* P, int batch, const float* p,
@@ -519,10 +554,60 @@ extern "C" int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_o
     cudaStream_t st = g_ctx.stream;
     float* d = reinterpret_cast<float*>(g_ctx.stage);
     cudaError_t e = cudaSuccess;
+    const bool packed = bytes <= (size_t)256 * 1024;
+    if (!packed) {
+        // Large batches: device row arrays [B][K] in the staging buffer; the batch is cut into (at most) two chunks of
+        // whole rows, each chunk uploaded, solved and downloaded on its own stream with its own scratch lane.  The
+        // first chunk is small, so the kernels start after a fraction of the upload and the rest of the upload (and
+        // the first chunk's download) runs under them; the second chunk's CTAs move onto the SMs as the first
+        // chunk's CTAs retire, so the cut costs no tail.
+        struct Row { const float* src; float* dev; size_t k; };
+        Row rows[10] = {{p, nullptr, 3}, {v, nullptr, 3}, {quat, nullptr, 4}, {w, nullptr, 3}, {r_feet, nullptr, 12},
+                        {rpy, nullptr, 3}, {traj, nullptr, (size_t)12 * h}, {gait, nullptr, (size_t)4 * h},
+                        {mu_i, nullptr, 1}, {fmax_i, nullptr, 1}};
+        for (Row& r : rows) { r.dev = d; d += B * r.k; }
+        float* dgrf = d; d += B * 12;
+        float* du = nullptr;
+        if (u_out) { du = d; d += B * 12 * h; }
+        int32_t* dstat = reinterpret_cast<int32_t*>(d);
+        int32_t* dit = dstat + B;
+        if (!g_ctx.stream2) {
+            std::lock_guard<std::mutex> lk(g_mu);
+            e = cudaStreamCreateWithFlags(&g_ctx.stream2, cudaStreamNonBlocking);
+            if (e != cudaSuccess) return fail(QR_ECUDA, "cudaStreamCreate", e);
+        }
+        const size_t first = B >= 8192 ? B / 8 : B;
+        const size_t cut[3] = {0, first, B};
+        const int nchunk = first < B ? 2 : 1;
+        for (int c = 0; c < nchunk; ++c) {
+            cudaStream_t cs = c == 0 ? g_ctx.stream : g_ctx.stream2;
+            const size_t b0 = cut[c], nb = cut[c + 1] - cut[c];
+            for (const Row& r : rows)
+                if (r.src && e == cudaSuccess)
+                    e = cudaMemcpyAsync(r.dev + b0 * r.k, r.src + b0 * r.k, nb * r.k * sizeof(float), cudaMemcpyHostToDevice, cs);
+            if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpyAsync H2D", e);
+            auto at = [&](const Row& r) -> const float* { return r.src ? r.dev + b0 * r.k : nullptr; };
+            int rc = mpc_solve_batch_lane(c, P, opt, (int)nb, at(rows[0]), at(rows[1]), at(rows[2]), at(rows[3]), at(rows[4]),
+                                          at(rows[5]), at(rows[6]), at(rows[7]), at(rows[8]), at(rows[9]),
+                                          dgrf + b0 * 12, du ? du + b0 * 12 * h : nullptr, dstat + b0, dit + 2 * b0, cs);
+            if (rc) return rc;
+            e = cudaMemcpyAsync(grf_out + b0 * 12, dgrf + b0 * 12, nb * 12 * sizeof(float), cudaMemcpyDeviceToHost, cs);
+            if (e == cudaSuccess && u_out)
+                e = cudaMemcpyAsync(u_out + b0 * 12 * h, du + b0 * 12 * h, nb * 12 * h * sizeof(float), cudaMemcpyDeviceToHost, cs);
+            if (e == cudaSuccess && status_out)
+                e = cudaMemcpyAsync(status_out + b0, dstat + b0, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, cs);
+            if (e == cudaSuccess && iters_out)
+                e = cudaMemcpyAsync(iters_out + 2 * b0, dit + 2 * b0, 2 * nb * sizeof(int32_t), cudaMemcpyDeviceToHost, cs);
+            if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpyAsync D2H", e);
+        }
+        e = cudaStreamSynchronize(g_ctx.stream);
+        if (e == cudaSuccess && nchunk > 1) e = cudaStreamSynchronize(g_ctx.stream2);
+        if (e != cudaSuccess) return fail(QR_ECUDA, "cudaStreamSynchronize", e);
+        return QR_OK;
+    }
     // Small batches (latency path): gather the rows into a pinned mirror of the staging buffer so that
     // the whole call is one host->device and one device->host copy.
-    const bool packed = bytes <= (size_t)256 * 1024;
-    if (packed && !g_ctx.pin) {
+    if (!g_ctx.pin) {
         std::lock_guard<std::mutex> lk(g_mu);
         e = cudaMallocHost(&g_ctx.pin, (size_t)256 * 1024);
         if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMallocHost(pinned stage)", e);
@@ -532,8 +617,7 @@ extern "C" int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_o
     auto up = [&](const float* src, size_t cnt) -> float* {
         float* dst = d;
         d += cnt;
-        if (src && packed) memcpy(hp + (dst - reinterpret_cast<float*>(g_ctx.stage)), src, cnt * sizeof(float));
-        else if (src && e == cudaSuccess) e = cudaMemcpyAsync(dst, src, cnt * sizeof(float), cudaMemcpyHostToDevice, st);
+        if (src) memcpy(hp + (dst - reinterpret_cast<float*>(g_ctx.stage)), src, cnt * sizeof(float));
         return src ? dst : nullptr;
     };
     float* dp = up(p, B * 3);
@@ -546,8 +630,7 @@ extern "C" int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_o
     float* dgait = up(gait, B * 4 * h);
     float* dmu = up(mu_i, B);
     float* dfm = up(fmax_i, B);
-    if (packed && e == cudaSuccess)
-        e = cudaMemcpyAsync(g_ctx.stage, g_ctx.pin, n_in * sizeof(float), cudaMemcpyHostToDevice, st);
+    e = cudaMemcpyAsync(g_ctx.stage, g_ctx.pin, n_in * sizeof(float), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpyAsync H2D", e);
     float* dgrf = d; d += B * 12;
     float* du = nullptr;
@@ -557,26 +640,16 @@ extern "C" int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_o
     int rc = qr_gpu_mpc_solve_batch(P, opt, batch, dp, dv, dq, dw, dr, drpy, dtraj, dgait, dmu, dfm, dgrf, du,
                                     dstat, dit, st);
     if (rc) return rc;
-    if (packed) {
-        const size_t off = n_in * sizeof(float), nout = n_out * sizeof(float) + 3 * B * sizeof(int32_t);
-        e = cudaMemcpyAsync(g_ctx.pin + off, g_ctx.stage + off, nout, cudaMemcpyDeviceToHost, st);
-        if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpyAsync D2H", e);
-        e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) return fail(QR_ECUDA, "cudaStreamSynchronize", e);
-        const unsigned char* hb = g_ctx.pin;
-        memcpy(grf_out, hb + ((unsigned char*)dgrf - g_ctx.stage), B * 12 * sizeof(float));
-        if (u_out) memcpy(u_out, hb + ((unsigned char*)du - g_ctx.stage), B * 12 * h * sizeof(float));
-        if (status_out) memcpy(status_out, hb + ((unsigned char*)dstat - g_ctx.stage), B * sizeof(int32_t));
-        if (iters_out) memcpy(iters_out, hb + ((unsigned char*)dit - g_ctx.stage), 2 * B * sizeof(int32_t));
-        return QR_OK;
-    }
-    e = cudaMemcpyAsync(grf_out, dgrf, B * 12 * sizeof(float), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && u_out) e = cudaMemcpyAsync(u_out, du, B * 12 * h * sizeof(float), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && status_out) e = cudaMemcpyAsync(status_out, dstat, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && iters_out) e = cudaMemcpyAsync(iters_out, dit, 2 * B * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    const size_t off = n_in * sizeof(float), nout = n_out * sizeof(float) + 3 * B * sizeof(int32_t);
+    e = cudaMemcpyAsync(g_ctx.pin + off, g_ctx.stage + off, nout, cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpyAsync D2H", e);
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail(QR_ECUDA, "cudaStreamSynchronize", e);
+    const unsigned char* hb = g_ctx.pin;
+    memcpy(grf_out, hb + ((unsigned char*)dgrf - g_ctx.stage), B * 12 * sizeof(float));
+    if (u_out) memcpy(u_out, hb + ((unsigned char*)du - g_ctx.stage), B * 12 * h * sizeof(float));
+    if (status_out) memcpy(status_out, hb + ((unsigned char*)dstat - g_ctx.stage), B * sizeof(int32_t));
+    if (iters_out) memcpy(iters_out, hb + ((unsigned char*)dit - g_ctx.stage), 2 * B * sizeof(int32_t));
     return QR_OK;
 }
 
