@@ -48,7 +48,7 @@ typedef struct {
 
 /* Solver knobs; pass NULL for the defaults written next to each field. */
 typedef struct {
-    int32_t max_as_rounds;    /* 24    cold-start active-set rounds before the interior-point fallback */
+    int32_t max_as_rounds;    /* 32    cold-start active-set rounds before the interior-point fallback */
     int32_t max_ipm_iter;     /* 40    interior-point iteration cap (fallback path)               */
     int32_t max_polish_rounds;/* 12    active-set verification / correction rounds after it       */
     double ipm_tol;           /* 1e-7  fallback: scaled stationarity and complementarity-gap tolerance */

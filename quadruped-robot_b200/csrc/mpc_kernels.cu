@@ -189,7 +189,7 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
 
 qr_qp_options default_options() {
     qr_qp_options o;
-    o.max_as_rounds = 24;
+    o.max_as_rounds = 32;
     o.max_ipm_iter = 40;
     o.max_polish_rounds = 12;
     o.ipm_tol = 1e-7;

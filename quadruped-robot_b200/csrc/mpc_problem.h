@@ -47,7 +47,7 @@ QR_HD size_t qr_mpc_smem_bytes(int nfcap, int horizon, bool hs_in_smem = true, b
                        : ((sizeof(QrCondenseTables) + 15) & ~(size_t)15);   // the tables alone
     bytes += (size_t)(9 + 9 + 6 * 3 + 1) * nfcap * sizeof(double) + 8 * sizeof(double);
     bytes += (size_t)(16 * horizon + 32) * sizeof(float);          // staged traj + gait + state rows
-    bytes += (size_t)(3 * nfcap + (nfcap + 1) + 3 * nfcap + 2 * 4 * horizon + 8) * sizeof(int);
+    bytes += (size_t)(3 * nfcap + (nfcap + 1) + 3 * nfcap + 2 * 4 * horizon + 8 + 24 + nfcap) * sizeof(int);
     bytes += (size_t)((qr_ntri(nfcap) + 1) / 2) * sizeof(int);         // tri (unsigned short, padded to ints)
     return (bytes + 15) & ~(size_t)15;
 }
@@ -94,6 +94,7 @@ QR_DEV void qr_mpc_carve(QrMpcSmem& S, unsigned char* base, int nfcap, int horiz
     W.foff = ip; ip += nfcap + 1;
     W.rfoot = ip; ip += 3 * nfcap;
     S.misc = ip; ip += 8;
+    W.hist = ip; ip += 24 + nfcap;
     W.tri = reinterpret_cast<unsigned short*>(ip);
     ip += (qr_ntri(nfcap) + 1) / 2;
     float* f = reinterpret_cast<float*>(ip);

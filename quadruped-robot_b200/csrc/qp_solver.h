@@ -34,6 +34,10 @@
 #define QR_TRACE_ROUND(round, nred, W) ((void)0)   // scratch analysis hook (host emulation only)
 #endif
 
+#ifndef QR_CYCLE_CHANGES
+#define QR_CYCLE_CHANGES 9
+#endif
+
 struct QrQpWork {
     int nf;             // stance foot-steps
     double mu_;         // 1/mu as the reference rounds it (float32 value)
@@ -54,6 +58,8 @@ struct QrQpWork {
     int* foff;          // [cap+1] first reduced variable of every foot-step
     int* rfoot;         // [3*cap] foot-step of every reduced variable (-1: padding)
     unsigned short* tri;// [ntri(cap)] lower-triangular index decode table, (I << 8) | J
+    int* hist;          // [24 + cap] or null: cycle detection -- hashes of the last 16 guesses, two hash accumulators,
+                        // [18] trigger flag, [24 + f] how often foot-step f has changed its guess
     // fallback-only vectors (global scratch)
     double *x, *dxa, *rd, *yv;          // [3*cap]
     double *s, *lam, *dsa, *dla, *rc, *dl;  // [5*cap]
@@ -381,6 +387,16 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
                 if (W.s[5 * f + c] < opt.act_kappa * W.lam[5 * f + c]) a |= (1 << c);
         W.act[f] = a;
     }
+    // Cycle detection.  The block updates are a primal-dual active-set iteration and can enter a cycle (period 2-8 in
+    // practice, 0.5 % of the Lite3 trot instances).  Every round's new guess is hashed; when a hash of the last 16
+    // rounds comes back the iteration continues in RESTRICTED mode: per round only one foot-step -- the one with the
+    // most negative multiplier -- may drop rows and only one -- the one with the most violated row -- may add rows.
+    // That ends the cycles seen so far within 4-8 more rounds instead of running into the interior-point fallback.
+    // Quasi-cycles (a few foot-steps rotate through the same guesses while others wobble, so that no hash repeats)
+    // are caught by counting how often each foot-step has changed its guess: in converging instances -- including the
+    // long "waves" of 15-20 rounds -- a foot-step changes at most 8 times.
+    int restricted = 0;
+    if (W.hist) { QR_FOR(i, 24 + nf) W.hist[i] = 0; }
     QR_SYNC();
     *ok = 0;
     int round = 0;
@@ -495,9 +511,12 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
             const double* r = W.q + 3 * f;
             const int act = W.act[f];
             int nact = act;
+            double score = 0.0;   // most negative multiplier of a foot-step that wants to drop rows
+            double ascore = 0.0;  // most negative value of a violated row of a foot-step that wants to add rows
             if (W.vert[f]) {
                 // apex: the gradient must lie in the cone spanned by the four face normals
                 if (r[2] < (fabs(r[0]) + fabs(r[1])) * im - opt.mult_tol) {
+                    score = r[2] - (fabs(r[0]) + fabs(r[1])) * im;
                     const double l0 = r[0] > 0.0 ? r[0] * im : 0.0, l1 = r[0] < 0.0 ? -r[0] * im : 0.0;
                     const double l2 = r[1] > 0.0 ? r[1] * im : 0.0, l3 = r[1] < 0.0 ? -r[1] * im : 0.0;
                     nact = (l0 > 0.0 ? 1 : 0) | (l1 > 0.0 ? 2 : 0) | (l2 > 0.0 ? 4 : 0) | (l3 > 0.0 ? 8 : 0);
@@ -518,7 +537,7 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
                 qr_foot_constraints(mu_, W.ubz[f], W.xn + 3 * f, c);
                 int viol = 0;
                 for (int k = 0; k < 5; ++k)
-                    if (!((act >> k) & 1) && c[k] < -opt.feas_tol) viol |= (1 << k);
+                    if (!((act >> k) & 1) && c[k] < -opt.feas_tol) { viol |= (1 << k); ascore = qr_min(ascore, c[k]); }
                 if (viol) {
                     nact = act | viol;
                 } else if (act) {
@@ -531,15 +550,53 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
                     if ((act & 3) && lx < worst) { worst = lx; drop = act & 3; }
                     if ((act & 12) && ly < worst) { worst = ly; drop = act & 12; }
                     if ((act & 16) && lc < worst) { worst = lc; drop = 16; }
-                    if (drop) nact = act & ~drop;
+                    if (drop) { nact = act & ~drop; score = worst; }
                 }
             }
             W.act[f] = nact;
             changed |= (nact != act);
+            if (W.hist) {
+                if (restricted) {
+                    W.flag[f] = act;                                   // (flag, wv, dx are dead until the next round)
+                    const int grows = (nact | act) == nact;
+                    W.wv[f] = (nact != act && !grows) ? score : 1.0;   // a drop has a negative score,
+                    W.dx[f] = (nact != act && grows) ? ascore : 1.0;   // and so has an addition
+                } else {
+                    unsigned hsh = ((unsigned)f * 37u + (unsigned)nact + 1u) * 2654435761u;
+                    hsh ^= hsh >> 15;
+                    QR_ATOMIC_ADD(&W.hist[16 + (round & 1)], (int)(hsh * 2246822519u));
+                    if (nact != act && ++W.hist[24 + f] >= QR_CYCLE_CHANGES) W.hist[18] = 1;
+                }
+            }
         }
         const int any_changed = QR_ANY(changed);
         QR_PROF(7);
         if (!any_changed) { *ok = 1; ++round; break; }
+        if (W.hist) {
+            if (restricted) {
+                QR_FOR(f, nf) {
+                    const double* sv = W.wv[f] < 0.0 ? W.wv : W.dx;
+                    const double sc = sv[f];
+                    if (sc < 0.0) {
+                        int keep = 1;
+                        for (int gidx = 0; gidx < nf; ++gidx) {
+                            const double o = sv[gidx];
+                            if (o < sc || (o == sc && gidx < f)) keep = 0;
+                        }
+                        if (!keep) W.act[f] = W.flag[f];
+                    }
+                }
+                QR_SYNC();
+            } else {
+                const int cur = W.hist[16 + (round & 1)];
+                int hit = 0;
+                for (int j = 0; j < 16; ++j) hit |= (j != (round & 15)) & (W.hist[j] == cur) & (j < round || round >= 16);
+                QR_THREADS(t) {
+                    if (t == 0) { W.hist[round & 15] = cur; W.hist[16 + ((round + 1) & 1)] = 0; }
+                }
+                restricted = hit | W.hist[18];
+            }
+        }
     }
     return round;
 }

@@ -39,6 +39,7 @@ __device__ __forceinline__ int qr_team_any(int v) {
     return __syncthreads_or(v);
 }
 #define QR_ANY(v) qr_team_any<NT>(v)
+#define QR_ATOMIC_ADD(ptr, v) atomicAdd((ptr), (v))
 // float32 arithmetic that must not be contracted into FMAs (bit-exact condensing)
 #define QR_FMUL(a, b) __fmul_rn((a), (b))
 #define QR_FADD(a, b) __fadd_rn((a), (b))
@@ -52,6 +53,7 @@ __device__ __forceinline__ int qr_team_any(int v) {
 #define QR_THREADS(t) for (int t = 0; t < NT; ++t)
 #define QR_SYNC() ((void)0)
 #define QR_ANY(v) (v)
+#define QR_ATOMIC_ADD(ptr, v) (*(ptr) += (v))
 #define QR_FMUL(a, b) ((a) * (b))
 #define QR_FADD(a, b) ((a) + (b))
 #define QR_FSUB(a, b) ((a) - (b))

@@ -118,6 +118,7 @@ QR_DEV void qr_wbc_carve(QrWbcWork& W, unsigned char* base) {
     Q.act = ip; ip += 4; Q.flag = ip; ip += 4; Q.vert = ip; ip += 4;
     Q.foff = ip; ip += 5; Q.rfoot = ip; ip += 12;
     Q.tri = reinterpret_cast<unsigned short*>(ip);
+    Q.hist = nullptr;   // at most four contact blocks: no cycle detection
 }
 
 // ---- small team-parallel dense kernels (row-major, contiguous).  Every helper ends with a barrier. ----

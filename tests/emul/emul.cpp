@@ -15,7 +15,7 @@
 
 static qr_qp_options emul_default_options() {
     qr_qp_options o;
-    o.max_as_rounds = 24; o.max_ipm_iter = 40; o.max_polish_rounds = 12; o.ipm_tol = 1e-7; o.act_kappa = 1e3;
+    o.max_as_rounds = 32; o.max_ipm_iter = 40; o.max_polish_rounds = 12; o.ipm_tol = 1e-7; o.act_kappa = 1e3;
     o.feas_tol = 1e-9; o.mult_tol = 1e-11;
     return o;
 }
