@@ -37,6 +37,9 @@
 #ifndef QR_CYCLE_CHANGES
 #define QR_CYCLE_CHANGES 9
 #endif
+#ifndef QR_CYCLE_CHANGES_DIV
+#define QR_CYCLE_CHANGES_DIV 4
+#endif
 
 struct QrQpWork {
     int nf;             // stance foot-steps
@@ -396,6 +399,7 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
     // are caught by counting how often each foot-step has changed its guess: in converging instances -- including the
     // long "waves" of 15-20 rounds -- a foot-step changes at most 8 times.
     int restricted = 0;
+    const int kchg = QR_CYCLE_CHANGES + (nf > 24 ? (nf - 24) / QR_CYCLE_CHANGES_DIV : 0);   // longer horizons: longer waves
     if (W.hist) { QR_FOR(i, 24 + nf) W.hist[i] = 0; }
     QR_SYNC();
     *ok = 0;
@@ -565,7 +569,7 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
                     unsigned hsh = ((unsigned)f * 37u + (unsigned)nact + 1u) * 2654435761u;
                     hsh ^= hsh >> 15;
                     QR_ATOMIC_ADD(&W.hist[16 + (round & 1)], (int)(hsh * 2246822519u));
-                    if (nact != act && ++W.hist[24 + f] >= QR_CYCLE_CHANGES) W.hist[18] = 1;
+                    if (nact != act && ++W.hist[24 + f] >= kchg) W.hist[18] = 1;
                 }
             }
         }
