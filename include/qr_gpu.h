@@ -46,11 +46,15 @@ typedef struct {
     float alpha;      /* 4e-6 */
 } qr_mpc_params;
 
+#define QR_QP_NO_PREDICTION 1
+
 /* Solver knobs; pass NULL for the defaults written next to each field. */
 typedef struct {
     int32_t max_as_rounds;    /* 32    cold-start active-set rounds before the interior-point fallback */
     int32_t max_ipm_iter;     /* 40    interior-point iteration cap (fallback path)               */
     int32_t max_polish_rounds;/* 12    active-set verification / correction rounds after it       */
+    int32_t flags;            /* 0     QR_QP_NO_PREDICTION: skip the coarse active-set prediction (diagnostics / tests);
+                                       occupies what used to be alignment padding: the layout is unchanged */
     double ipm_tol;           /* 1e-7  fallback: scaled stationarity and complementarity-gap tolerance */
     double act_kappa;         /* 1e3   constraint i is guessed active when s_i < kappa*lambda_i   */
     double feas_tol;          /* 1e-9  admissible constraint violation after the polish [N]      */

@@ -25,12 +25,15 @@ class MpcParams(C.Structure):
 class QpOptions(C.Structure):
     """qr_qp_options (include/qr_gpu.h)."""
     _fields_ = [("max_as_rounds", C.c_int32), ("max_ipm_iter", C.c_int32), ("max_polish_rounds", C.c_int32),
-                ("_pad", C.c_int32), ("ipm_tol", C.c_double),
+                ("flags", C.c_int32), ("ipm_tol", C.c_double),
                 ("act_kappa", C.c_double), ("feas_tol", C.c_double), ("mult_tol", C.c_double)]
 
 
+QP_NO_PREDICTION = 1
+
+
 def default_options() -> QpOptions:
-    return QpOptions(24, 40, 12, 0, 1e-7, 1e3, 1e-9, 1e-11)
+    return QpOptions(32, 40, 12, 0, 1e-7, 1e3, 1e-9, 1e-11)
 
 
 EXPORTS = ["qr_gpu_init", "qr_gpu_shutdown", "qr_gpu_last_error", "qr_gpu_mpc_occupancy",

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(qr_fused_nt(CAP), qr_fused_min_ctas(CAP)) qr_m
     qr_mpc_carve(S, smem, CAP, A.P.horizon, A.scratch + (size_t)blockIdx.x * qr_fallback_doubles(CAP),
                  HSG ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(CAP) : nullptr,
                  KG ? A.k_global + (size_t)blockIdx.x * 9 * qr_ntri(CAP) : nullptr);
+    S.Hc = A.hc_global ? A.hc_global + (size_t)blockIdx.x * 9 * qr_ntri(CAP) : nullptr;
     qr_mpc_init_tables<NT>(S, CAP);
     // A.next == null (small batches): one launch, instances strided over the grid, no work lists.
     const int total = A.count ? *A.count : A.batch;
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(QR_LAT_NT, 1) qr_mpc_fused_latency_kernel(cons
     qr_mpc_carve(S, smem, A.nfcap, A.P.horizon, A.scratch + (size_t)blockIdx.x * qr_fallback_doubles(A.nfcap),
                  A.hs_global ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr,
                  A.k_global ? A.k_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr);
+    S.Hc = A.hc_global ? A.hc_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr;
     qr_mpc_init_tables<NT>(S, A.nfcap);
     for (int prob = blockIdx.x; prob < A.batch; prob += gridDim.x) qr_mpc_solve_problem<NT>(A, prob, S);
 }
@@ -149,6 +151,7 @@ __global__ void __launch_bounds__(QR_NT) qr_qp_solve_kernel(const QrMpcArgs A) {
     qr_mpc_carve(S, smem, A.nfcap, A.P.horizon, A.scratch + (size_t)blockIdx.x * qr_fallback_doubles(A.nfcap),
                  A.hs_global ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr,
                  A.k_global ? A.k_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr);
+    S.Hc = A.hc_global ? A.hc_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr;
     qr_mpc_init_tables<NT>(S, A.nfcap);
     for (int prob = blockIdx.x; prob < A.batch; prob += gridDim.x)
         qr_qp_solve_problem<NT>(A, prob, S);
@@ -191,7 +194,7 @@ qr_qp_options default_options() {
     qr_qp_options o;
     o.max_as_rounds = 32;
     o.max_ipm_iter = 40;
-    o.max_polish_rounds = 12;
+    o.max_polish_rounds = 12; o.flags = 0;
     o.ipm_tol = 1e-7;
     o.act_kappa = 1e3;
     o.feas_tol = 1e-9;
@@ -209,8 +212,9 @@ struct Plan {
     int grid = 0, occ = 0;
     size_t smem = 0;
     bool hsg = false, kg = false;
-    size_t scratch_doubles(int nfcap) const {   // per launch: [grid][fallback] [grid][Hs] [grid][K]
+    size_t scratch_doubles(int nfcap) const {   // per launch: [grid][fallback] [grid][Hc] [grid][Hs] [grid][K]
         size_t d = (size_t)grid * qr_fallback_doubles(nfcap);
+        d += (size_t)grid * 9 * qr_ntri(nfcap);   // coarse Hessian of the active-set prediction
         if (hsg) d += (size_t)grid * 9 * qr_ntri(nfcap);
         if (kg) d += (size_t)grid * 9 * qr_ntri(nfcap);
         return d;
@@ -277,6 +281,8 @@ void bind_scratch(QrMpcArgs& A, const Plan& pl, int nfcap, int lane = 0) {
     double* s = g_ctx.scratch_[lane];
     A.scratch = s;
     s += (size_t)pl.grid * qr_fallback_doubles(nfcap);
+    A.hc_global = s;
+    s += (size_t)pl.grid * 9 * qr_ntri(nfcap);
     A.hs_global = nullptr;
     A.k_global = nullptr;
     if (pl.hsg) { A.hs_global = s; s += (size_t)pl.grid * 9 * qr_ntri(nfcap); }

@@ -20,6 +20,7 @@ struct QrMpcArgs {
     double* scratch;         // [teams][qr_fallback_doubles(nfcap)] vectors of the interior-point fallback
     double* hs_global;       // [teams][9*ntri(nfcap)] Hessian blocks when they are kept out of shared memory, else null
     double* k_global;        // [teams][9*ntri(nfcap)] matrix under factorisation when it does not fit in shared memory, else null
+    double* hc_global;       // [teams][9*ntri(nfcap)] Hessian of the coarse (move-blocked) problem that predicts the active set, or null
     // work list of this launch (size class): problems list[0 .. *count), handed out through *next.
     // list == null: problems 0 .. batch-1.
     const int* list;
@@ -35,6 +36,9 @@ struct QrMpcArgs {
 
 QR_HD int qr_ntri(int nf) { return (nf * (nf + 1)) / 2; }
 QR_HD size_t qr_fallback_doubles(int nfcap) { return (size_t)46 * nfcap + 8; }
+// The coarse problem pairs consecutive foot-steps of a leg; it is only used when that removes at least a quarter
+// of the foot-steps.
+QR_HD int qr_coarse_cap(int nfcap) { return (3 * nfcap + 3) / 4; }
 QR_HD size_t qr_kbytes(int nfcap) {
     size_t kb = (size_t)9 * qr_ntri(nfcap) * sizeof(double);
     return kb > sizeof(QrCondenseTables) ? kb : ((sizeof(QrCondenseTables) + 15) & ~(size_t)15);
@@ -46,8 +50,9 @@ QR_HD size_t qr_mpc_smem_bytes(int nfcap, int horizon, bool hs_in_smem = true, b
     bytes += k_in_smem ? qr_kbytes(nfcap)                          // K (aliased by the condense tables)
                        : ((sizeof(QrCondenseTables) + 15) & ~(size_t)15);   // the tables alone
     bytes += (size_t)(9 + 9 + 6 * 3 + 1) * nfcap * sizeof(double) + 8 * sizeof(double);
+    bytes += (size_t)(3 + 1) * qr_coarse_cap(nfcap) * sizeof(double);   // coarse problem: g, ub
     bytes += (size_t)(16 * horizon + 32) * sizeof(float);          // staged traj + gait + state rows
-    bytes += (size_t)(3 * nfcap + (nfcap + 1) + 3 * nfcap + 2 * 4 * horizon + 8 + 24 + nfcap) * sizeof(int);
+    bytes += (size_t)(3 * nfcap + (nfcap + 1) + 3 * nfcap + 2 * 4 * horizon + 8 + 24 + nfcap + 3 * nfcap) * sizeof(int);   // .. + grp, gmem
     bytes += (size_t)((qr_ntri(nfcap) + 1) / 2) * sizeof(int);         // tri (unsigned short, padded to ints)
     return (bytes + 15) & ~(size_t)15;
 }
@@ -62,6 +67,12 @@ struct QrMpcSmem {
     int* slot;     // [4h] inverse map (or -1)
     int* misc;     // [8]
     double* scal;  // [8] scalars broadcast through shared memory (scal[0] = mu_)
+    // coarse (move-blocked) problem used to predict the active set: see qr_mpc_predict_active_set
+    double* Hc;    // [9*ntri(coarse cap)] global (L2-resident) or null: prediction disabled
+    double* gc;    // [3*coarse cap]
+    double* ubc;   // [coarse cap]
+    int* grp;      // [nfcap] coarse foot-step of every stance foot-step
+    int* gmem;     // [2*nfcap] members of every coarse foot-step (second = -1 for a single)
 };
 
 QR_DEV void qr_mpc_carve(QrMpcSmem& S, unsigned char* base, int nfcap, int horizon, double* fallback,
@@ -84,6 +95,9 @@ QR_DEV void qr_mpc_carve(QrMpcSmem& S, unsigned char* base, int nfcap, int horiz
     W.ps = d; d += n; W.g = d; d += n; W.xn = d; d += n; W.q = d; d += n; W.wv = d; d += n;
     W.dx = d; d += n;
     W.ubz = d; d += nfcap;
+    S.gc = d; d += 3 * qr_coarse_cap(nfcap);
+    S.ubc = d; d += qr_coarse_cap(nfcap);
+    S.Hc = nullptr;
     S.scal = d; d += 8;
     // fixed-size integer tables first, the horizon-dependent rows last: with a compile-time capacity every
     // pointer of the solver is then a constant offset from the shared-memory base
@@ -95,6 +109,8 @@ QR_DEV void qr_mpc_carve(QrMpcSmem& S, unsigned char* base, int nfcap, int horiz
     W.rfoot = ip; ip += 3 * nfcap;
     S.misc = ip; ip += 8;
     W.hist = ip; ip += 24 + nfcap;
+    S.grp = ip; ip += nfcap;
+    S.gmem = ip; ip += 2 * nfcap;
     W.tri = reinterpret_cast<unsigned short*>(ip);
     ip += (qr_ntri(nfcap) + 1) / 2;
     float* f = reinterpret_cast<float*>(ip);
@@ -199,6 +215,78 @@ QR_DEV void qr_mpc_condense_to_work(const QrMpcArgs& A, QrMpcSmem& S) {
     QR_SYNC();
 }
 
+
+// Active-set prediction on a coarse problem.
+//
+// The block active-set iteration spends two thirds of its factorisation work in the first three rounds (72, 61, 52
+// free variables for the A1 trot at h = 10) while the set of active rows spreads along the horizon like a wave, one
+// or two time steps per round.  Here the wave is run on a QUARTER of the work first: consecutive foot-steps of the
+// same leg (same stance phase) are tied pairwise to one force ("move blocking": x = T z, H_c = T'HT, g_c = T'g, same
+// pyramid and cap per pair), that half-size QP is solved by the same iteration, and every foot-step starts the
+// full-size iteration from its pair's active rows (qr_qp_solve, stage 0).  The full-size iteration then needs 4-5
+// rounds instead of 7-8, all of them on the small final systems, and still ends only on verified KKT conditions --
+// the prediction changes the starting guess, never the result.  This routine builds the coarse problem.
+template <int NT>
+QR_DEV QrCoarse qr_mpc_build_coarse(QrMpcSmem& S, const qr_qp_options& opt) {
+    QrQpWork& W = S.W;
+    const int nf = W.nf;
+    QrCoarse C;
+    C.ng = 0; C.Hs = S.Hc; C.g = S.gc; C.ubz = S.ubc; C.grp = S.grp;
+    if (!S.Hc || nf < 8 || (opt.flags & QR_QP_NO_PREDICTION)) return C;
+    QR_THREADS(t) {
+        if (t == 0) {
+            int open[4] = {-1, -1, -1, -1}, last[4] = {-9, -9, -9, -9};
+            int ng = 0;
+            for (int s = 0; s < nf; ++s) {
+                const int k = S.fs[s], step = k >> 2, leg = k & 3;
+                if (open[leg] >= 0 && last[leg] == step - 1 && W.ubz[S.gmem[2 * open[leg]]] == W.ubz[s]) {
+                    S.grp[s] = open[leg];
+                    S.gmem[2 * open[leg] + 1] = s;
+                    open[leg] = -1;
+                } else {
+                    S.grp[s] = ng;
+                    S.gmem[2 * ng] = s;
+                    S.gmem[2 * ng + 1] = -1;
+                    open[leg] = ng;
+                    ++ng;
+                }
+                last[leg] = step;
+            }
+            S.misc[2] = ng;
+        }
+    }
+    QR_SYNC();
+    const int ng = S.misc[2];
+    if (4 * ng > 3 * nf) return C;   // hardly anything to pair
+    // H_c = T'HT by 3x3 blocks (block-packed like W.Hs, diagonal blocks in full), g_c = T'g
+    QR_FOR(idx, 9 * qr_ntri(ng)) {
+        const int b = idx / 9, e = idx - 9 * b;
+        const int code = W.tri[b];
+        const int Ac = code >> 8, Bc = code & 255;
+        const int r = e / 3, c = e - 3 * r;
+        double acc = 0.0;
+        for (int i = 0; i < 2; ++i) {
+            const int f = S.gmem[2 * Ac + i];
+            if (f < 0) continue;
+            for (int j = 0; j < 2; ++j) {
+                const int f2 = S.gmem[2 * Bc + j];
+                if (f2 < 0) continue;
+                acc += f >= f2 ? W.Hs[qr_blk(f, f2) + 3 * r + c] : W.Hs[qr_blk(f2, f) + 3 * c + r];
+            }
+        }
+        S.Hc[idx] = acc;
+    }
+    QR_FOR(i, 3 * ng) {
+        const int gidx = i / 3, a = i - 3 * gidx;
+        const int f = S.gmem[2 * gidx], f2 = S.gmem[2 * gidx + 1];
+        S.gc[i] = W.g[3 * f + a] + (f2 >= 0 ? W.g[3 * f2 + a] : 0.0);
+        if (a == 0) S.ubc[gidx] = W.ubz[f];
+    }
+    QR_SYNC();
+    C.ng = ng;
+    return C;
+}
+
 // Scatter the stance solution into the 12h force vector (swing foot-steps are exactly zero).
 template <int NT>
 QR_DEV void qr_mpc_scatter(const QrMpcArgs& A, int prob, QrMpcSmem& S, const double* x, int status,
@@ -242,7 +330,9 @@ QR_DEV void qr_mpc_solve_problem(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
     if (status == 0) {
         qr_mpc_condense_to_work<NT>(A, S);
         QR_PROF(21);
-        status = qr_qp_solve<NT>(S.W, A.opt, &it, &rounds, &x QR_PROF_PASS);
+        const QrCoarse C = qr_mpc_build_coarse<NT>(S, A.opt);
+        QR_PROF(23);
+        status = qr_qp_solve<NT>(S.W, A.opt, &it, &rounds, &x, &C QR_PROF_PASS);
         status = qr_result_status<NT>(S, x, status);
     }
     qr_mpc_scatter<NT>(A, prob, S, x, status, it, rounds);
@@ -314,7 +404,8 @@ QR_DEV void qr_qp_solve_problem(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
         QR_FOR(i, 3 * nf) S.W.g[i] = (double)g[3 * S.fs[i / 3] + i % 3];
         QR_SYNC();
         QR_PROF_DECL;
-        status = qr_qp_solve<NT>(S.W, A.opt, &it, &rounds, &x QR_PROF_PASS);
+        const QrCoarse C = qr_mpc_build_coarse<NT>(S, A.opt);
+        status = qr_qp_solve<NT>(S.W, A.opt, &it, &rounds, &x, &C QR_PROF_PASS);
         status = qr_result_status<NT>(S, x, status);
     }
     qr_mpc_scatter<NT>(A, prob, S, x, status, it, rounds);

@@ -376,19 +376,22 @@ QR_DEV int qr_foot_basis(int act, double mu_, double ub, double* Z, double* p) {
 }
 
 // Block active-set iteration (see the header comment).  cold = 1: start with no row active;
-// cold = 0: start from the active set the interior-point iterate (W.s, W.lam) suggests.
+// cold = 0: start from the active set the interior-point iterate (W.s, W.lam) suggests;
+// cold = 2: start from the guess the caller left in W.act (the coarse prediction of mpc_problem.h).
 // Result in W.xn.  Returns rounds used; *ok = 1 when the KKT conditions were verified.
 template <int NT>
 QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int cold, int max_rounds QR_PROF_ARG) {
     const int nf = W.nf, n = 3 * nf;
     const double mu_ = W.mu_;
     const double im = 1.0 / mu_;
-    QR_FOR(f, nf) {
-        int a = 0;
-        if (!cold)
-            for (int c = 0; c < 5; ++c)
-                if (W.s[5 * f + c] < opt.act_kappa * W.lam[5 * f + c]) a |= (1 << c);
-        W.act[f] = a;
+    if (cold != 2) {
+        QR_FOR(f, nf) {
+            int a = 0;
+            if (!cold)
+                for (int c = 0; c < 5; ++c)
+                    if (W.s[5 * f + c] < opt.act_kappa * W.lam[5 * f + c]) a |= (1 << c);
+            W.act[f] = a;
+        }
     }
     // Cycle detection.  The block updates are a primal-dual active-set iteration and can enter a cycle (period 2-8 in
     // practice, 0.5 % of the Lite3 trot instances).  Every round's new guess is hashed; when a hash of the last 16
@@ -914,25 +917,58 @@ QR_DEV int qr_ipm(QrQpWork& W, const qr_qp_options& opt, double tol, int* conver
     return it;
 }
 
+// Optional coarse problem whose solution predicts the active set of the full-size one (built by the caller, see
+// qr_mpc_build_coarse in mpc_problem.h): ng tied foot-steps, grp[f] = tied foot-step of foot-step f.
+struct QrCoarse {
+    int ng;
+    double *Hs, *g, *ubz;
+    const int* grp;
+};
+
 // Full solve on a prepared workspace (Hs, g, ubz, mu_ set).  Result in W.xn (verified) or W.x.
 // Returns the per-instance status code of qr_gpu.h.
+//
+// Stages: [0: the iteration on the coarse problem, whose active rows every foot-step inherits] -> 1: the iteration on
+// the full-size problem (cold, or from the inherited guess) -> on failure 2: interior point to identify the active
+// set (tightening the tolerance once if the verification still does not settle) and 3: the same verification from
+// its guess.  Written as one loop around a single qr_active_set call site so that the (force-inlined) iteration is
+// instantiated once.
 template <int NT>
 QR_DEV int qr_qp_solve(QrQpWork& W, const qr_qp_options& opt, int* ipm_iters, int* as_rounds,
-                       const double** result QR_PROF_ARG) {
+                       const double** result, const QrCoarse* C QR_PROF_ARG) {
     int conv = 0, ok = 0;
     *ipm_iters = 0; *as_rounds = 0;
     *result = W.xn;
     if (W.nf == 0) return 0;
-    // 1. block active-set iteration from a cold start
-    *as_rounds = qr_active_set<NT>(W, opt, &ok, 1, opt.max_as_rounds QR_PROF_PASS);
-    if (ok) return 0;
-    // 2. fallback: interior point to identify the active set (tightening the tolerance once if the
-    //    verification still does not settle), then the same verification
+    const int nf_full = W.nf;
+    double* const hs_full = W.Hs;
+    double* const g_full = W.g;
+    double* const ubz_full = W.ubz;
+    int stage = (C && C->ng > 0) ? 0 : 1;
+    int mode = 1, attempt = 0;
     double tol = opt.ipm_tol;
-    for (int attempt = 0; attempt < 2; ++attempt, tol *= 1e-2) {
-        *ipm_iters += qr_ipm<NT>(W, opt, tol, &conv QR_PROF_PASS);
-        *as_rounds += qr_active_set<NT>(W, opt, &ok, 0, opt.max_polish_rounds QR_PROF_PASS);
+    for (;;) {
+        int maxr = opt.max_as_rounds;
+        if (stage == 0) { W.nf = C->ng; W.Hs = C->Hs; W.g = C->g; W.ubz = C->ubz; maxr = 16; }
+        else if (stage == 3) { mode = 0; maxr = opt.max_polish_rounds; }
+        const int rounds = qr_active_set<NT>(W, opt, &ok, mode, maxr QR_PROF_PASS);
+        if (stage == 0) {
+            // every foot-step inherits its tied foot-step's active rows (through W.flag: rewritten in place)
+            W.nf = nf_full; W.Hs = hs_full; W.g = g_full; W.ubz = ubz_full;
+            QR_FOR(f, nf_full) W.flag[f] = W.act[C->grp[f]];
+            QR_SYNC();
+            QR_FOR(f, nf_full) W.act[f] = W.flag[f];
+            QR_SYNC();
+            stage = 1; mode = 2;
+            continue;
+        }
+        *as_rounds += rounds;
         if (ok) return 0;
+        if (attempt == 2) break;
+        *ipm_iters += qr_ipm<NT>(W, opt, tol, &conv QR_PROF_PASS);
+        tol *= 1e-2;
+        ++attempt;
+        stage = 3;
     }
     *result = W.x;
     return 1;

@@ -15,7 +15,7 @@
 
 static qr_qp_options emul_default_options() {
     qr_qp_options o;
-    o.max_as_rounds = 32; o.max_ipm_iter = 40; o.max_polish_rounds = 12; o.ipm_tol = 1e-7; o.act_kappa = 1e3;
+    o.max_as_rounds = 32; o.max_ipm_iter = 40; o.max_polish_rounds = 12; o.flags = 0; o.ipm_tol = 1e-7; o.act_kappa = 1e3;
     o.feas_tol = 1e-9; o.mult_tol = 1e-11;
     return o;
 }
@@ -23,10 +23,12 @@ static qr_qp_options emul_default_options() {
 // Workspace of one emulated team, sized like the CUDA launch of the same size class would be.
 struct EmulTeam {
     std::vector<unsigned char> smem;
-    std::vector<double> fallback;
+    std::vector<double> fallback, coarse;
     QrMpcSmem S;
-    EmulTeam(int nfcap, int horizon) : smem(qr_mpc_smem_bytes(nfcap, horizon) + 64), fallback(qr_fallback_doubles(nfcap)) {
+    EmulTeam(int nfcap, int horizon) : smem(qr_mpc_smem_bytes(nfcap, horizon) + 64), fallback(qr_fallback_doubles(nfcap)),
+                                       coarse(9 * qr_ntri(nfcap)) {
         qr_mpc_carve(S, smem.data(), nfcap, horizon, fallback.data());
+        S.Hc = coarse.data();
         qr_mpc_init_tables<128>(S, nfcap);
     }
 };

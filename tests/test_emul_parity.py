@@ -130,3 +130,27 @@ def test_permutation_and_determinism(emul, oracle, pkg):
     b2 = {k: (np.ascontiguousarray(v[perm]) if isinstance(v, np.ndarray) else v) for k, v in b.items()}
     r2 = emul.solve(P, b2)
     assert np.array_equal(r1["u64"][perm], r2["u64"])
+
+
+def test_cycling_instances_converge_without_fallback(emul, oracle, pkg):
+    """Lite3 trot instances on which the plain block active-set updates cycle (period 4, found by tracing):
+    the cycle detection switches to the restricted one-add / one-drop mode, which ends at the verified optimum
+    without the interior-point fallback; the result is the exact optimum of the oracle-built QP."""
+    h, dt, B = 10, 0.03, 1500
+    b = pkg.synth.make_mpc_batch("lite3", h, dt, B, seed=3, gait="trot")
+    idx = np.array([29, 338, 366, 520, 720, 802, 927])
+    sub = {k: (np.ascontiguousarray(v[idx]) if isinstance(v, np.ndarray) and v.shape[:1] == (B,) else v) for k, v in b.items()}
+    P = oracle.params_of(sub["robot"], h, dt)
+    from quadruped_robot_b200 import capi
+    opt = capi.default_options()
+    opt.flags = capi.QP_NO_PREDICTION   # from a cold start (with the coarse prediction they no longer cycle)
+    e = emul.solve(P, sub, opt=opt)
+    assert (e["status"] == 0).all()
+    assert (e["iters"][:, 0] == 0).all(), e["iters"]
+    assert e["iters"][:, 1].max() <= 32 and e["iters"][:, 1].min() >= 12   # these really are the hard ones
+    Po = P
+    A = oracle.constraint_rows(h, Po.mu)
+    for i in range(len(idx)):
+        H, g, ub = oracle.mpc_build(Po, sub, i)
+        stat, feas = oracle.kkt_certificate(H, g, A, np.zeros(20 * h), ub.astype(float), e["u64"][i])
+        assert stat < 1e-7 and feas < 1e-7, (i, stat, feas)
