@@ -258,23 +258,27 @@ QR_DEV QrCoarse qr_mpc_build_coarse(QrMpcSmem& S, const qr_qp_options& opt) {
     QR_SYNC();
     const int ng = S.misc[2];
     if (4 * ng > 3 * nf) return C;   // hardly anything to pair
-    // H_c = T'HT by 3x3 blocks (block-packed like W.Hs, diagonal blocks in full), g_c = T'g
-    QR_FOR(idx, 9 * qr_ntri(ng)) {
-        const int b = idx / 9, e = idx - 9 * b;
-        const int code = W.tri[b];
-        const int Ac = code >> 8, Bc = code & 255;
-        const int r = e / 3, c = e - 3 * r;
-        double acc = 0.0;
-        for (int i = 0; i < 2; ++i) {
-            const int f = S.gmem[2 * Ac + i];
-            if (f < 0) continue;
-            for (int j = 0; j < 2; ++j) {
-                const int f2 = S.gmem[2 * Bc + j];
-                if (f2 < 0) continue;
-                acc += f >= f2 ? W.Hs[qr_blk(f, f2) + 3 * r + c] : W.Hs[qr_blk(f2, f) + 3 * c + r];
-            }
+    // H_c = T'HT by 3x3 blocks (block-packed like W.Hs, diagonal blocks in full), g_c = T'g.  The four loads of an
+    // entry are issued together (a missing second member reads the first one's entry with weight 0): W.Hs lives in
+    // L2, so the latency of a dependent or branchy load sequence would dominate this phase.
+    {
+        const double* __restrict__ Hs = W.Hs;
+        double* __restrict__ Hc = S.Hc;
+        QR_FOR(idx, 9 * qr_ntri(ng)) {
+            const int b = idx / 9, e = idx - 9 * b;
+            const int code = W.tri[b];
+            const int Ac = code >> 8, Bc = code & 255;
+            const int r = e / 3, c = e - 3 * r;
+            const int f0 = S.gmem[2 * Ac], f1r = S.gmem[2 * Ac + 1], g0 = S.gmem[2 * Bc], g1r = S.gmem[2 * Bc + 1];
+            const int f1 = f1r < 0 ? f0 : f1r, g1 = g1r < 0 ? g0 : g1r;
+            const double wf = f1r < 0 ? 0.0 : 1.0, wg = g1r < 0 ? 0.0 : 1.0;
+            const int erc = 3 * r + c, ecr = 3 * c + r;
+            const double v00 = f0 >= g0 ? Hs[qr_blk(f0, g0) + erc] : Hs[qr_blk(g0, f0) + ecr];
+            const double v01 = f0 >= g1 ? Hs[qr_blk(f0, g1) + erc] : Hs[qr_blk(g1, f0) + ecr];
+            const double v10 = f1 >= g0 ? Hs[qr_blk(f1, g0) + erc] : Hs[qr_blk(g0, f1) + ecr];
+            const double v11 = f1 >= g1 ? Hs[qr_blk(f1, g1) + erc] : Hs[qr_blk(g1, f1) + ecr];
+            Hc[idx] = (v00 + wg * v01) + wf * (v10 + wg * v11);
         }
-        S.Hc[idx] = acc;
     }
     QR_FOR(i, 3 * ng) {
         const int gidx = i / 3, a = i - 3 * gidx;

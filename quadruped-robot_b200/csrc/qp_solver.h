@@ -37,6 +37,9 @@
 #ifndef QR_CYCLE_CHANGES
 #define QR_CYCLE_CHANGES 9
 #endif
+#ifndef QR_COARSE_MAX_ROUNDS
+#define QR_COARSE_MAX_ROUNDS 4   // rounds spent on the coarse problem (its last guess is used either way); measured on B200, A1 trot 65536: cap 3 / 4 / 5 / 7 / 16 -> 3.89 / 3.84 / 3.78 / 3.69 / 3.56 M QP/s, mixed gaits best at 4-5
+#endif
 #ifndef QR_CYCLE_CHANGES_DIV
 #define QR_CYCLE_CHANGES_DIV 4
 #endif
@@ -509,7 +512,11 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
         }
         QR_SYNC();
         QR_PROF(5);
-        QR_FOR(i, n) W.q[i] = qr_sym_matvec_row(W.Hs, W.xn, nf, i) + W.g[i];
+        // gradient rows of the foot-steps with active rows only: the verification reads nothing else (a free foot-step's
+        // gradient is zero by construction), and with the Hessian in L2 this phase is bound by its L2 -> SM traffic
+        QR_FOR(i, n) {
+            if (W.act[i / 3]) W.q[i] = qr_sym_matvec_row(W.Hs, W.xn, nf, i) + W.g[i];
+        }
         QR_SYNC();
         QR_PROF(6);
         // ---- verify / correct the active sets
@@ -949,7 +956,7 @@ QR_DEV int qr_qp_solve(QrQpWork& W, const qr_qp_options& opt, int* ipm_iters, in
     double tol = opt.ipm_tol;
     for (;;) {
         int maxr = opt.max_as_rounds;
-        if (stage == 0) { W.nf = C->ng; W.Hs = C->Hs; W.g = C->g; W.ubz = C->ubz; maxr = 16; }
+        if (stage == 0) { W.nf = C->ng; W.Hs = C->Hs; W.g = C->g; W.ubz = C->ubz; maxr = QR_COARSE_MAX_ROUNDS; }
         else if (stage == 3) { mode = 0; maxr = opt.max_polish_rounds; }
         const int rounds = qr_active_set<NT>(W, opt, &ok, mode, maxr QR_PROF_PASS);
         if (stage == 0) {
