@@ -454,12 +454,12 @@ def run_gpu(args, rank, local_rank, world):
         "config": {"workload": f"A1 convex MPC h={h} dt={DT_MPC} trot, batch {B} per GPU (BASELINE configs[2] shape)",
                    "global_batch": world * B, "parallelism": f"dp{world} (independent instances, no collective on the solve path)",
                    "l2": f"{N_INPUT_SETS} rotating input sets ({N_INPUT_SETS * h2d / 1e6:.0f} MB) > 126 MB L2",
-                   "arith": "float32 condensing (reference operation order) + float64 interior point / active-set polish",
+                   "arith": "float32 condensing (reference operation order) + float64 block active-set iteration (coarse move-blocked prediction, then full size; ends on verified KKT conditions), interior-point fallback",
                    "launch": occ, "not_converged": n_bad,
                    "ipm_iters_mean": float(iters[:, 0].mean()), "polish_rounds_mean": float(iters[:, 1].mean())},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "QP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "qr_gpu_mpc_solve_batch_host (pinned host buffers, H2D + kernel + D2H + stream sync per step)"},
+                "api": "qr_gpu_mpc_solve_batch_host (pinned host buffers; per step H2D + kernels + D2H + stream sync, the batch cut into two chunks on two streams so that most of the upload runs under the kernels)"},
         "gpu_launches": args.steps * (1 + n_size_classes),   # per step: qr_mpc_classify_kernel + one qr_mpc_fused_kernel per size class
         "roofline": roofline,
         "cpu_baseline": cpu,
