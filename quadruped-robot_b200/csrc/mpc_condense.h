@@ -214,6 +214,46 @@ QR_DEV float qr_condense_h_entry(const QrCondenseTables& T, int h, int i, int la
     return s;
 }
 
+// Entry (12*i + 3*la + aa, 12*j + 3*lb + ab) of qH and its transposed entry in ONE loop: the same two float32
+// summation chains as two calls of qr_condense_h_entry (bit-identical results), interleaved so that the dependent
+// FADD chain of one hides the latency of the other (the symmetrised Hessian needs both, see qr_mpc_condense_to_work).
+QR_DEV void qr_condense_h_pair(const QrCondenseTables& T, int h, int i, int la, int aa, int j, int lb, int ab,
+                               float* hst, float* hts) {
+    const int ca = 3 * la + aa, cb = 3 * lb + ab;
+    const bool same_axis = (aa == ab);
+    const float p6 = QR_FMUL(T.TG68[0][ca], T.G68[0][cb]), q6 = QR_FMUL(T.TG68[0][cb], T.G68[0][ca]);
+    const float p7 = QR_FMUL(T.TG68[1][ca], T.G68[1][cb]), q7 = QR_FMUL(T.TG68[1][cb], T.G68[1][ca]);
+    const float p8 = QR_FMUL(T.TG68[2][ca], T.G68[2][cb]), q8 = QR_FMUL(T.TG68[2][cb], T.G68[2][ca]);
+    const float pv = QR_FMUL(T.tgvel[aa], T.gvel), qv = QR_FMUL(T.tgvel[ab], T.gvel);
+    float s = 0.f, u = 0.f;
+    const int r0 = (i > j ? i : j);
+    const QrF4* tga = &T.TGx[r0 - i][ca];
+    const QrF4* gga = &T.Gx[r0 - i][ca];
+    const QrF4* tgb = &T.TGx[r0 - j][cb];
+    const QrF4* ggb = &T.Gx[r0 - j][cb];
+    for (int r = r0; r < h; ++r, tga += 12, gga += 12, tgb += 12, ggb += 12) {
+        const QrF4 a = *tga, b = *ggb;     // entry (s, t): TGx[r - i][ca] . Gx[r - j][cb]
+        const QrF4 c = *tgb, d = *gga;     // entry (t, s): TGx[r - j][cb] . Gx[r - i][ca]
+        s = QR_FADD(s, QR_FMUL(a.x, b.x));
+        u = QR_FADD(u, QR_FMUL(c.x, d.x));
+        s = QR_FADD(s, QR_FMUL(a.y, b.y));
+        u = QR_FADD(u, QR_FMUL(c.y, d.y));
+        s = QR_FADD(s, QR_FMUL(a.z, b.z));
+        u = QR_FADD(u, QR_FMUL(c.z, d.z));
+        if (same_axis) { s = QR_FADD(s, QR_FMUL(a.w, b.w)); u = QR_FADD(u, QR_FMUL(c.w, d.w)); }
+        s = QR_FADD(s, p6);
+        u = QR_FADD(u, q6);
+        s = QR_FADD(s, p7);
+        u = QR_FADD(u, q7);
+        s = QR_FADD(s, p8);
+        u = QR_FADD(u, q8);
+        if (same_axis) { s = QR_FADD(s, pv); u = QR_FADD(u, qv); }
+    }
+    if (i == j && ca == cb) { s = QR_FADD(s, T.two_alpha); u = QR_FADD(u, T.two_alpha); }
+    *hst = s;
+    *hts = u;
+}
+
 // One float32 entry of qg: row 12*i + 3*la + aa  (:412).
 QR_DEV float qr_condense_g_entry(const QrCondenseTables& T, int h, int i, int la, int aa) {
     const int ca = 3 * la + aa;

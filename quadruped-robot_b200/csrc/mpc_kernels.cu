@@ -106,6 +106,9 @@ __global__ void __launch_bounds__(qr_fused_nt(CAP), qr_fused_min_ctas(CAP)) qr_m
 
 // Latency path (batches that cannot fill the device): one instantiation with the capacity as a runtime value, both
 // matrices in shared memory whenever they fit and no register cap -- per-instance latency matters here, not occupancy.
+#ifndef QR_COARSE_MAX_ROUNDS_LAT
+#define QR_COARSE_MAX_ROUNDS_LAT 4   // coarse-round cap of the latency path
+#endif
 #ifndef QR_LAT_NT
 #define QR_LAT_NT 256   // a wider team shortens the phases with plenty of parallel work (condensing, early LDL' steps)
 #endif
@@ -407,6 +410,7 @@ static int mpc_solve_batch_lane(int lane, const qr_mpc_params* P, const qr_qp_op
         rc = ensure_scratch_doubles(pl.scratch_doubles(cap), lane);
         if (rc) return rc;
         A.nfcap = cap;
+        A.coarse_rounds = QR_COARSE_MAX_ROUNDS_LAT;
         bind_scratch(A, pl, cap, lane);
         qr_mpc_fused_latency_kernel<<<pl.grid, QR_LAT_NT, pl.smem, st>>>(A);
         cudaError_t e1 = cudaGetLastError();

@@ -21,6 +21,7 @@ struct QrMpcArgs {
     double* hs_global;       // [teams][9*ntri(nfcap)] Hessian blocks when they are kept out of shared memory, else null
     double* k_global;        // [teams][9*ntri(nfcap)] matrix under factorisation when it does not fit in shared memory, else null
     double* hc_global;       // [teams][9*ntri(nfcap)] Hessian of the coarse (move-blocked) problem that predicts the active set, or null
+    int coarse_rounds;       // rounds spent on the coarse problem at most (0: the default QR_COARSE_MAX_ROUNDS)
     // work list of this launch (size class): problems list[0 .. *count), handed out through *next.
     // list == null: problems 0 .. batch-1.
     const int* list;
@@ -204,8 +205,8 @@ QR_DEV void qr_mpc_condense_to_work(const QrMpcArgs& A, QrMpcSmem& S) {
         const int code = S.W.tri[b];
         const int ks = S.fs[code >> 8], kt = S.fs[code & 255];
         const int r = e / 3, c = e - 3 * r;
-        const float hst = qr_condense_h_entry(T, h, ks >> 2, ks & 3, r, kt >> 2, kt & 3, c);
-        const float hts = qr_condense_h_entry(T, h, kt >> 2, kt & 3, c, ks >> 2, ks & 3, r);
+        float hst, hts;
+        qr_condense_h_pair(T, h, ks >> 2, ks & 3, r, kt >> 2, kt & 3, c, &hst, &hts);
         S.W.Hs[idx] = 0.5 * ((double)hst + (double)hts);
     }
     QR_FOR(i, 3 * nf) {
@@ -227,11 +228,12 @@ QR_DEV void qr_mpc_condense_to_work(const QrMpcArgs& A, QrMpcSmem& S) {
 // rounds instead of 7-8, all of them on the small final systems, and still ends only on verified KKT conditions --
 // the prediction changes the starting guess, never the result.  This routine builds the coarse problem.
 template <int NT>
-QR_DEV QrCoarse qr_mpc_build_coarse(QrMpcSmem& S, const qr_qp_options& opt) {
+QR_DEV QrCoarse qr_mpc_build_coarse(QrMpcSmem& S, const qr_qp_options& opt, int max_rounds) {
     QrQpWork& W = S.W;
     const int nf = W.nf;
     QrCoarse C;
     C.ng = 0; C.Hs = S.Hc; C.g = S.gc; C.ubz = S.ubc; C.grp = S.grp;
+    C.max_rounds = max_rounds > 0 ? max_rounds : QR_COARSE_MAX_ROUNDS;
     if (!S.Hc || nf < 8 || (opt.flags & QR_QP_NO_PREDICTION)) return C;
     QR_THREADS(t) {
         if (t == 0) {
@@ -334,7 +336,7 @@ QR_DEV void qr_mpc_solve_problem(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
     if (status == 0) {
         qr_mpc_condense_to_work<NT>(A, S);
         QR_PROF(21);
-        const QrCoarse C = qr_mpc_build_coarse<NT>(S, A.opt);
+        const QrCoarse C = qr_mpc_build_coarse<NT>(S, A.opt, A.coarse_rounds);
         QR_PROF(23);
         status = qr_qp_solve<NT>(S.W, A.opt, &it, &rounds, &x, &C QR_PROF_PASS);
         status = qr_result_status<NT>(S, x, status);
@@ -408,7 +410,7 @@ QR_DEV void qr_qp_solve_problem(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
         QR_FOR(i, 3 * nf) S.W.g[i] = (double)g[3 * S.fs[i / 3] + i % 3];
         QR_SYNC();
         QR_PROF_DECL;
-        const QrCoarse C = qr_mpc_build_coarse<NT>(S, A.opt);
+        const QrCoarse C = qr_mpc_build_coarse<NT>(S, A.opt, A.coarse_rounds);
         status = qr_qp_solve<NT>(S.W, A.opt, &it, &rounds, &x, &C QR_PROF_PASS);
         status = qr_result_status<NT>(S, x, status);
     }

@@ -928,6 +928,7 @@ QR_DEV int qr_ipm(QrQpWork& W, const qr_qp_options& opt, double tol, int* conver
 // qr_mpc_build_coarse in mpc_problem.h): ng tied foot-steps, grp[f] = tied foot-step of foot-step f.
 struct QrCoarse {
     int ng;
+    int max_rounds;   // rounds spent on the coarse problem at most
     double *Hs, *g, *ubz;
     const int* grp;
 };
@@ -956,7 +957,7 @@ QR_DEV int qr_qp_solve(QrQpWork& W, const qr_qp_options& opt, int* ipm_iters, in
     double tol = opt.ipm_tol;
     for (;;) {
         int maxr = opt.max_as_rounds;
-        if (stage == 0) { W.nf = C->ng; W.Hs = C->Hs; W.g = C->g; W.ubz = C->ubz; maxr = QR_COARSE_MAX_ROUNDS; }
+        if (stage == 0) { W.nf = C->ng; W.Hs = C->Hs; W.g = C->g; W.ubz = C->ubz; maxr = C->max_rounds; }
         else if (stage == 3) { mode = 0; maxr = opt.max_polish_rounds; }
         const int rounds = qr_active_set<NT>(W, opt, &ok, mode, maxr QR_PROF_PASS);
         if (stage == 0) {

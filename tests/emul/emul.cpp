@@ -76,6 +76,36 @@ extern "C" int qr_emul_mpc_condense_batch(const qr_mpc_params* P, int batch, con
     return 0;
 }
 
+// Number of (row, column) pairs of qH for which qr_condense_h_pair (the interleaved evaluation the fused path uses)
+// differs in any bit from two calls of qr_condense_h_entry (the evaluation that is checked against the oracle).
+extern "C" int qr_emul_condense_pair_mismatches(const qr_mpc_params* P, int batch, const float* p, const float* v,
+                                                const float* quat, const float* w, const float* r_feet,
+                                                const float* rpy, const float* traj, const float* gait) {
+    QrMpcArgs A;
+    memset(&A, 0, sizeof(A));
+    A.P = *P; A.opt = emul_default_options(); A.batch = batch; A.nfcap = 4 * P->horizon;
+    A.p = p; A.v = v; A.quat = quat; A.w = w; A.r_feet = r_feet; A.rpy = rpy; A.traj = traj; A.gait = gait;
+    EmulTeam team(A.nfcap, P->horizon);
+    QrMpcSmem& S = team.S;
+    const int h = P->horizon, n = 12 * h;
+    int bad = 0;
+    for (int i = 0; i < batch; ++i) {
+        qr_mpc_stage<128>(A, i, S);
+        QrCondenseTables& T = *S.T;
+        qr_condense_model(A.P, S.state, S.state + 3, S.state + 6, S.state + 10, S.state + 13, S.state + 25, T);
+        qr_condense_tables<128>(A.P, S.traj, T);
+        for (int r = 0; r < n; ++r)
+            for (int c = 0; c <= r; ++c) {
+                float a, b;
+                qr_condense_h_pair(T, h, r / 12, (r % 12) / 3, r % 3, c / 12, (c % 12) / 3, c % 3, &a, &b);
+                const float a0 = qr_condense_h_entry(T, h, r / 12, (r % 12) / 3, r % 3, c / 12, (c % 12) / 3, c % 3);
+                const float b0 = qr_condense_h_entry(T, h, c / 12, (c % 12) / 3, c % 3, r / 12, (r % 12) / 3, r % 3);
+                bad += (memcmp(&a, &a0, 4) != 0) + (memcmp(&b, &b0, 4) != 0);
+            }
+    }
+    return bad;
+}
+
 extern "C" int qr_emul_qp_solve_batch(int horizon, float mu, const qr_qp_options* opt, int batch,
                                       const float* H, const float* g, const float* ub, const float* mu_i,
                                       float* x_out, double* x_out_f64, int32_t* status_out, int32_t* iters_out) {

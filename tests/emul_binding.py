@@ -38,6 +38,10 @@ class Emul:
                                             self._fp(H), self._fp(g), self._fp(ub))
         return H, g, ub
 
+    def condense_pair_mismatches(self, P, batch):
+        B = batch["p"].shape[0]
+        return int(self.lib.qr_emul_condense_pair_mismatches(C.byref(P), B, *[self._fp(batch[k]) for k in _KEYS]))
+
     def solve(self, P, batch, opt=None, per_instance_mu=False):
         B, h = batch["p"].shape[0], P.horizon
         n = 12 * h

@@ -154,3 +154,12 @@ def test_cycling_instances_converge_without_fallback(emul, oracle, pkg):
         H, g, ub = oracle.mpc_build(Po, sub, i)
         stat, feas = oracle.kkt_certificate(H, g, A, np.zeros(20 * h), ub.astype(float), e["u64"][i])
         assert stat < 1e-7 and feas < 1e-7, (i, stat, feas)
+
+
+def test_interleaved_hessian_pair_is_bit_identical(emul, oracle, pkg):
+    """The fused path evaluates a Hessian entry and its transposed entry in one interleaved loop
+    (qr_condense_h_pair); every bit equals the entry-wise evaluation that the golden / oracle tests pin."""
+    for robot, h, gait, seed in (("a1", 10, "trot", 51), ("lite3", 5, "trot", 52), ("aliengo", 16, "mixed", 53)):
+        b = pkg.synth.make_mpc_batch(robot, h, 0.03, 6, seed=seed, gait=gait)
+        P = oracle.params_of(b["robot"], h, 0.03)
+        assert emul.condense_pair_mismatches(P, b) == 0
