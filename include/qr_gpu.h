@@ -61,8 +61,18 @@ typedef struct {
     double mult_tol;          /* 1e-11 admissible negative multiplier after the polish           */
 } qr_qp_options;
 
-/* Device selection / workspace creation.  Must be called once per process (per GPU) before any
- * solve.  device < 0 keeps the current CUDA device. */
+/* Device selection / context creation.  qr_gpu_init(device) makes `device` the calling thread's current CUDA
+ * device (device < 0 keeps the current one) and creates the engine's context on it; it may be called for several
+ * devices of one process and again from every thread that wants to use a device.  qr_gpu_shutdown frees the
+ * contexts of all devices.
+ *
+ * Threading / stream contract.  Every entry point works on the CALLING THREAD'S CURRENT DEVICE, which must have
+ * been initialised (QR_ECUDA otherwise), and all device pointers passed to it must belong to that device.  The
+ * device-pointer calls only enqueue work on the caller's stream and may be issued concurrently from several host
+ * threads and on several streams: workspaces are pooled per device and keyed by stream (a launch sequence never
+ * shares its scratch, counters or work lists with one that may run at the same time).  The *_host calls are
+ * synchronous, take a private staging slot for their duration and are equally safe to call from several threads.
+ * qr_gpu_last_error() returns the last error text of the calling thread. */
 int qr_gpu_init(int device);
 void qr_gpu_shutdown(void);
 const char* qr_gpu_last_error(void);
@@ -87,8 +97,10 @@ int qr_gpu_mpc_occupancy(int horizon, int stance_footsteps, int* sm_count, int* 
  *   u_out          [batch][12h] or NULL  full solution vector
  *   status_out     [batch] or NULL
  *   iters_out      [batch][2] or NULL    {interior-point iterations (0 unless the fallback ran),
- *                                         active-set rounds (all phases)}
- * All pointers are DEVICE pointers; the call is asynchronous on `cuda_stream` (a cudaStream_t). */
+ *                                         full-size active-set rounds incl. the verification rounds after a
+ *                                         fallback; the rounds on the coarse prediction problem are not counted}
+ * All pointers are DEVICE pointers; the call is asynchronous on `cuda_stream` (a cudaStream_t) and safe to issue
+ * concurrently on other streams / from other threads (see the contract above). */
 int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_options* opt, int batch,
                            const float* p, const float* v, const float* quat, const float* w,
                            const float* r_feet, const float* rpy, const float* traj,
@@ -105,6 +117,19 @@ int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_options* opt
                                 const float* gait, const float* mu_i, const float* fmax_i,
                                 float* grf_out, float* u_out, int32_t* status_out,
                                 int32_t* iters_out);
+
+/* The same host-buffer call sharded over several GPUs of this process (BASELINE.json configs[2]: "batch 65536
+ * sharded across 8 B200"; the reference's seam is the single SolveDenseMPC call,
+ * qr_mpc_stance_leg_controller.cpp:385-410).  The batch is cut into contiguous shards [g*B/G, (g+1)*B/G), one per
+ * entry of devices[]; one host thread per device uploads its shard, runs the fused kernel and downloads the
+ * results straight into the caller's arrays (that device->host copy is the "final gather").  There is no
+ * collective on the path.  Contexts of devices not yet initialised are created on the fly; the calling thread's
+ * current device is restored before returning.  Returns the first failing shard's code. */
+int qr_gpu_mpc_solve_batch_host_multi(int n_devices, const int* devices, const qr_mpc_params* P,
+                                      const qr_qp_options* opt, int batch, const float* p, const float* v,
+                                      const float* quat, const float* w, const float* r_feet, const float* rpy,
+                                      const float* traj, const float* gait, const float* mu_i, const float* fmax_i,
+                                      float* grf_out, float* u_out, int32_t* status_out, int32_t* iters_out);
 
 /* qr_gpu_mpc_condense_batch -- replaces ComputeContinuousTimeStateSpaceMatrices + ConvertToDiscreteQP
  * + the H/g/U_b build of SolveMPC (qr_mpc_interface.cpp:296-331, 257-293, 359-412): float32 QP data

@@ -243,6 +243,77 @@ def polish_from_working_set(H, g, A, lb, ub, cstat, refine: int = 8):
     return sol[:n].astype(float), sol[n:].astype(float)
 
 
+def polish_fast(H, g, A, lb, ub, cstat, refine: int = 4):
+    """Same x* as polish_from_working_set, for bulk use: ONE float64 LU factorisation of the KKT matrix of the
+    working set (qpOASES keeps its rows linearly independent, H is positive definite, so K is non-singular) and
+    residual refinement in numpy.longdouble against that factorisation.  Falls back to the least-squares version
+    when the refinement does not contract (a dependent working set)."""
+    import scipy.linalg as sla
+    LD = np.longdouble
+    Hs = (np.asarray(H, LD) + np.asarray(H, LD).T) / 2
+    rows = np.nonzero(cstat)[0]
+    Ar = np.asarray(A, LD)[rows]
+    rhs = np.where(np.asarray(cstat)[rows] > 0, np.asarray(ub, LD)[rows], np.asarray(lb, LD)[rows])
+    n, k = Hs.shape[0], len(rows)
+    K = np.zeros((n + k, n + k), LD)
+    K[:n, :n] = Hs
+    K[:n, n:] = -Ar.T
+    K[n:, :n] = Ar
+    r = np.concatenate([-np.asarray(g, LD), rhs])
+    try:
+        lu = sla.lu_factor(K.astype(float), check_finite=False)
+        sol = sla.lu_solve(lu, r.astype(float), check_finite=False).astype(LD)
+        res0 = None
+        for _ in range(refine):
+            res = r - K @ sol
+            sol = sol + sla.lu_solve(lu, res.astype(float), check_finite=False).astype(LD)
+            res0 = float(np.abs(res).max()) if res0 is None else res0
+        final = float(np.abs(r - K @ sol).max())
+        if np.isfinite(final) and final <= 1e-12 * max(1.0, float(np.abs(r).max())):
+            return sol[:n].astype(float), sol[n:].astype(float)
+    except (ValueError, sla.LinAlgError):
+        pass
+    return polish_from_working_set(H, g, A, lb, ub, cstat)
+
+
+def exact_optimum(H, g, A, lb, ub, cstat, max_changes: int = 60, tol: float = 1e-9):
+    """x* = THE minimiser of the reference's QP (strictly convex, so unique), certified.
+
+    Starts from converged qpOASES' final working set (cstat) and its extended-precision KKT solve (polish_fast).  That
+    point is the exact optimum only if the working set is the optimal one; qpOASES stops on its homotopy-length
+    tolerance, and on about one instance in a thousand the working set it stops with still misses a row that the exact
+    KKT point violates by ~1e-3 N (or holds a row whose exact multiplier is slightly negative).  So the working set is
+    corrected here by a plain primal-dual active-set continuation in extended precision -- add the most violated row,
+    else drop the row with the most wrong-signed multiplier, re-solve -- until every row is feasible to `tol` and every
+    multiplier has the right sign.  Returns (x, working set, changes made)."""
+    cstat = np.array(cstat, np.int32, copy=True)
+    lb = np.asarray(lb, float)
+    ub = np.asarray(ub, float)
+    A = np.asarray(A, float)
+    eq = lb == ub
+    for change in range(max_changes + 1):
+        x, lam = polish_fast(H, g, A, lb, ub, cstat)
+        rows = np.nonzero(cstat)[0]
+        ax = A @ x
+        viol_lo = np.where(cstat == 0, lb - ax, -np.inf)
+        viol_up = np.where(cstat == 0, ax - ub, -np.inf)
+        worst_lo, worst_up = int(viol_lo.argmax()), int(viol_up.argmax())
+        if max(viol_lo[worst_lo], viol_up[worst_up]) > tol:
+            if viol_lo[worst_lo] >= viol_up[worst_up]:
+                cstat[worst_lo] = -1
+            else:
+                cstat[worst_up] = 1
+            continue
+        # Hs x + g = Ar' lam: a row at its lower bound needs lam >= 0, at its upper bound lam <= 0
+        wrong = np.where(eq[rows], 0.0, np.where(cstat[rows] < 0, -lam, lam))
+        k = int(wrong.argmax()) if len(rows) else -1
+        if k >= 0 and wrong[k] > tol:
+            cstat[rows[k]] = 0
+            continue
+        return x, cstat, change
+    raise RuntimeError("exact_optimum: the working set did not settle")
+
+
 def kkt_certificate(H, g, A, lb, ub, x, act_tol: float = 1e-7):
     """Independent optimality check of a candidate x for min 1/2 x'Hs x + g'x, lb <= Ax <= ub.
 
@@ -318,6 +389,22 @@ def wbc_step(model: WbcModel, state, cmd, contact, precision: str = "f64"):
         out[name] = dbg[o:o + n].reshape(shape).copy()
         o += n
     return out
+
+
+def ref_wbc_time_batch(model: WbcModel, state, cmd, contact, want_tau: bool = False):
+    """Times the reference's own WBC classes (oracle/_ref/libqr_wbc_ref.so: controller objects built once, then per
+    robot UpdateModel + ContactTaskUpdate + FindConfiguration + MakeTorque, qr_wbc_locomotion_controller.cpp:108-134)
+    on the rows of state / cmd / contact in this process.  Returns (seconds, lat[count], tau[count,12] or None)."""
+    fn = _ref_wbc().qr_ref_wbc_time_batch
+    fn.restype = C.c_double
+    state = np.ascontiguousarray(state, np.float32)
+    cmd = np.ascontiguousarray(cmd, np.float32)
+    contact = np.ascontiguousarray(contact, np.int32)
+    cnt = state.shape[0]
+    lat = np.empty(cnt)
+    tau = np.empty((cnt, 12), np.float32) if want_tau else None
+    sec = fn(C.byref(model), cnt, _fp(state), _fp(cmd), _ip(contact), _fp(tau) if want_tau else None, _dp(lat))
+    return sec, lat, tau
 
 
 def swing_parabola(start, end, height, t, phase_module=False):

@@ -22,8 +22,10 @@
 
 #include "qr_oracle.h"
 
+#include <chrono>
 #include <cmath>
 #include <memory>
+#include <vector>
 
 using robotics::math::coordinateRotation;
 using robotics::math::CoordinateAxis;
@@ -101,40 +103,52 @@ void build_model(FloatingBaseModel<float>& model, const qro_wbc_model* cfg) {
 
 }   // namespace
 
-extern "C" int qr_ref_wbc_step(const qro_wbc_model* cfg, const float* state, const float* cmd, const int* contact,
-                               float* tau, float* fr, float* qdes, float* qddes, float* dbg) {
+namespace {
+
+// The controller objects qrWbcLocomotionController owns (construction + gains, qr_wbc_locomotion_controller.cpp:29-73),
+// built once per robot model like the reference does at start-up; step() is one recomputing tick.
+struct RefWbc {
+    static constexpr size_t dimConfig = 18;
     const int FOOT[4] = {9, 11, 13, 15};   // Quadruped::linkID::FR, FL, HR, HL (config/qr_enum_types.h:35-45)
     FloatingBaseModel<float> fb;
-    build_model(fb, cfg);
-
-    // construction + gains, qr_wbc_locomotion_controller.cpp:29-73
-    const size_t dimConfig = 18;
     std::vector<qrTask<float>*> taskList;
     std::vector<qrSingleContact<float>*> contactList;
-    qrMultitaskProjection<float> multitask(dimConfig);
-    qrWholeBodyImpulseCtrl<float> wbic(dimConfig, &contactList, &taskList);
+    qrMultitaskProjection<float> multitask;
+    qrWholeBodyImpulseCtrl<float> wbic;
     qrWBICExtraData<float> extra;
-    extra.weightFb = DVec<float>::Constant(6, 0.1);
-    extra.weightFr = DVec<float>::Constant(12, 1);
-    qrTaskBodyOrientation<float> taskOri(&fb);
-    qrTaskBodyPosition<float> taskPos(&fb);
+    std::unique_ptr<qrTaskBodyOrientation<float>> taskOriP;
+    std::unique_ptr<qrTaskBodyPosition<float>> taskPosP;
     std::unique_ptr<qrSingleContact<float>> footContact[4];
     std::unique_ptr<qrTaskLinkPosition<float>> taskFoot[4];
-    for (int l = 0; l < 4; ++l) {
-        footContact[l].reset(new qrSingleContact<float>(&fb, FOOT[l]));
-        taskFoot[l].reset(new qrTaskLinkPosition<float>(&fb, FOOT[l]));
-    }
-    for (int i = 0; i < 3; ++i) {
-        taskPos.Kp[i] = 100.;
-        taskPos.Kd[i] = 10.;
-        taskOri.Kp[i] = 100.;
-        taskOri.Kd[i] = 10.;
+
+    explicit RefWbc(const qro_wbc_model* cfg) : multitask(dimConfig), wbic(dimConfig, &contactList, &taskList) {
+        build_model(fb, cfg);
+        extra.weightFb = DVec<float>::Constant(6, 0.1);
+        extra.weightFr = DVec<float>::Constant(12, 1);
+        taskOriP.reset(new qrTaskBodyOrientation<float>(&fb));
+        taskPosP.reset(new qrTaskBodyPosition<float>(&fb));
         for (int l = 0; l < 4; ++l) {
-            taskFoot[l]->Kp[i] = 500;
-            taskFoot[l]->Kd[i] = 10.;
+            footContact[l].reset(new qrSingleContact<float>(&fb, FOOT[l]));
+            taskFoot[l].reset(new qrTaskLinkPosition<float>(&fb, FOOT[l]));
+        }
+        for (int i = 0; i < 3; ++i) {
+            taskPosP->Kp[i] = 100.;
+            taskPosP->Kd[i] = 10.;
+            taskOriP->Kp[i] = 100.;
+            taskOriP->Kd[i] = 10.;
+            for (int l = 0; l < 4; ++l) {
+                taskFoot[l]->Kp[i] = 500;
+                taskFoot[l]->Kd[i] = 10.;
+            }
         }
     }
 
+    int step(const float* state, const float* cmd, const int* contact, float* tau, float* fr, float* qdes, float* qddes,
+             float* dbg) {
+    qrTaskBodyOrientation<float>& taskOri = *taskOriP;
+    qrTaskBodyPosition<float>& taskPos = *taskPosP;
+    taskList.clear();      // qr_wbc_locomotion_controller.cpp:175-176 (ContactTaskUpdate starts from empty lists)
+    contactList.clear();
     // UpdateModel, :138-168
     FBModelState<float> ms;
     ms.q = DVec<float>::Zero(12);
@@ -220,4 +234,34 @@ extern "C" int qr_ref_wbc_step(const qro_wbc_model* cfg, const float* state, con
         for (int i = 0; i < 18; ++i) *o++ = 0.f;
     }
     return 0;
+    }   // step
+};
+
+}   // namespace
+
+extern "C" int qr_ref_wbc_step(const qro_wbc_model* cfg, const float* state, const float* cmd, const int* contact,
+                               float* tau, float* fr, float* qdes, float* qddes, float* dbg) {
+    RefWbc ctl(cfg);
+    return ctl.step(state, cmd, contact, tau, fr, qdes, qddes, dbg);
+}
+
+// Times `count` ticks (rows of state [37], cmd [66], contact [4]) on controller objects built once, like the running
+// reference: per tick UpdateModel + ContactTaskUpdate + FindConfiguration + MakeTorque.  tau_out [count][12] or NULL,
+// lat_out [count] seconds or NULL.  Returns the total seconds.
+
+extern "C" double qr_ref_wbc_time_batch(const qro_wbc_model* cfg, int count, const float* state, const float* cmd,
+                                        const int* contact, float* tau_out, double* lat_out) {
+    RefWbc ctl(cfg);
+    float tau[12], fr[12], qdes[12], qddes[12];
+    double total = 0;
+    for (int i = 0; i < count; ++i) {
+        const auto t0 = std::chrono::steady_clock::now();
+        ctl.step(state + 37 * (size_t)i, cmd + 66 * (size_t)i, contact + 4 * (size_t)i, tau, fr, qdes, qddes, nullptr);
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        total += dt;
+        if (lat_out) lat_out[i] = dt;
+        if (tau_out)
+            for (int k = 0; k < 12; ++k) tau_out[12 * (size_t)i + k] = tau[k];
+    }
+    return total;
 }

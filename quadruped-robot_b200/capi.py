@@ -40,7 +40,7 @@ EXPORTS = ["qr_gpu_init", "qr_gpu_shutdown", "qr_gpu_last_error", "qr_gpu_mpc_oc
            "qr_gpu_mpc_solve_batch", "qr_gpu_mpc_solve_batch_host", "qr_gpu_mpc_condense_batch",
            "qr_gpu_qp_solve_batch", "qr_gpu_wbc_solve_batch", "qr_gpu_wbc_solve_batch_f64",
            "qr_gpu_swing_parabola_batch", "qr_gpu_mpc_inputs_batch", "qr_gpu_mpc_leg_torque_batch", "qr_gpu_force_balance_batch", "qr_gpu_wbc_solve_batch_host", "qr_gpu_swing_bspline_batch",
-           "qr_gpu_foothold_heuristic_batch"]
+           "qr_gpu_foothold_heuristic_batch", "qr_gpu_mpc_solve_batch_host_multi"]
 
 
 class WbcModel(C.Structure):
@@ -118,6 +118,25 @@ def mpc_solve_batch_host(P: MpcParams, batch: dict, opt: QpOptions | None = None
         C.byref(P), C.byref(opt) if opt is not None else None, B, *[_vp(batch[k]) for k in _KEYS],
         _vp(batch["mu"]) if per_instance_mu else None, None, _vp(grf), _vp(u), _vp(status), _vp(iters))
     _check(rc, "qr_gpu_mpc_solve_batch_host")
+    return dict(grf=grf, u=u, status=status, iters=iters)
+
+
+def mpc_solve_batch_host_multi(P: MpcParams, batch: dict, devices, opt: QpOptions | None = None, per_instance_mu=False,
+                               want_u=False, want_info=True, out: dict | None = None):
+    """One host batch sharded over `devices` (one host thread and one contiguous shard per GPU of this process);
+    results gathered into one set of host arrays.  `out` may supply preallocated (e.g. pinned) result arrays."""
+    B = batch["p"].shape[0]
+    h = P.horizon
+    out = out or {}
+    grf = out.get("grf") if out.get("grf") is not None else np.empty((B, 12), np.float32)
+    u = out.get("u") if want_u and out.get("u") is not None else (np.empty((B, 12 * h), np.float32) if want_u else None)
+    status = out.get("status") if out.get("status") is not None else (np.empty(B, np.int32) if want_info else None)
+    iters = out.get("iters") if out.get("iters") is not None else (np.empty((B, 2), np.int32) if want_info else None)
+    devs = (C.c_int * len(devices))(*devices)
+    rc = lib().qr_gpu_mpc_solve_batch_host_multi(
+        len(devices), devs, C.byref(P), C.byref(opt) if opt is not None else None, B, *[_vp(batch[k]) for k in _KEYS],
+        _vp(batch["mu"]) if per_instance_mu else None, None, _vp(grf), _vp(u), _vp(status), _vp(iters))
+    _check(rc, "qr_gpu_mpc_solve_batch_host_multi")
     return dict(grf=grf, u=u, status=status, iters=iters)
 
 

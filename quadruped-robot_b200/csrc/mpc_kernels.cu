@@ -9,8 +9,11 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "mpc_problem.h"
 
@@ -161,36 +164,99 @@ __global__ void __launch_bounds__(QR_NT) qr_qp_solve_kernel(const QrMpcArgs A) {
 }
 
 // ------------------------------------------------------------------------------------------
-// host-side context
+// host-side contexts: one per initialised device
 // ------------------------------------------------------------------------------------------
+// Threading and stream contract (include/qr_gpu.h): every entry point runs on the calling thread's CURRENT device,
+// which must have been initialised by qr_gpu_init; device-pointer calls are asynchronous on the caller's stream and
+// may be issued concurrently from several host threads and on several streams.  What makes that safe:
+//  * workspaces ("lanes": the L2-resident scratch slices, the size-class counters, tickets and work lists of one
+//    launch sequence) come from a per-device pool keyed by stream.  A lane is handed to the stream that used it last
+//    (stream order protects it), else an idle lane is taken (its completion event has fired), else a new one is
+//    created, and only when the pool is full does the stream wait on the least recently used lane's event;
+//  * the *_host entry points take a private staging slot (device staging buffer, pinned mirror, two streams) for
+//    the whole call, so two host threads never share a buffer; error paths drain the slot's streams before it is
+//    released, so no copy from caller memory is left pending;
+//  * g_mu serialises only the bookkeeping and the launch calls themselves, never device execution.
+constexpr int QR_MAX_DEVICES = 16;
+constexpr int QR_MAX_LANES = 8;
+constexpr int QR_MAX_SLOTS = 4;
+constexpr int QR_MAX_WBC_MODELS = 4;
+
+struct Plan {
+    int grid = 0, occ = 0;
+    size_t smem = 0;
+    bool hsg = false, kg = false;
+    size_t scratch_doubles(int nfcap) const {   // per launch: [grid][fallback] [grid][Hc] [grid][Hs] [grid][K]
+        size_t d = (size_t)grid * qr_fallback_doubles(nfcap);
+        d += (size_t)grid * 9 * qr_ntri(nfcap);   // coarse Hessian of the active-set prediction
+        if (hsg) d += (size_t)grid * 9 * qr_ntri(nfcap);
+        if (kg) d += (size_t)grid * 9 * qr_ntri(nfcap);
+        return d;
+    }
+};
+struct GeomEntry { const void* kern; int nfcap, horizon; bool want_hsg, want_kg; Plan plan; };
+
+struct Lane {
+    double* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    int* work = nullptr;            // [2*nclass] counters (counts, tickets) followed by [nclass][batch] lists
+    size_t work_bytes = 0;
+    cudaEvent_t done = nullptr;     // recorded behind the last launch that used the lane
+    cudaStream_t last = nullptr;    // stream of that launch
+    bool used = false;              // `done` has been recorded at least once
+    unsigned long long stamp = 0;   // least-recently-used order
+};
+
+struct HostSlot {
+    bool created = false, busy = false;
+    unsigned char* stage = nullptr;   // device staging buffer
+    size_t stage_bytes = 0;
+    unsigned char* pin = nullptr;     // pinned host mirror (small batches: one copy each way)
+    size_t pin_bytes = 0;
+    cudaStream_t stream[2] = {nullptr, nullptr};
+};
+
+struct WbcModelSlot {
+    bool valid = false;
+    qr_wbc_model key;
+    void* dev = nullptr;              // QrWbcModelDev on this device
+    unsigned long long stamp = 0;
+};
+
 struct Ctx {
     bool ready = false;
     int device = 0;
     int sm_count = 0;
     size_t smem_optin = 0;
-    // Per-launch device buffers exist twice ("lanes"): the *_host entry point solves a large batch as two chunks
-    // on two streams, so that the second chunk's upload runs under the first chunk's kernels and its CTAs move in
-    // as the first chunk's CTAs retire.  Everything else uses lane 0.
-    double* scratch_[2] = {nullptr, nullptr};
-    size_t scratch_bytes_[2] = {0, 0};
-    int* work_[2] = {nullptr, nullptr};   // [2*nclass] counters (counts, tickets) followed by [nclass][batch] lists
-    size_t work_bytes_[2] = {0, 0};
-    cudaStream_t stream2 = nullptr;       // lane 1 of the *_host entry point
-    // staging buffers of the *_host entry point
-    unsigned char* stage = nullptr;
-    size_t stage_bytes = 0;
-    unsigned char* pin = nullptr;   // pinned host mirror of the staging buffer (small batches: one copy each way)
-    size_t pin_bytes = 0;
-    cudaStream_t stream = nullptr;
-    char err[256] = {0};
+    Lane lanes[QR_MAX_LANES];
+    int nlanes = 0;
+    unsigned long long clock = 0;
+    HostSlot slots[QR_MAX_SLOTS];
+    GeomEntry geom[96];
+    int ngeom = 0;
+    WbcModelSlot wbc_models[QR_MAX_WBC_MODELS];
+    int wbc_occ = 0;                  // resident CTAs per SM of the WBC kernel (0: not queried yet)
 };
-Ctx g_ctx;
+Ctx g_dev[QR_MAX_DEVICES];
 std::mutex g_mu;
+std::condition_variable g_slot_cv;
+thread_local char t_err[256] = {0};
 
 int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
-    if (e != cudaSuccess) snprintf(g_ctx.err, sizeof(g_ctx.err), "%s: %s", what, cudaGetErrorString(e));
-    else snprintf(g_ctx.err, sizeof(g_ctx.err), "%s", what);
+    if (e != cudaSuccess) snprintf(t_err, sizeof(t_err), "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(t_err, sizeof(t_err), "%s", what);
     return code;
+}
+
+// Context of the calling thread's current device (null + error when that device was not initialised).
+Ctx* current_ctx() {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess || dev < 0 || dev >= QR_MAX_DEVICES || !g_dev[dev].ready) {
+        fail(QR_ECUDA, "qr_gpu_init was not called for the current device (or no CUDA device)");
+        return nullptr;
+    }
+    return &g_dev[dev];
 }
 
 qr_qp_options default_options() {
@@ -205,37 +271,18 @@ qr_qp_options default_options() {
     return o;
 }
 
-// Launch geometry of one size class.  *hs_global is set when H does not fit in shared memory next to
-// the matrix under factorisation (capacities above ~44 foot-steps) and has to live in the L2-resident
-// global scratch instead.
 // Launch plan of one kernel for one workspace capacity: where the two block-packed matrices live, dynamic shared
-// memory, resident CTAs per SM.  hsg / kg are requests on input (true: keep that matrix in the global scratch) and
+// memory, resident CTAs per SM.  want_hsg / want_kg are requests (true: keep that matrix in the global scratch) and
 // are forced to true when the workspace would not fit in shared memory otherwise.
-struct Plan {
-    int grid = 0, occ = 0;
-    size_t smem = 0;
-    bool hsg = false, kg = false;
-    size_t scratch_doubles(int nfcap) const {   // per launch: [grid][fallback] [grid][Hc] [grid][Hs] [grid][K]
-        size_t d = (size_t)grid * qr_fallback_doubles(nfcap);
-        d += (size_t)grid * 9 * qr_ntri(nfcap);   // coarse Hessian of the active-set prediction
-        if (hsg) d += (size_t)grid * 9 * qr_ntri(nfcap);
-        if (kg) d += (size_t)grid * 9 * qr_ntri(nfcap);
-        return d;
-    }
-};
-struct GeomEntry { const void* kern; int nfcap, horizon; bool want_hsg, want_kg; Plan plan; };
-GeomEntry g_geom[96];
-int g_ngeom = 0;
-
 template <typename Kern>
-int launch_geometry(Kern kern, int nfcap, int horizon, int batch, Plan* out, bool want_hsg = false, bool want_kg = false,
-                    int nt = QR_NT) {
+int launch_geometry(Ctx& cx, Kern kern, int nfcap, int horizon, int batch, Plan* out, bool want_hsg = false,
+                    bool want_kg = false, int nt = QR_NT) {
     if (!kern) return fail(QR_EINVAL, "no kernel instantiated for this size class");
     Plan pl;
     bool found = false;
     // attribute + occupancy queries cost microseconds each: remember them per (kernel, class, horizon, request)
-    for (int i = 0; i < g_ngeom && !found; ++i) {
-        const GeomEntry& ge = g_geom[i];
+    for (int i = 0; i < cx.ngeom && !found; ++i) {
+        const GeomEntry& ge = cx.geom[i];
         if (ge.kern == (const void*)kern && ge.nfcap == nfcap && ge.horizon == horizon && ge.want_hsg == want_hsg &&
             ge.want_kg == want_kg) {
             pl = ge.plan;
@@ -246,20 +293,20 @@ int launch_geometry(Kern kern, int nfcap, int horizon, int batch, Plan* out, boo
         pl.hsg = want_hsg;
         pl.kg = want_kg;
         size_t bytes = qr_mpc_smem_bytes(nfcap, horizon, !pl.hsg, !pl.kg);
-        if (bytes + 1024 > g_ctx.smem_optin && !pl.hsg) { pl.hsg = true; bytes = qr_mpc_smem_bytes(nfcap, horizon, false, !pl.kg); }
-        if (bytes + 1024 > g_ctx.smem_optin && !pl.kg) { pl.kg = true; bytes = qr_mpc_smem_bytes(nfcap, horizon, false, false); }
-        if (bytes + 1024 > g_ctx.smem_optin) return fail(QR_EINVAL, "horizon needs more shared memory than one CTA may use");
+        if (bytes + 1024 > cx.smem_optin && !pl.hsg) { pl.hsg = true; bytes = qr_mpc_smem_bytes(nfcap, horizon, false, !pl.kg); }
+        if (bytes + 1024 > cx.smem_optin && !pl.kg) { pl.kg = true; bytes = qr_mpc_smem_bytes(nfcap, horizon, false, false); }
+        if (bytes + 1024 > cx.smem_optin) return fail(QR_EINVAL, "horizon needs more shared memory than one CTA may use");
         // opt in to the device maximum once per kernel (the launch's own byte count decides the occupancy)
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_ctx.smem_optin - 256);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cx.smem_optin - 256);
         if (e != cudaSuccess) return fail(QR_ECUDA, "cudaFuncSetAttribute", e);
         int occ = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, bytes);
         if (e != cudaSuccess) return fail(QR_ECUDA, "cudaOccupancyMaxActiveBlocksPerMultiprocessor", e);
         pl.occ = occ < 1 ? 1 : occ;
         pl.smem = bytes;
-        if (g_ngeom < 96) g_geom[g_ngeom++] = GeomEntry{(const void*)kern, nfcap, horizon, want_hsg, want_kg, pl};
+        if (cx.ngeom < 96) cx.geom[cx.ngeom++] = GeomEntry{(const void*)kern, nfcap, horizon, want_hsg, want_kg, pl};
     }
-    int g = g_ctx.sm_count * pl.occ;
+    int g = cx.sm_count * pl.occ;
     if (g > batch) g = batch;
     if (g < 1) g = 1;
     pl.grid = g;
@@ -267,21 +314,70 @@ int launch_geometry(Kern kern, int nfcap, int horizon, int batch, Plan* out, boo
     return QR_OK;
 }
 
-int ensure_scratch_doubles(size_t doubles, int lane = 0) {
-    const size_t need = doubles * sizeof(double);
-    if (need <= g_ctx.scratch_bytes_[lane]) return QR_OK;
-    if (g_ctx.scratch_[lane]) cudaFree(g_ctx.scratch_[lane]);
-    g_ctx.scratch_[lane] = nullptr;
-    g_ctx.scratch_bytes_[lane] = 0;
-    cudaError_t e = cudaMalloc(&g_ctx.scratch_[lane], need);
-    if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMalloc(scratch)", e);
-    g_ctx.scratch_bytes_[lane] = need;
+// Workspace for a launch sequence on stream `st` (g_mu held).  See the contract at the top of this section.
+int acquire_lane(Ctx& cx, cudaStream_t st, Lane** out) {
+    Lane* pick = nullptr;
+    for (int i = 0; i < cx.nlanes && !pick; ++i)
+        if (cx.lanes[i].used && cx.lanes[i].last == st) pick = &cx.lanes[i];
+    for (int i = 0; i < cx.nlanes && !pick; ++i) {
+        Lane& l = cx.lanes[i];
+        if (!l.used) { pick = &l; break; }
+        cudaError_t q = cudaEventQuery(l.done);
+        if (q == cudaSuccess) pick = &l;
+        else if (q != cudaErrorNotReady) return fail(QR_ECUDA, "cudaEventQuery(lane)", q);
+    }
+    if (!pick && cx.nlanes < QR_MAX_LANES) {
+        Lane& l = cx.lanes[cx.nlanes];
+        cudaError_t e = cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming);
+        if (e != cudaSuccess) return fail(QR_ECUDA, "cudaEventCreate(lane)", e);
+        ++cx.nlanes;
+        pick = &l;
+    }
+    if (!pick) {
+        pick = &cx.lanes[0];
+        for (int i = 1; i < cx.nlanes; ++i)
+            if (cx.lanes[i].stamp < pick->stamp) pick = &cx.lanes[i];
+        cudaError_t e = cudaStreamWaitEvent(st, pick->done, 0);
+        if (e != cudaSuccess) return fail(QR_ECUDA, "cudaStreamWaitEvent(lane)", e);
+    }
+    pick->last = st;
+    pick->stamp = ++cx.clock;
+    *out = pick;
     return QR_OK;
 }
 
-// Point the kernel arguments at this launch's slices of the scratch.
-void bind_scratch(QrMpcArgs& A, const Plan& pl, int nfcap, int lane = 0) {
-    double* s = g_ctx.scratch_[lane];
+// Mark the end of the lane's use on the stream (also on launch errors: whatever was enqueued still owns the lane).
+void release_lane(Lane& l, cudaStream_t st) {
+    if (cudaEventRecord(l.done, st) == cudaSuccess) l.used = true;
+}
+
+int ensure_scratch_doubles(Lane& l, size_t doubles) {
+    const size_t need = doubles * sizeof(double);
+    if (need <= l.scratch_bytes) return QR_OK;
+    if (l.scratch) cudaFree(l.scratch);   // cudaFree waits for the device: nothing still reads the old buffer
+    l.scratch = nullptr;
+    l.scratch_bytes = 0;
+    cudaError_t e = cudaMalloc(&l.scratch, need);
+    if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMalloc(scratch)", e);
+    l.scratch_bytes = need;
+    return QR_OK;
+}
+
+int ensure_work(Lane& l, int nclass, int batch) {
+    const size_t need = ((size_t)2 * nclass + (size_t)nclass * batch) * sizeof(int);
+    if (need <= l.work_bytes) return QR_OK;
+    if (l.work) cudaFree(l.work);
+    l.work = nullptr;
+    l.work_bytes = 0;
+    cudaError_t e = cudaMalloc(&l.work, need);
+    if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMalloc(work lists)", e);
+    l.work_bytes = need;
+    return QR_OK;
+}
+
+// Point the kernel arguments at this launch's slices of the lane's scratch.
+void bind_scratch(QrMpcArgs& A, const Plan& pl, int nfcap, Lane& l) {
+    double* s = l.scratch;
     A.scratch = s;
     s += (size_t)pl.grid * qr_fallback_doubles(nfcap);
     A.hc_global = s;
@@ -293,16 +389,94 @@ void bind_scratch(QrMpcArgs& A, const Plan& pl, int nfcap, int lane = 0) {
 }
 
 int check_params(const qr_mpc_params* P, int batch) {
-    if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
     if (!P || batch < 0) return fail(QR_EINVAL, "null params or negative batch");
     if (P->horizon < 1 || P->horizon > QR_MAX_HORIZON) return fail(QR_EINVAL, "horizon out of range");
     if (!(P->dt > 0.f) || !(P->mass > 0.f) || !(P->mu > 0.f)) return fail(QR_EINVAL, "dt, mass and mu must be positive");
     return QR_OK;
 }
 
+// A staging slot of the *_host entry points, held for one call.  The destructor drains the slot's streams (so that
+// no copy from or to caller memory is pending when the call returns, error paths included) and hands the slot back.
+struct SlotHold {
+    Ctx* cx = nullptr;
+    HostSlot* s = nullptr;
+    ~SlotHold() {
+        if (!s) return;
+        cudaStreamSynchronize(s->stream[0]);
+        cudaStreamSynchronize(s->stream[1]);
+        {
+            std::lock_guard<std::mutex> lk(g_mu);
+            s->busy = false;
+        }
+        g_slot_cv.notify_one();
+    }
+};
+
+// Take a free staging slot of the device (waits when all QR_MAX_SLOTS are in use) with at least `bytes` of device
+// staging and, when pinned_bytes > 0, a pinned mirror of that size.
+int acquire_slot(Ctx& cx, size_t bytes, size_t pinned_bytes, SlotHold& hold) {
+    std::unique_lock<std::mutex> lk(g_mu);
+    HostSlot* s = nullptr;
+    for (;;) {
+        for (int i = 0; i < QR_MAX_SLOTS && !s; ++i)
+            if (cx.slots[i].created && !cx.slots[i].busy) s = &cx.slots[i];
+        for (int i = 0; i < QR_MAX_SLOTS && !s; ++i)
+            if (!cx.slots[i].created) s = &cx.slots[i];
+        if (s) break;
+        g_slot_cv.wait(lk);
+    }
+    if (!s->created) {
+        for (int k = 0; k < 2; ++k) {
+            cudaError_t e = cudaStreamCreateWithFlags(&s->stream[k], cudaStreamNonBlocking);
+            if (e != cudaSuccess) return fail(QR_ECUDA, "cudaStreamCreate", e);
+        }
+        s->created = true;
+    }
+    s->busy = true;
+    hold.cx = &cx;
+    hold.s = s;
+    if (bytes > s->stage_bytes) {
+        if (s->stage) cudaFree(s->stage);
+        s->stage = nullptr;
+        s->stage_bytes = 0;
+        cudaError_t e = cudaMalloc(&s->stage, bytes);
+        if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMalloc(stage)", e);
+        s->stage_bytes = bytes;
+    }
+    if (pinned_bytes > s->pin_bytes) {
+        if (s->pin) cudaFreeHost(s->pin);
+        s->pin = nullptr;
+        s->pin_bytes = 0;
+        cudaError_t e = cudaMallocHost(&s->pin, pinned_bytes);
+        if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMallocHost(pinned stage)", e);
+        s->pin_bytes = pinned_bytes;
+    }
+    return QR_OK;
+}
+
+void free_ctx(Ctx& cx) {
+    if (!cx.ready) return;
+    cudaSetDevice(cx.device);
+    cudaDeviceSynchronize();
+    for (int l = 0; l < cx.nlanes; ++l) {
+        if (cx.lanes[l].scratch) cudaFree(cx.lanes[l].scratch);
+        if (cx.lanes[l].work) cudaFree(cx.lanes[l].work);
+        if (cx.lanes[l].done) cudaEventDestroy(cx.lanes[l].done);
+    }
+    for (HostSlot& s : cx.slots) {
+        if (s.stage) cudaFree(s.stage);
+        if (s.pin) cudaFreeHost(s.pin);
+        for (int k = 0; k < 2; ++k)
+            if (s.stream[k]) cudaStreamDestroy(s.stream[k]);
+    }
+    for (WbcModelSlot& m : cx.wbc_models)
+        if (m.dev) cudaFree(m.dev);
+    cx = Ctx();
+}
+
 }  // namespace
 
-extern "C" const char* qr_gpu_last_error(void) { return g_ctx.err; }
+extern "C" const char* qr_gpu_last_error(void) { return t_err; }
 
 extern "C" int qr_gpu_init(int device) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -313,84 +487,69 @@ extern "C" int qr_gpu_init(int device) {
         e = cudaSetDevice(device);
         if (e != cudaSuccess) return fail(QR_ECUDA, "cudaSetDevice", e);
     }
-    e = cudaGetDevice(&g_ctx.device);
+    int dev = -1;
+    e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return fail(QR_ECUDA, "cudaGetDevice", e);
-    cudaDeviceProp prop;
-    e = cudaGetDeviceProperties(&prop, g_ctx.device);
-    if (e != cudaSuccess) return fail(QR_ECUDA, "cudaGetDeviceProperties", e);
-    if (prop.major < 10) return fail(QR_ECUDA, "libqr_gpu.so is built for sm_100a only");
-    g_ctx.sm_count = prop.multiProcessorCount;
-    g_ctx.smem_optin = prop.sharedMemPerBlockOptin;
-    if (!g_ctx.stream) {
-        e = cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking);
-        if (e != cudaSuccess) return fail(QR_ECUDA, "cudaStreamCreate", e);
+    if (dev < 0 || dev >= QR_MAX_DEVICES) return fail(QR_EINVAL, "device index out of range");
+    Ctx& cx = g_dev[dev];
+    if (!cx.ready) {
+        cudaDeviceProp prop;
+        e = cudaGetDeviceProperties(&prop, dev);
+        if (e != cudaSuccess) return fail(QR_ECUDA, "cudaGetDeviceProperties", e);
+        if (prop.major < 10) return fail(QR_ECUDA, "libqr_gpu.so is built for sm_100a only");
+        cx.device = dev;
+        cx.sm_count = prop.multiProcessorCount;
+        cx.smem_optin = prop.sharedMemPerBlockOptin;
+        cx.ready = true;
     }
-    g_ctx.ready = true;
-    g_ctx.err[0] = 0;
+    t_err[0] = 0;
     return QR_OK;
 }
 
 extern "C" void qr_gpu_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
-    for (int l = 0; l < 2; ++l) {
-        if (g_ctx.scratch_[l]) cudaFree(g_ctx.scratch_[l]);
-        if (g_ctx.work_[l]) cudaFree(g_ctx.work_[l]);
-    }
-    if (g_ctx.stream2) cudaStreamDestroy(g_ctx.stream2);
-    if (g_ctx.stage) cudaFree(g_ctx.stage);
-    if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
-    if (g_ctx.pin) cudaFreeHost(g_ctx.pin);
-    g_ngeom = 0;
-    g_ctx = Ctx();
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (Ctx& cx : g_dev) free_ctx(cx);
+    if (prev >= 0) cudaSetDevice(prev);
 }
 
+namespace {
 int num_classes(int horizon) { return qr_class_of(4 * horizon) + 1; }
 int class_cap(int c, int /*horizon*/) { return qr_class_cap(c); }   // always one of the instantiated capacities
 bool class_hsg(int cap) { return cap >= QR_HSG_FROM_CAP; }
 bool class_kg(int cap) { return cap >= QR_KG_FROM_CAP; }
-
-int ensure_work(int nclass, int batch, int lane = 0) {
-    const size_t need = ((size_t)2 * nclass + (size_t)nclass * batch) * sizeof(int);
-    if (need <= g_ctx.work_bytes_[lane]) return QR_OK;
-    if (g_ctx.work_[lane]) cudaFree(g_ctx.work_[lane]);
-    g_ctx.work_[lane] = nullptr;
-    g_ctx.work_bytes_[lane] = 0;
-    cudaError_t e = cudaMalloc(&g_ctx.work_[lane], need);
-    if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMalloc(work lists)", e);
-    g_ctx.work_bytes_[lane] = need;
-    return QR_OK;
-}
+}  // namespace
 
 extern "C" int qr_gpu_mpc_occupancy(int horizon, int stance_footsteps, int* sm_count, int* ctas_per_sm,
                                     int* threads_per_cta, int* smem_bytes) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
+    Ctx* cx = current_ctx();
+    if (!cx) return QR_ECUDA;
     if (horizon < 1 || horizon > QR_MAX_HORIZON) return fail(QR_EINVAL, "horizon out of range");
     if (stance_footsteps < 0 || stance_footsteps > 4 * horizon) return fail(QR_EINVAL, "stance count out of range");
     const int cap = class_cap(qr_class_of(stance_footsteps), horizon);
     Plan pl;
-    int rc = launch_geometry(fused_kernel_for(cap), cap, horizon, 1 << 30, &pl, class_hsg(cap), class_kg(cap), qr_fused_nt(cap));
+    int rc = launch_geometry(*cx, fused_kernel_for(cap), cap, horizon, 1 << 30, &pl, class_hsg(cap), class_kg(cap), qr_fused_nt(cap));
     if (rc) return rc;
-    if (sm_count) *sm_count = g_ctx.sm_count;
+    if (sm_count) *sm_count = cx->sm_count;
     if (ctas_per_sm) *ctas_per_sm = pl.occ;
     if (threads_per_cta) *threads_per_cta = qr_fused_nt(cap);
     if (smem_bytes) *smem_bytes = (int)pl.smem;
     return QR_OK;
 }
 
-static int mpc_solve_batch_lane(int lane, const qr_mpc_params* P, const qr_qp_options* opt, int batch,
-                                const float* p, const float* v, const float* quat,
-                                const float* w, const float* r_feet, const float* rpy,
-                                const float* traj, const float* gait, const float* mu_i,
-                                const float* fmax_i, float* grf_out, float* u_out,
-                                int32_t* status_out, int32_t* iters_out, void* cuda_stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
+namespace {
+// Enqueue the fused MPC solve of one batch on `st` (g_mu held by the caller).
+int mpc_enqueue(Ctx& cx, const qr_mpc_params* P, const qr_qp_options* opt, int batch, const float* p, const float* v,
+                const float* quat, const float* w, const float* r_feet, const float* rpy, const float* traj,
+                const float* gait, const float* mu_i, const float* fmax_i, float* grf_out, float* u_out,
+                int32_t* status_out, int32_t* iters_out, cudaStream_t st) {
     int rc = check_params(P, batch);
     if (rc) return rc;
     if (batch == 0) return QR_OK;
     if (!p || !v || !quat || !w || !r_feet || !rpy || !traj || !gait || !grf_out)
         return fail(QR_EINVAL, "null input/output pointer");
-    cudaStream_t st = (cudaStream_t)cuda_stream;
     const int h = P->horizon, nclass = num_classes(h);
     QrMpcArgs A;
     memset(&A, 0, sizeof(A));
@@ -400,61 +559,68 @@ static int mpc_solve_batch_lane(int lane, const qr_mpc_params* P, const qr_qp_op
     A.p = p; A.v = v; A.quat = quat; A.w = w; A.r_feet = r_feet; A.rpy = rpy; A.traj = traj; A.gait = gait;
     A.mu_i = mu_i; A.fmax_i = fmax_i;
     A.grf_out = grf_out; A.u_out = u_out; A.status_out = status_out; A.iters_out = iters_out;
-    if (batch <= g_ctx.sm_count) {
+    Lane* lane = nullptr;
+    if (batch <= cx.sm_count) {
         // Latency path: the grid cannot fill the device anyway, so skip the classification and launch the
         // largest size class once (its workspace holds any instance of this horizon).
         const int cap = class_cap(nclass - 1, h);
         Plan pl;
-        rc = launch_geometry(qr_mpc_fused_latency_kernel, cap, h, batch, &pl, false, false, QR_LAT_NT);
+        rc = launch_geometry(cx, qr_mpc_fused_latency_kernel, cap, h, batch, &pl, false, false, QR_LAT_NT);
         if (rc) return rc;
-        rc = ensure_scratch_doubles(pl.scratch_doubles(cap), lane);
+        rc = acquire_lane(cx, st, &lane);
+        if (rc) return rc;
+        rc = ensure_scratch_doubles(*lane, pl.scratch_doubles(cap));
         if (rc) return rc;
         A.nfcap = cap;
         A.coarse_rounds = QR_COARSE_MAX_ROUNDS_LAT;
-        bind_scratch(A, pl, cap, lane);
+        bind_scratch(A, pl, cap, *lane);
         qr_mpc_fused_latency_kernel<<<pl.grid, QR_LAT_NT, pl.smem, st>>>(A);
         cudaError_t e1 = cudaGetLastError();
+        release_lane(*lane, st);
         if (e1 != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_fused_latency_kernel", e1);
         return QR_OK;
     }
-    rc = ensure_work(nclass, batch, lane);
-    if (rc) return rc;
-    int* counts = g_ctx.work_[lane];
-    int* tickets = g_ctx.work_[lane] + nclass;
-    int* lists = g_ctx.work_[lane] + 2 * nclass;
     // plan of every class first (so that the scratch is sized once, before any launch)
     Plan plan[QR_NCLASS_MAX];
     size_t scratch_need = 0;
     for (int c = 0; c < nclass; ++c) {
         const int cap = class_cap(c, h);
-        rc = launch_geometry(fused_kernel_for(cap), cap, h, batch, &plan[c], class_hsg(cap), class_kg(cap), qr_fused_nt(cap));
+        rc = launch_geometry(cx, fused_kernel_for(cap), cap, h, batch, &plan[c], class_hsg(cap), class_kg(cap), qr_fused_nt(cap));
         if (rc) return rc;
         if (plan[c].hsg != class_hsg(cap) || plan[c].kg != class_kg(cap))
             return fail(QR_EINVAL, "unexpected shared-memory capacity for this size class");
         const size_t need = plan[c].scratch_doubles(cap);
         if (need > scratch_need) scratch_need = need;
     }
-    rc = ensure_scratch_doubles(scratch_need, lane);
+    rc = acquire_lane(cx, st, &lane);
     if (rc) return rc;
+    rc = ensure_work(*lane, nclass, batch);
+    if (rc) return rc;
+    rc = ensure_scratch_doubles(*lane, scratch_need);
+    if (rc) return rc;
+    int* counts = lane->work;
+    int* tickets = lane->work + nclass;
+    int* lists = lane->work + 2 * nclass;
     cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)2 * nclass * sizeof(int), st);
     if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemsetAsync(work counters)", e);
     qr_mpc_classify_kernel<<<(batch + 255) / 256, 256, 0, st>>>(A, nclass, counts, lists);
     e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_classify_kernel", e);
-    // largest workspaces first: their instances take longest.  The classes share the scratch; they run one after
-    // the other on the stream.
-    for (int c = nclass - 1; c >= 0; --c) {
+    // largest workspaces first: their instances take longest.  The classes share the lane's scratch; they run one
+    // after the other on the stream.
+    for (int c = nclass - 1; c >= 0 && e == cudaSuccess; --c) {
         A.nfcap = class_cap(c, h);
-        bind_scratch(A, plan[c], A.nfcap, lane);
+        bind_scratch(A, plan[c], A.nfcap, *lane);
         A.list = lists + (size_t)c * batch;
         A.count = counts + c;
         A.next = tickets + c;
         fused_kernel_for(A.nfcap)<<<plan[c].grid, qr_fused_nt(A.nfcap), plan[c].smem, st>>>(A);
         e = cudaGetLastError();
-        if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_fused_kernel", e);
     }
+    release_lane(*lane, st);
+    if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_classify_kernel / qr_mpc_fused_kernel", e);
     return QR_OK;
 }
+}  // namespace
 
 extern "C" int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_options* opt, int batch,
                                       const float* p, const float* v, const float* quat,
@@ -462,8 +628,11 @@ extern "C" int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_option
                                       const float* traj, const float* gait, const float* mu_i,
                                       const float* fmax_i, float* grf_out, float* u_out,
                                       int32_t* status_out, int32_t* iters_out, void* cuda_stream) {
-    return mpc_solve_batch_lane(0, P, opt, batch, p, v, quat, w, r_feet, rpy, traj, gait, mu_i, fmax_i, grf_out, u_out,
-                                status_out, iters_out, cuda_stream);
+    std::lock_guard<std::mutex> lk(g_mu);
+    Ctx* cx = current_ctx();
+    if (!cx) return QR_ECUDA;
+    return mpc_enqueue(*cx, P, opt, batch, p, v, quat, w, r_feet, rpy, traj, gait, mu_i, fmax_i, grf_out, u_out,
+                       status_out, iters_out, (cudaStream_t)cuda_stream);
 }
 
 extern "C" int qr_gpu_mpc_condense_batch(const qr_mpc_params* P, int batch, const float* p,
@@ -472,14 +641,16 @@ extern "C" int qr_gpu_mpc_condense_batch(const qr_mpc_params* P, int batch, cons
                                          const float* gait, const float* fmax_i, float* H_out,
                                          float* g_out, float* ub_out, void* cuda_stream) {
     std::lock_guard<std::mutex> lk(g_mu);
+    Ctx* cx = current_ctx();
+    if (!cx) return QR_ECUDA;
     int rc = check_params(P, batch);
     if (rc) return rc;
     if (batch == 0) return QR_OK;
     if (!p || !v || !quat || !w || !r_feet || !rpy || !traj || !gait || !H_out || !g_out || !ub_out)
         return fail(QR_EINVAL, "null input/output pointer");
-    // the condense-only kernel needs the tables and the staged rows, not the QP workspace
+    // the condense-only kernel needs the tables and the staged rows, not the QP workspace (no lane)
     Plan pl;
-    rc = launch_geometry(qr_mpc_condense_kernel, QR_CLASS_STEP, P->horizon, batch, &pl);
+    rc = launch_geometry(*cx, qr_mpc_condense_kernel, QR_CLASS_STEP, P->horizon, batch, &pl);
     if (rc) return rc;
     if (pl.hsg || pl.kg) return fail(QR_EINVAL, "workspace does not fit in shared memory");
     QrMpcArgs A;
@@ -502,6 +673,8 @@ extern "C" int qr_gpu_qp_solve_batch(int horizon, float mu, const qr_qp_options*
                                      const float* mu_i, float* x_out, double* x_out_f64,
                                      int32_t* status_out, int32_t* iters_out, void* cuda_stream) {
     std::lock_guard<std::mutex> lk(g_mu);
+    Ctx* cx = current_ctx();
+    if (!cx) return QR_ECUDA;
     qr_mpc_params P;
     memset(&P, 0, sizeof(P));
     P.horizon = horizon; P.mu = mu; P.dt = 1.f; P.mass = 1.f;
@@ -509,10 +682,14 @@ extern "C" int qr_gpu_qp_solve_batch(int horizon, float mu, const qr_qp_options*
     if (rc) return rc;
     if (batch == 0) return QR_OK;
     if (!H || !g || !ub || (!x_out && !x_out_f64)) return fail(QR_EINVAL, "null input/output pointer");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
     Plan pl;
-    rc = launch_geometry(qr_qp_solve_kernel, 4 * horizon, horizon, batch, &pl);
+    rc = launch_geometry(*cx, qr_qp_solve_kernel, 4 * horizon, horizon, batch, &pl);
     if (rc) return rc;
-    rc = ensure_scratch_doubles(pl.scratch_doubles(4 * horizon));
+    Lane* lane = nullptr;
+    rc = acquire_lane(*cx, st, &lane);
+    if (rc) return rc;
+    rc = ensure_scratch_doubles(*lane, pl.scratch_doubles(4 * horizon));
     if (rc) return rc;
     QrMpcArgs A;
     memset(&A, 0, sizeof(A));
@@ -523,9 +700,10 @@ extern "C" int qr_gpu_qp_solve_batch(int horizon, float mu, const qr_qp_options*
     A.mu_i = mu_i;
     A.H_in = H; A.g_in = g; A.ub_in = ub;
     A.x_out = x_out; A.x_out_f64 = x_out_f64; A.status_out = status_out; A.iters_out = iters_out;
-    bind_scratch(A, pl, A.nfcap);
-    qr_qp_solve_kernel<<<pl.grid, QR_NT, pl.smem, (cudaStream_t)cuda_stream>>>(A);
+    bind_scratch(A, pl, A.nfcap, *lane);
+    qr_qp_solve_kernel<<<pl.grid, QR_NT, pl.smem, st>>>(A);
     cudaError_t e = cudaGetLastError();
+    release_lane(*lane, st);
     if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_qp_solve_kernel", e);
     return QR_OK;
 }
@@ -536,8 +714,11 @@ extern "C" int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_o
                                            const float* traj, const float* gait, const float* mu_i,
                                            const float* fmax_i, float* grf_out, float* u_out,
                                            int32_t* status_out, int32_t* iters_out) {
+    Ctx* cx = nullptr;
     {
         std::lock_guard<std::mutex> lk(g_mu);
+        cx = current_ctx();
+        if (!cx) return QR_ECUDA;
         int rc = check_params(P, batch);
         if (rc) return rc;
     }
@@ -550,24 +731,16 @@ extern "C" int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_o
     const size_t n_in = B * (3 + 3 + 4 + 3 + 12 + 3 + 12 * h + 4 * h + 2);
     const size_t n_out = B * (12 + (u_out ? 12 * h : 0));
     const size_t bytes = (n_in + n_out) * sizeof(float) + B * 3 * sizeof(int32_t) + 256;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        if (bytes > g_ctx.stage_bytes) {
-            if (g_ctx.stage) cudaFree(g_ctx.stage);
-            g_ctx.stage = nullptr;
-            g_ctx.stage_bytes = 0;
-            cudaError_t e = cudaMalloc(&g_ctx.stage, bytes);
-            if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMalloc(stage)", e);
-            g_ctx.stage_bytes = bytes;
-        }
-    }
-    cudaStream_t st = g_ctx.stream;
-    float* d = reinterpret_cast<float*>(g_ctx.stage);
-    cudaError_t e = cudaSuccess;
     const bool packed = bytes <= (size_t)256 * 1024;
+    SlotHold hold;   // private to this call; drained and released on every return path
+    int rc = acquire_slot(*cx, bytes, packed ? (size_t)256 * 1024 : 0, hold);
+    if (rc) return rc;
+    HostSlot& S = *hold.s;
+    float* d = reinterpret_cast<float*>(S.stage);
+    cudaError_t e = cudaSuccess;
     if (!packed) {
         // Large batches: device row arrays [B][K] in the staging buffer; the batch is cut into (at most) two chunks of
-        // whole rows, each chunk uploaded, solved and downloaded on its own stream with its own scratch lane.  The
+        // whole rows, each chunk uploaded, solved and downloaded on its own stream with its own workspace lane.  The
         // first chunk is small, so the kernels start after a fraction of the upload and the rest of the upload (and
         // the first chunk's download) runs under them; the second chunk's CTAs move onto the SMs as the first
         // chunk's CTAs retire, so the cut costs no tail.
@@ -581,25 +754,23 @@ extern "C" int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_o
         if (u_out) { du = d; d += B * 12 * h; }
         int32_t* dstat = reinterpret_cast<int32_t*>(d);
         int32_t* dit = dstat + B;
-        if (!g_ctx.stream2) {
-            std::lock_guard<std::mutex> lk(g_mu);
-            e = cudaStreamCreateWithFlags(&g_ctx.stream2, cudaStreamNonBlocking);
-            if (e != cudaSuccess) return fail(QR_ECUDA, "cudaStreamCreate", e);
-        }
         const size_t first = B >= 8192 ? B / 8 : B;
         const size_t cut[3] = {0, first, B};
         const int nchunk = first < B ? 2 : 1;
         for (int c = 0; c < nchunk; ++c) {
-            cudaStream_t cs = c == 0 ? g_ctx.stream : g_ctx.stream2;
+            cudaStream_t cs = S.stream[c];
             const size_t b0 = cut[c], nb = cut[c + 1] - cut[c];
             for (const Row& r : rows)
                 if (r.src && e == cudaSuccess)
                     e = cudaMemcpyAsync(r.dev + b0 * r.k, r.src + b0 * r.k, nb * r.k * sizeof(float), cudaMemcpyHostToDevice, cs);
             if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpyAsync H2D", e);
             auto at = [&](const Row& r) -> const float* { return r.src ? r.dev + b0 * r.k : nullptr; };
-            int rc = mpc_solve_batch_lane(c, P, opt, (int)nb, at(rows[0]), at(rows[1]), at(rows[2]), at(rows[3]), at(rows[4]),
-                                          at(rows[5]), at(rows[6]), at(rows[7]), at(rows[8]), at(rows[9]),
-                                          dgrf + b0 * 12, du ? du + b0 * 12 * h : nullptr, dstat + b0, dit + 2 * b0, cs);
+            {
+                std::lock_guard<std::mutex> lk(g_mu);
+                rc = mpc_enqueue(*cx, P, opt, (int)nb, at(rows[0]), at(rows[1]), at(rows[2]), at(rows[3]), at(rows[4]),
+                                 at(rows[5]), at(rows[6]), at(rows[7]), at(rows[8]), at(rows[9]), dgrf + b0 * 12,
+                                 du ? du + b0 * 12 * h : nullptr, dstat + b0, dit + 2 * b0, cs);
+            }
             if (rc) return rc;
             e = cudaMemcpyAsync(grf_out + b0 * 12, dgrf + b0 * 12, nb * 12 * sizeof(float), cudaMemcpyDeviceToHost, cs);
             if (e == cudaSuccess && u_out)
@@ -610,24 +781,19 @@ extern "C" int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_o
                 e = cudaMemcpyAsync(iters_out + 2 * b0, dit + 2 * b0, 2 * nb * sizeof(int32_t), cudaMemcpyDeviceToHost, cs);
             if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpyAsync D2H", e);
         }
-        e = cudaStreamSynchronize(g_ctx.stream);
-        if (e == cudaSuccess && nchunk > 1) e = cudaStreamSynchronize(g_ctx.stream2);
+        e = cudaStreamSynchronize(S.stream[0]);
+        if (e == cudaSuccess && nchunk > 1) e = cudaStreamSynchronize(S.stream[1]);
         if (e != cudaSuccess) return fail(QR_ECUDA, "cudaStreamSynchronize", e);
         return QR_OK;
     }
-    // Small batches (latency path): gather the rows into a pinned mirror of the staging buffer so that
+    // Small batches (latency path): gather the rows into the slot's pinned mirror of the staging buffer so that
     // the whole call is one host->device and one device->host copy.
-    if (!g_ctx.pin) {
-        std::lock_guard<std::mutex> lk(g_mu);
-        e = cudaMallocHost(&g_ctx.pin, (size_t)256 * 1024);
-        if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMallocHost(pinned stage)", e);
-        g_ctx.pin_bytes = (size_t)256 * 1024;
-    }
-    float* hp = reinterpret_cast<float*>(g_ctx.pin);
+    cudaStream_t st = S.stream[0];
+    float* hp = reinterpret_cast<float*>(S.pin);
     auto up = [&](const float* src, size_t cnt) -> float* {
         float* dst = d;
         d += cnt;
-        if (src) memcpy(hp + (dst - reinterpret_cast<float*>(g_ctx.stage)), src, cnt * sizeof(float));
+        if (src) memcpy(hp + (dst - reinterpret_cast<float*>(S.stage)), src, cnt * sizeof(float));
         return src ? dst : nullptr;
     };
     float* dp = up(p, B * 3);
@@ -640,26 +806,76 @@ extern "C" int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_o
     float* dgait = up(gait, B * 4 * h);
     float* dmu = up(mu_i, B);
     float* dfm = up(fmax_i, B);
-    e = cudaMemcpyAsync(g_ctx.stage, g_ctx.pin, n_in * sizeof(float), cudaMemcpyHostToDevice, st);
+    e = cudaMemcpyAsync(S.stage, S.pin, n_in * sizeof(float), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpyAsync H2D", e);
     float* dgrf = d; d += B * 12;
     float* du = nullptr;
     if (u_out) { du = d; d += B * 12 * h; }
     int32_t* dstat = reinterpret_cast<int32_t*>(d);
     int32_t* dit = dstat + B;
-    int rc = qr_gpu_mpc_solve_batch(P, opt, batch, dp, dv, dq, dw, dr, drpy, dtraj, dgait, dmu, dfm, dgrf, du,
-                                    dstat, dit, st);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        rc = mpc_enqueue(*cx, P, opt, batch, dp, dv, dq, dw, dr, drpy, dtraj, dgait, dmu, dfm, dgrf, du, dstat, dit, st);
+    }
     if (rc) return rc;
     const size_t off = n_in * sizeof(float), nout = n_out * sizeof(float) + 3 * B * sizeof(int32_t);
-    e = cudaMemcpyAsync(g_ctx.pin + off, g_ctx.stage + off, nout, cudaMemcpyDeviceToHost, st);
+    e = cudaMemcpyAsync(S.pin + off, S.stage + off, nout, cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpyAsync D2H", e);
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail(QR_ECUDA, "cudaStreamSynchronize", e);
-    const unsigned char* hb = g_ctx.pin;
-    memcpy(grf_out, hb + ((unsigned char*)dgrf - g_ctx.stage), B * 12 * sizeof(float));
-    if (u_out) memcpy(u_out, hb + ((unsigned char*)du - g_ctx.stage), B * 12 * h * sizeof(float));
-    if (status_out) memcpy(status_out, hb + ((unsigned char*)dstat - g_ctx.stage), B * sizeof(int32_t));
-    if (iters_out) memcpy(iters_out, hb + ((unsigned char*)dit - g_ctx.stage), 2 * B * sizeof(int32_t));
+    const unsigned char* hb = S.pin;
+    memcpy(grf_out, hb + ((unsigned char*)dgrf - S.stage), B * 12 * sizeof(float));
+    if (u_out) memcpy(u_out, hb + ((unsigned char*)du - S.stage), B * 12 * h * sizeof(float));
+    if (status_out) memcpy(status_out, hb + ((unsigned char*)dstat - S.stage), B * sizeof(int32_t));
+    if (iters_out) memcpy(iters_out, hb + ((unsigned char*)dit - S.stage), 2 * B * sizeof(int32_t));
+    return QR_OK;
+}
+
+// One batch of host rows sharded over several devices of this process (the reference's seam is the
+// single SolveDenseMPC call of qr_mpc_stance_leg_controller.cpp:385-410): contiguous shards [g*B/G, (g+1)*B/G), one
+// host thread per device running the host entry point above on its shard, results written straight into the
+// caller's arrays (the "final gather" is each shard's own device->host copy).  No collective.
+extern "C" int qr_gpu_mpc_solve_batch_host_multi(int n_devices, const int* devices, const qr_mpc_params* P,
+                                                 const qr_qp_options* opt, int batch, const float* p, const float* v,
+                                                 const float* quat, const float* w, const float* r_feet,
+                                                 const float* rpy, const float* traj, const float* gait,
+                                                 const float* mu_i, const float* fmax_i, float* grf_out, float* u_out,
+                                                 int32_t* status_out, int32_t* iters_out) {
+    if (n_devices < 1 || n_devices > QR_MAX_DEVICES || !devices) return fail(QR_EINVAL, "bad device list");
+    int rc = check_params(P, batch);
+    if (rc) return rc;
+    for (int g = 0; g < n_devices; ++g)
+        for (int k = 0; k < g; ++k)
+            if (devices[k] == devices[g]) return fail(QR_EINVAL, "device listed twice");
+    if (batch == 0) return QR_OK;
+    const int h = P->horizon;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    int codes[QR_MAX_DEVICES];
+    char errs[QR_MAX_DEVICES][320];
+    auto shard = [&](int g) {
+        errs[g][0] = 0;
+        const size_t b0 = (size_t)batch * g / n_devices, b1 = (size_t)batch * (g + 1) / n_devices, nb = b1 - b0;
+        int r = qr_gpu_init(devices[g]);   // binds this thread to the device; creates its context on first use
+        if (r == QR_OK && nb > 0) {
+            auto at = [&](const float* a, size_t k) -> const float* { return a ? a + b0 * k : nullptr; };
+            r = qr_gpu_mpc_solve_batch_host(P, opt, (int)nb, at(p, 3), at(v, 3), at(quat, 4), at(w, 3), at(r_feet, 12),
+                                            at(rpy, 3), at(traj, (size_t)12 * h), at(gait, (size_t)4 * h), at(mu_i, 1),
+                                            at(fmax_i, 1), grf_out + b0 * 12, u_out ? u_out + b0 * 12 * h : nullptr,
+                                            status_out ? status_out + b0 : nullptr, iters_out ? iters_out + 2 * b0 : nullptr);
+        }
+        codes[g] = r;
+        if (r != QR_OK) snprintf(errs[g], sizeof(errs[g]), "device %d: %s", devices[g], t_err);
+    };
+    {
+        std::vector<std::thread> workers;
+        for (int g = 1; g < n_devices; ++g) workers.emplace_back(shard, g);
+        shard(0);
+        for (std::thread& t : workers) t.join();
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    for (int g = 0; g < n_devices; ++g)
+        if (codes[g] != QR_OK) { snprintf(t_err, sizeof(t_err), "%s", errs[g]); return codes[g]; }
     return QR_OK;
 }
 
@@ -702,44 +918,68 @@ __global__ void qr_swing_parabola_kernel(int batch, const float* start, const fl
     if (valid) valid[i] = ok;
 }
 
-QrWbcModelDev* g_wbc_model_dev = nullptr;
-qr_wbc_model g_wbc_model_host;
-bool g_wbc_model_valid = false;
+// Device copy of the robot constants for `model` on this context (g_mu held).  Every distinct model keeps its own
+// buffer (a few robots per process at most), so a batch in flight never sees its constants overwritten; when the
+// table is full the least recently used entry is recycled after the device has drained.
+int wbc_model_on_device(Ctx& cx, const qr_wbc_model* model, const QrWbcModelDev** out) {
+    WbcModelSlot* pick = nullptr;
+    for (WbcModelSlot& m : cx.wbc_models)
+        if (m.valid && memcmp(&m.key, model, sizeof(*model)) == 0) pick = &m;
+    if (!pick) {
+        for (WbcModelSlot& m : cx.wbc_models)
+            if (!m.valid && !pick) pick = &m;
+        if (!pick) {
+            pick = &cx.wbc_models[0];
+            for (WbcModelSlot& m : cx.wbc_models)
+                if (m.stamp < pick->stamp) pick = &m;
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) return fail(QR_ECUDA, "cudaDeviceSynchronize(wbc model)", e);
+            pick->valid = false;
+        }
+        if (!pick->dev) {
+            cudaError_t e = cudaMalloc(&pick->dev, sizeof(QrWbcModelDev));
+            if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMalloc(wbc model)", e);
+        }
+        QrWbcModelDev host;
+        qr_wbc_host::build(model, &host);
+        // synchronous upload into a buffer no launch references yet
+        cudaError_t e = cudaMemcpy(pick->dev, &host, sizeof(host), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpy(wbc model)", e);
+        pick->key = *model;
+        pick->valid = true;
+    }
+    pick->stamp = ++cx.clock;
+    *out = static_cast<const QrWbcModelDev*>(pick->dev);
+    return QR_OK;
+}
 
-int wbc_launch(const qr_wbc_model* model, int batch, const float* state, const float* cmd, const int32_t* contact,
+// g_mu held by the caller.
+int wbc_launch(Ctx& cx, const qr_wbc_model* model, int batch, const float* state, const float* cmd, const int32_t* contact,
                QrWbcArgs& A, void* cuda_stream) {
-    if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
     if (!model || batch < 0) return fail(QR_EINVAL, "null model or negative batch");
     if (batch == 0) return QR_OK;
     if (!state || !cmd || !contact) return fail(QR_EINVAL, "null input pointer");
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    if (!g_wbc_model_dev) {
-        cudaError_t e = cudaMalloc(&g_wbc_model_dev, sizeof(QrWbcModelDev));
-        if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMalloc(wbc model)", e);
-    }
-    if (!g_wbc_model_valid || memcmp(&g_wbc_model_host, model, sizeof(*model)) != 0) {
-        QrWbcModelDev host;
-        qr_wbc_host::build(model, &host);
-        // synchronous upload (the constants change only when the robot model changes)
-        cudaError_t e = cudaMemcpy(g_wbc_model_dev, &host, sizeof(host), cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpy(wbc model)", e);
-        g_wbc_model_host = *model;
-        g_wbc_model_valid = true;
-    }
+    const QrWbcModelDev* dev_model = nullptr;
+    int rc = wbc_model_on_device(cx, model, &dev_model);
+    if (rc) return rc;
     const size_t smem = qr_wbc_smem_bytes();
-    cudaError_t e = cudaFuncSetAttribute(qr_wbc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(QR_ECUDA, "cudaFuncSetAttribute(wbc)", e);
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qr_wbc_kernel, QR_WBC_NT, smem);
-    if (e != cudaSuccess) return fail(QR_ECUDA, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(wbc)", e);
-    int grid = g_ctx.sm_count * (occ < 1 ? 1 : occ);
+    if (!cx.wbc_occ) {
+        cudaError_t e = cudaFuncSetAttribute(qr_wbc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(QR_ECUDA, "cudaFuncSetAttribute(wbc)", e);
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qr_wbc_kernel, QR_WBC_NT, smem);
+        if (e != cudaSuccess) return fail(QR_ECUDA, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(wbc)", e);
+        cx.wbc_occ = occ < 1 ? 1 : occ;
+    }
+    int grid = cx.sm_count * cx.wbc_occ;
     if (grid > batch) grid = batch;
-    A.model = g_wbc_model_dev;
+    A.model = dev_model;
     A.opt = default_options();
     A.batch = batch;
     A.state = state; A.cmd = cmd; A.contact = contact;
     qr_wbc_kernel<<<grid, QR_WBC_NT, smem, st>>>(A);
-    e = cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_wbc_kernel", e);
     return QR_OK;
 }
@@ -750,35 +990,35 @@ extern "C" int qr_gpu_wbc_solve_batch(const qr_wbc_model* model, int batch, cons
                                       const int32_t* contact, float* tau_out, float* fr_out, float* qdes_out,
                                       float* qddes_out, int32_t* status_out, void* cuda_stream) {
     std::lock_guard<std::mutex> lk(g_mu);
+    Ctx* cx = current_ctx();
+    if (!cx) return QR_ECUDA;
     if (batch > 0 && !tau_out) return fail(QR_EINVAL, "null output pointer");
     QrWbcArgs A;
     memset(&A, 0, sizeof(A));
     A.tau32 = tau_out; A.fr32 = fr_out; A.qdes32 = qdes_out; A.qddes32 = qddes_out; A.status = status_out;
-    return wbc_launch(model, batch, state, cmd, contact, A, cuda_stream);
+    return wbc_launch(*cx, model, batch, state, cmd, contact, A, cuda_stream);
 }
 
 extern "C" int qr_gpu_wbc_solve_batch_host(const qr_wbc_model* model, int batch, const float* state, const float* cmd,
                                            const int32_t* contact, float* tau_out, float* fr_out, float* qdes_out,
                                            float* qddes_out, int32_t* status_out) {
-    if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
+    Ctx* cx = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        cx = current_ctx();
+        if (!cx) return QR_ECUDA;
+    }
     if (!model || batch < 0) return fail(QR_EINVAL, "null model or negative batch");
     if (batch == 0) return QR_OK;
     if (!state || !cmd || !contact || !tau_out) return fail(QR_EINVAL, "null pointer");
     const size_t B = (size_t)batch;
     const size_t bytes = B * ((37 + 66 + 4 * 12) * sizeof(float) + 5 * sizeof(int32_t)) + 256;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        if (bytes > g_ctx.stage_bytes) {
-            if (g_ctx.stage) cudaFree(g_ctx.stage);
-            g_ctx.stage = nullptr;
-            g_ctx.stage_bytes = 0;
-            cudaError_t e = cudaMalloc(&g_ctx.stage, bytes);
-            if (e != cudaSuccess) return fail(QR_ENOMEM, "cudaMalloc(stage)", e);
-            g_ctx.stage_bytes = bytes;
-        }
-    }
-    cudaStream_t st = g_ctx.stream;
-    float* d_state = reinterpret_cast<float*>(g_ctx.stage);
+    SlotHold hold;   // private staging slot; drained and released on every return path
+    int rc = acquire_slot(*cx, bytes, 0, hold);
+    if (rc) return rc;
+    HostSlot& S = *hold.s;
+    cudaStream_t st = S.stream[0];
+    float* d_state = reinterpret_cast<float*>(S.stage);
     float* d_cmd = d_state + B * 37;
     float* d_tau = d_cmd + B * 66;
     float* d_fr = d_tau + B * 12;
@@ -790,7 +1030,7 @@ extern "C" int qr_gpu_wbc_solve_batch_host(const qr_wbc_model* model, int batch,
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_cmd, cmd, B * 66 * sizeof(float), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_contact, contact, B * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpyAsync H2D", e);
-    int rc = qr_gpu_wbc_solve_batch(model, batch, d_state, d_cmd, d_contact, d_tau, d_fr, d_qdes, d_qddes, d_status, st);
+    rc = qr_gpu_wbc_solve_batch(model, batch, d_state, d_cmd, d_contact, d_tau, d_fr, d_qdes, d_qddes, d_status, st);
     if (rc) return rc;
     e = cudaMemcpyAsync(tau_out, d_tau, B * 12 * sizeof(float), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && fr_out) e = cudaMemcpyAsync(fr_out, d_fr, B * 12 * sizeof(float), cudaMemcpyDeviceToHost, st);
@@ -807,18 +1047,21 @@ extern "C" int qr_gpu_wbc_solve_batch_f64(const qr_wbc_model* model, int batch, 
                                           const int32_t* contact, double* tau_out, double* fr_out, double* qdes_out,
                                           double* qddes_out, double* dbg_out, int32_t* status_out, void* cuda_stream) {
     std::lock_guard<std::mutex> lk(g_mu);
+    Ctx* cx = current_ctx();
+    if (!cx) return QR_ECUDA;
     if (batch > 0 && !tau_out) return fail(QR_EINVAL, "null output pointer");
     QrWbcArgs A;
     memset(&A, 0, sizeof(A));
     A.tau64 = tau_out; A.fr64 = fr_out; A.qdes64 = qdes_out; A.qddes64 = qddes_out; A.dbg = dbg_out; A.status = status_out;
-    return wbc_launch(model, batch, state, cmd, contact, A, cuda_stream);
+    return wbc_launch(*cx, model, batch, state, cmd, contact, A, cuda_stream);
 }
 
 extern "C" int qr_gpu_swing_parabola_batch(int batch, const float* start, const float* end, const float* height,
                                            const float* phase, int phase_module, float* pos_out, int32_t* valid_out,
                                            void* cuda_stream) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
+    Ctx* cx = current_ctx();
+    if (!cx) return QR_ECUDA;
     if (batch < 0) return fail(QR_EINVAL, "negative batch");
     if (batch == 0) return QR_OK;
     if (!start || !end || !height || !phase || !pos_out) return fail(QR_EINVAL, "null pointer");
@@ -864,7 +1107,8 @@ extern "C" int qr_gpu_mpc_inputs_batch(int horizon, int num_horizon_l, float dt_
                                        const float* traj_init, const float* pos_xy, float* gait_out, float* traj_out,
                                        void* cuda_stream) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
+    Ctx* cx = current_ctx();
+    if (!cx) return QR_ECUDA;
     if (horizon < 1 || horizon > QR_MAX_HORIZON || num_horizon_l < 1 || batch < 0) return fail(QR_EINVAL, "bad size argument");
     if (batch == 0) return QR_OK;
     if (gait_out && (!progress || !duty)) return fail(QR_EINVAL, "contact table needs progress and duty");
@@ -880,7 +1124,8 @@ extern "C" int qr_gpu_mpc_leg_torque_batch(float hip_len, float upper_len, float
                                            const float* q, const float* grf, float* f_ff_out, float* tau_out,
                                            void* cuda_stream) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
+    Ctx* cx = current_ctx();
+    if (!cx) return QR_ECUDA;
     if (batch < 0) return fail(QR_EINVAL, "negative batch");
     if (batch == 0) return QR_OK;
     if (!quat || !q || !grf || !tau_out) return fail(QR_EINVAL, "null pointer");
@@ -908,7 +1153,8 @@ extern "C" int qr_gpu_force_balance_batch(const qr_fb_params* P, int batch, cons
                                           const float* frame, float* force_out, int32_t* status_out, int32_t* iters_out,
                                           void* cuda_stream) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
+    Ctx* cx = current_ctx();
+    if (!cx) return QR_ECUDA;
     if (!P || batch < 0) return fail(QR_EINVAL, "null params or negative batch");
     if (!(P->mass > 0.f) || !(P->mu > 0.f)) return fail(QR_EINVAL, "mass and mu must be positive");
     if (batch == 0) return QR_OK;
@@ -963,7 +1209,8 @@ extern "C" int qr_gpu_swing_bspline_batch(int batch, const float* initial_pos, c
                                           const float* duration, const float* initial_time, const float* time,
                                           float* pos_out, float* vel_out, int32_t* valid_out, void* cuda_stream) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
+    Ctx* cx = current_ctx();
+    if (!cx) return QR_ECUDA;
     if (batch < 0) return fail(QR_EINVAL, "negative batch");
     if (batch == 0) return QR_OK;
     if (!initial_pos || !target_pos || !height || !duration || !initial_time || !time || !pos_out || !vel_out)
@@ -981,7 +1228,8 @@ extern "C" int qr_gpu_foothold_heuristic_batch(const qr_foothold_params* P, int 
                                                const float* swing_remain, const float* norm_phase, const int32_t* allow_switch,
                                                const int32_t* swing_mask, float* foothold_io, float* phase_io, void* cuda_stream) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!g_ctx.ready) return fail(QR_ECUDA, "qr_gpu_init was not called (or no CUDA device)");
+    Ctx* cx = current_ctx();
+    if (!cx) return QR_ECUDA;
     if (!P || batch < 0) return fail(QR_EINVAL, "null params or negative batch");
     if (batch == 0) return QR_OK;
     if (!com_vel || !rpy_rate || !dR || !base_R || !rpy || !foot_base || !des_speed || !des_twist || !des_height ||

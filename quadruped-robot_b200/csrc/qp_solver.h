@@ -497,8 +497,10 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
         }
         QR_SYNC();
         QR_PROF(4);
-        qr_ldl_factor<NT>(W, nbr, 1 QR_PROF_PASS);
-        qr_ldl_backward<NT>(W, nbr, W.dx QR_PROF_PASS);
+        if (nbr > 0) {   // nbr == 0: every foot-step is pinned to the apex, x = p and only the verification is left
+            qr_ldl_factor<NT>(W, nbr, 1 QR_PROF_PASS);
+            qr_ldl_backward<NT>(W, nbr, W.dx QR_PROF_PASS);
+        }
         QR_FOR(f, nf) {
             double x0 = W.ps[3 * f], x1 = W.ps[3 * f + 1], x2 = W.ps[3 * f + 2];
             const int off = W.foff[f], d = W.flag[f];
