@@ -31,6 +31,8 @@ BATCH_PER_GPU = 65536
 N_INPUT_SETS = 4            # 4 x 49 MB of inputs > 126 MB L2: every step reads inputs not resident in L2
 F_ALG_FLOP = 4.38e6         # algorithmic flops per QP at h=10
 HBM_ALG_BYTES = 188 * 4 + 48 + 4   # algorithmic HBM bytes per QP: input rows + 12 forces + status
+F_ALG_FLOP_H30 = 117.2e6    # the same count at h=30
+WBC_F_ALG_FLOP = 0.3e6      # algorithmic flops per WBC tick
 KEYS = ("p", "v", "quat", "w", "r_feet", "rpy", "traj", "gait")
 
 
@@ -100,6 +102,21 @@ class ClockSampler:
 # SetupProblem / SolveMPCKernel / GetMPCSolution.  kind "port" (only if that file is absent): the oracle's
 # float32 restatement + the same qpOASES.
 # ------------------------------------------------------------------------------------------------
+def _preload_reference_libs():
+    """dlopen the reference-compiled libraries in THIS process before the per-core workers are forked, so that the
+    driver's loaded-library record of the bench process shows what the CPU arm runs (the workers inherit the mapping)."""
+    loaded = []
+    for name in ("libqr_mpc_ref.so", "libqr_wbc_ref.so"):
+        path = os.path.join(ROOT, "oracle", "_ref", name)
+        if os.path.exists(path):
+            try:
+                C.CDLL(path)
+                loaded.append(os.path.join("oracle", "_ref", name))
+            except OSError:
+                pass
+    return loaded
+
+
 def _cpu_worker(args):
     core, lo, hi, nwsr, seed = args
     try:
@@ -136,6 +153,7 @@ def cpu_reference_run(per_core: int, nwsr: int = 100, seed: int = 1234):
     except AttributeError:
         cores = list(range(os.cpu_count() or 1))
     jobs = [(c, i * per_core, (i + 1) * per_core, nwsr, seed) for i, c in enumerate(cores)]
+    _preload_reference_libs()
     ctx = mp.get_context("fork")
     t0 = time.perf_counter()
     with ctx.Pool(len(cores)) as pool:
@@ -147,6 +165,61 @@ def cpu_reference_run(per_core: int, nwsr: int = 100, seed: int = 1234):
     return dict(value=total / slowest, cores=len(cores), total=total, seconds=slowest, wall_with_setup=wall_all,
                 p50_ms=float(np.percentile(lat, 50) * 1e3), p99_ms=float(np.percentile(lat, 99) * 1e3),
                 capped=int(sum(r[2] for r in res)), nwsr=nwsr, kind=res[0][3])
+
+
+def _cpu_leg_worker(args):
+    """One pinned worker of a CPU leg: kind in {"wbc", "tick", "mixed", "h30"}; returns (seconds, count, label)."""
+    kind, core, per_core, seed = args
+    try:
+        os.sched_setaffinity(0, {core})
+    except (AttributeError, OSError):
+        pass
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import _pkg
+    import oracle as O
+    pkg = _pkg.load()
+    if kind == "wbc":
+        wb = pkg.synth.make_wbc_batch("lite3", per_core, seed=seed + core)
+        sec, _, _ = O.ref_wbc_time_batch(O.wbc_model_of(wb["robot"]), wb["state"], wb["cmd"], wb["contact"])
+        return sec, per_core, "reference"
+    if kind == "tick":
+        # one control tick per robot: SolveMPCKernel + GetMPCSolution, then the WBC tick fed with the MPC forces
+        mb = pkg.synth.make_mpc_batch("lite3", 10, 0.03, per_core, seed=seed + core, gait="trot")
+        wb = pkg.synth.make_wbc_batch("lite3", per_core, seed=seed + 100 + core)
+        P = O.params_of(mb["robot"], 10, 0.03)
+        sec, _, x12 = O.ref_mpc_time_batch(P, mb, 0, per_core, want_x=True)
+        wb["cmd"][:, 51:63] = x12.astype(np.float32)
+        sec2, _, _ = O.ref_wbc_time_batch(O.wbc_model_of(wb["robot"]), wb["state"], wb["cmd"], wb["contact"])
+        return sec + sec2, per_core, "reference"
+    if kind == "mixed":
+        mb = pkg.synth.make_mpc_batch("aliengo", 10, 0.03, per_core, seed=seed + core, gait="mixed")
+        P = O.params_of(mb["robot"], 10, 0.03)
+        sec, _, _ = O.ref_mpc_time_batch(P, mb, 0, per_core)
+        return sec, per_core, "reference"
+    if kind == "h30":
+        # beyond the reference's own K_MAX_GAIT_SEGMENTS = 16: the oracle's restatement + the reference's qpOASES, converged
+        mb = pkg.synth.make_mpc_batch("a1", 30, 0.03, per_core, seed=seed + core, gait="trot")
+        P = O.params_of(mb["robot"], 30, 0.03)
+        sec, _, _, _ = O.mpc_time_batch(P, mb, 0, per_core, 100000)
+        return sec, per_core, "port"
+    raise ValueError(kind)
+
+
+def cpu_leg(kind: str, per_core: int, seed: int = 4321):
+    """A bounded CPU sample of one of the side workloads on all host cores (one pinned process per core)."""
+    import multiprocessing as mp
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = list(range(os.cpu_count() or 1))
+    _preload_reference_libs()
+    with mp.get_context("fork").Pool(len(cores)) as pool:
+        res = pool.map(_cpu_leg_worker, [(kind, c, per_core, seed) for c in cores])
+    slowest = max(r[0] for r in res)
+    total = sum(r[1] for r in res)
+    return {"value": total / slowest, "cores": len(cores), "kind": res[0][2],
+            "sample": f"{total} units ({per_core} per core, {slowest:.2f} s on the slowest core), one pinned process per core",
+            "eigen": "oracle/mini_eigen (plain loops, not vectorised) in place of Eigen"}
 
 
 def run_reference(args, rank, world):
@@ -170,7 +243,10 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "A1 convex MPC h=10 dt=0.03 trot (reference CPU solver, bounded sample per step)"},
         "cpu_baseline": {"value": value, "unit": "QP/s", "cores": last["cores"], "kind": last["kind"], "sample": sample,
-                         "p50_ms": last["p50_ms"], "p99_ms": last["p99_ms"]},
+                         "p50_ms": last["p50_ms"], "p99_ms": last["p99_ms"],
+                         "eigen": "oracle/mini_eigen (plain loops, not vectorised) in place of Eigen: the condensing part "
+                                  "(about 5 % of a solve) runs slower than a real Eigen build would",
+                         "native_libs": _preload_reference_libs()},
         "e2e": {"value": value, "unit": "QP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -193,7 +269,7 @@ def _time_ms(torch, fn, reps, warm=3):
     return e0.elapsed_time(e1) / reps
 
 
-def bench_wbc_and_full_step(pkg, capi, torch, stream):
+def bench_wbc_and_full_step(pkg, capi, torch, stream, with_cpu=False, fp64_peak=None):
     """Reported beside the headline metric: qr_wbc_kernel throughput (Lite3, batches 1024 and 65536) and one full
     control tick of BASELINE configs[1] (Lite3 trot: contact table + reference trajectory -> MPC -> leg torques,
     swing-foot parabola, WBIC with the MPC forces as Fr_des), batch 1024, all resident on the device."""
@@ -208,6 +284,18 @@ def bench_wbc_and_full_step(pkg, capi, torch, stream):
         st = torch.empty(B, dtype=torch.int32, device="cuda")
         ms = _time_ms(torch, lambda: capi.wbc_solve_batch_device(M, state, cmd, contact, tau, stream, status=st), 10)
         out["wbc"][f"batch_{B}"] = {"value": B / ms * 1e3, "ms_per_step": ms, "status_nonzero": int((st != 0).sum())}
+    # roofline of qr_wbc_kernel: FP64 FMA pipe, algorithmic 0.3 MFLOP per robot, batch 65536
+    wbc_tf = out["wbc"]["batch_65536"]["value"] * WBC_F_ALG_FLOP / 1e12
+    out["wbc"]["roofline"] = {"bound": "fp64_fma", "kernel": "qr_wbc_kernel", "achieved": wbc_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                              "frac": (wbc_tf / fp64_peak) if fp64_peak else None, "algorithmic_flop_per_robot": WBC_F_ALG_FLOP,
+                              "hbm_algorithmic_bytes_per_robot": (37 + 66 + 4 + 12 + 1) * 4}
+    if with_cpu:
+        c = cpu_leg("wbc", 2048)
+        c["unit"] = "robots/s"
+        c["what"] = ("the reference's own FloatingBaseModel / qrSingleContact / task_set / qrMultitaskProjection / "
+                     "qrWholeBodyImpulseCtrl + QuadProg++ compiled from /root/reference (oracle/_ref/libqr_wbc_ref.so), "
+                     "controller objects built once, one recomputing tick per robot (qr_wbc_locomotion_controller.cpp:108-134)")
+        out["wbc"]["cpu_baseline"] = c
     # full tick, batch 1024
     B, h, dt = 1024, 10, 0.03
     mb = pkg.synth.make_mpc_batch("lite3", h, dt, B, seed=11, gait="trot")
@@ -247,6 +335,11 @@ def bench_wbc_and_full_step(pkg, capi, torch, stream):
                                     "swing parabola, WBIC (BASELINE configs[1]), batch 1024 on the device",
                         "value": B / ms * 1e3, "unit": "robot ticks/s", "ms_per_step": ms,
                         "mpc_not_converged": int((o["status"] != 0).sum()), "wbc_status_nonzero": int((st != 0).sum())}
+    if with_cpu:
+        c = cpu_leg("tick", 32)
+        c["unit"] = "robot ticks/s"
+        c["what"] = "reference MPC source build (SolveMPCKernel + GetMPCSolution, stock nWSR=100) followed by the reference WBC source build, per robot"
+        out["full_step"]["cpu_baseline"] = c
     # BASELINE configs[3]: Aliengo, gait drawn per instance (trot / walk / gallop: different contact masks and numbers of
     # eliminated swing variables -> several size classes in one call), batch 16384
     B, h, dt = 16384, 10, 0.03
@@ -262,6 +355,11 @@ def bench_wbc_and_full_step(pkg, capi, torch, stream):
                          "not_converged": int((om["status"] != 0).sum()),
                          "stance_footsteps_min_mean_max": [int(nf.min()), float(nf.mean()), int(nf.max())],
                          "rounds_mean": float(om["iters"][:, 1].float().mean())}
+    if with_cpu:
+        c = cpu_leg("mixed", 48)
+        c["unit"] = "QP/s"
+        c["what"] = "reference MPC source build on Aliengo mixed-gait instances, stock nWSR=100"
+        out["mixed_gait"]["cpu_baseline"] = c
     # BASELINE configs[4]: horizon-30 long-preview MPC (360 variables), batch 4096, A1 trot
     B, h, dt = 4096, 30, 0.03
     mb = pkg.synth.make_mpc_batch("a1", h, dt, B, seed=14, gait="trot")
@@ -275,6 +373,15 @@ def bench_wbc_and_full_step(pkg, capi, torch, stream):
                         "value": B / ms * 1e3, "unit": "QP/s", "ms_per_step": ms,
                         "not_converged": int((o30["status"] != 0).sum()),
                         "rounds_mean": float(o30["iters"][:, 1].float().mean())}
+    tf30 = out["horizon30"]["value"] * F_ALG_FLOP_H30 / 1e12
+    out["horizon30"]["roofline"] = {"bound": "fp64_fma", "achieved": tf30, "peak": fp64_peak, "unit": "TFLOP/s",
+                                    "frac": (tf30 / fp64_peak) if fp64_peak else None, "algorithmic_flop_per_qp": F_ALG_FLOP_H30}
+    if with_cpu:
+        c = cpu_leg("h30", 3)
+        c["unit"] = "QP/s"
+        c["what"] = ("h = 30 is beyond the reference's own arrays (K_MAX_GAIT_SEGMENTS = 16): the oracle's float32 restatement of "
+                     "qr_mpc_interface.cpp + the reference's qpOASES 3.2.0 run to convergence")
+        out["horizon30"]["cpu_baseline"] = c
     return out
 
 
@@ -375,6 +482,55 @@ def run_gpu(args, rank, local_rank, world):
     h2d = B * sum(sets_host[0][k].shape[1] for k in KEYS) * 4
     d2h = B * (12 * 4 + 4)
 
+    # ---- strong scaling (BASELINE configs[2]: "batch 65536 sharded across 8 B200"): the SAME 65536 instances cut into
+    # contiguous shards, one per GPU, and the forces gathered.  Under torchrun every rank solves its shard on the device
+    # and one ncclAllGather of 12*B/G floats per rank assembles the result on every GPU (inside the timed region).
+    # In a single process that sees several GPUs the library's own qr_gpu_mpc_solve_batch_host_multi is timed instead
+    # (host rows in, one host thread per GPU, results gathered into one host array).
+    strong = None
+    if world > 1:
+        Bs = BATCH_PER_GPU // world
+        full = pkg.synth.make_mpc_batch(ROBOT, h, DT_MPC, BATCH_PER_GPU, seed=777, gait=GAIT)
+        shard = {k: torch.from_numpy(np.ascontiguousarray(full[k][rank * Bs:(rank + 1) * Bs])).cuda() for k in KEYS}
+        o_s = dict(grf=torch.empty((Bs, 12), device="cuda"), status=torch.empty(Bs, dtype=torch.int32, device="cuda"))
+        gathered = torch.empty((world * Bs, 12), device="cuda")
+
+        def strong_step():
+            capi.mpc_solve_batch_device(P, shard, o_s, stream)
+            dist.all_gather_into_tensor(gathered, o_s["grf"])
+
+        for _ in range(3):
+            strong_step()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            strong_step()
+        s1.record()
+        barrier()
+        ts = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        ms = float(ts.item()) / args.steps
+        strong = {"workload": f"A1 h={h} trot, {world * Bs} instances in total, {Bs} per GPU, forces all-gathered (NCCL) every step",
+                  "value": world * Bs / ms * 1e3, "unit": "QP/s", "ms_per_step": ms, "n_gpus": world, "scaling": "strong",
+                  "not_converged": int((o_s["status"] != 0).sum())}
+    elif torch.cuda.device_count() > 1:
+        G = torch.cuda.device_count()
+        pb = pinned[0]
+        host_rows = {k: pb[k] for k in KEYS}
+        res = {"grf": grf_pin.numpy(), "status": st_pin.numpy()}
+        for _ in range(2):
+            capi.mpc_solve_batch_host_multi(P, host_rows, list(range(G)), want_info=True, out=res)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            capi.mpc_solve_batch_host_multi(P, host_rows, list(range(G)), want_info=True, out=res)
+        ms = (time.perf_counter() - t0) / args.steps * 1e3
+        torch.cuda.set_device(local_rank)
+        strong = {"workload": f"A1 h={h} trot, {B} instances in one host batch sharded over {G} GPUs of this process by "
+                              "qr_gpu_mpc_solve_batch_host_multi (pinned host rows in, forces gathered into one host array)",
+                  "value": B / ms * 1e3, "unit": "QP/s", "ms_per_step": ms, "n_gpus": G, "scaling": "strong",
+                  "not_converged": int((res["status"] != 0).sum())}
+
     # ---- batch-1 latency (rank 0): p50 / p99 of a synchronous host-API call
     lat = None
     if rank == 0:
@@ -396,9 +552,19 @@ def run_gpu(args, rank, local_rank, world):
 
     # ---- the other half of the hot path (rank 0, N = 1): the WBC kernel alone and BASELINE configs[1], one full
     # MPC + WBIC tick for a batch of robots, everything on the device
+    peaks = {}
+    if rank == 0:
+        try:
+            pl = C.CDLL(qbuild.PEAKS_LIB)
+            f64, f32 = C.c_double(), C.c_double()
+            if pl.qr_peak_fma(C.byref(f64), C.byref(f32)) == 0:
+                peaks = {"fp64_fma_tflops": f64.value, "fp32_fma_tflops": f32.value}
+        except OSError:
+            pass
     extra = None
     if rank == 0 and world == 1:
-        extra = bench_wbc_and_full_step(pkg, capi, torch, stream)
+        extra = bench_wbc_and_full_step(pkg, capi, torch, stream, with_cpu=not args.no_cpu_baseline,
+                                        fp64_peak=peaks.get("fp64_fma_tflops"))
 
     if rank != 0:
         if world > 1:
@@ -407,14 +573,6 @@ def run_gpu(args, rank, local_rank, world):
 
     # ---- roofline of the one kernel in the step (FMA pipe: SURVEY.md section 8d), HBM figures beside it
     kern_s = float(np.mean(kern_ms)) * 1e-3
-    peaks = {}
-    try:
-        pl = C.CDLL(qbuild.PEAKS_LIB)
-        f64, f32 = C.c_double(), C.c_double()
-        if pl.qr_peak_fma(C.byref(f64), C.byref(f32)) == 0:
-            peaks = {"fp64_fma_tflops": f64.value, "fp32_fma_tflops": f32.value}
-    except OSError:
-        pass
     mp_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak, hbm_src = 6650.0, "fallback"
     if os.path.exists(mp_path):
@@ -424,16 +582,18 @@ def run_gpu(args, rank, local_rank, world):
             pass
     achieved_tf = B * F_ALG_FLOP / kern_s / 1e12
     fp64_peak = peaks.get("fp64_fma_tflops")
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
         except ValueError:
             pass
     roofline = {
         "bound": "fp64_fma", "kernel": "qr_mpc_fused_kernel", "achieved": achieved_tf, "peak": fp64_peak,
         "unit": "TFLOP/s", "frac": (achieved_tf / fp64_peak) if fp64_peak else None, "traffic": traffic,
+        "traffic_source": traffic_src,
         "peak_source": "FP64 DFMA chain microbenchmark run in this process (csrc/peaks.cu); not in MEASURED_PEAKS.json",
         "algorithmic_flop_per_qp": F_ALG_FLOP, "kernel_ms": kern_s * 1e3, "fp32_fma_peak_tflops": peaks.get("fp32_fma_tflops"),
         "hbm": {"achieved": B * HBM_ALG_BYTES / kern_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -442,13 +602,31 @@ def run_gpu(args, rank, local_rank, world):
     }
 
     cpu = None
+    parity_rec = None
     if world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         r = cpu_reference_run(96)
         cpu = {"value": r["value"], "unit": "QP/s", "cores": r["cores"], "kind": r["kind"],
                "sample": (f"{r['total']} A1 h=10 trot QPs ({r['seconds']:.1f} s, 96 per core), cold QProblem + init per QP, "
                           f"stock nWSR=100, {_kind_text(r['kind'])}, one pinned process per core"),
-               "p50_ms": r["p50_ms"], "p99_ms": r["p99_ms"]}
+               "p50_ms": r["p50_ms"], "p99_ms": r["p99_ms"],
+               "eigen": "oracle/mini_eigen (plain loops, not vectorised) in place of Eigen: the condensing part (about 5 % "
+                        "of a solve) runs slower than a real Eigen build would"}
+        # parity of this run's GPU forces on a sample of the timed workload, checked by the same CPU leg: element-wise
+        # against the certified exact optimum of the reference's QP (converged qpOASES + extended-precision KKT solve)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import bulk
+        n_par = 1024
+        sub = {k: (np.ascontiguousarray(v[:n_par]) if isinstance(v, np.ndarray) and v.shape[:1] == (B,) else v)
+               for k, v in sets_host[0].items()}
+        gsub = capi.mpc_solve_batch_host(P, sub, want_u=True)
+        osub = bulk.run(sub, h, DT_MPC, np.arange(n_par))
+        eot = bulk.err_over_tol(gsub["u"], osub["x_star"]).max(axis=1)
+        parity_rec = {"n": n_par, "worst_err_over_tol": float(eot.max()), "n_fail": int((eot > 1.0).sum()),
+                      "tolerance": "|f - x*| <= 1e-4 |x*| + 1e-5 element-wise over all 12h forces; x* = certified exact optimum "
+                                   "of the reference's QP (oracle build -> converged qpOASES -> extended-precision KKT solve)",
+                      "qpoases_worst_err_over_tol": float(bulk.err_over_tol(osub["x_conv"], osub["x_star"]).max()),
+                      "status_nonzero": int((gsub["status"] != 0).sum())}
 
     n_size_classes = (4 * h + 7) // 8
     occ = capi.occupancy(h, int(round(float((sets_host[0]['gait'] > 0).sum(axis=1).mean()))))
@@ -468,7 +646,9 @@ def run_gpu(args, rank, local_rank, world):
         "gpu_launches": args.steps * (1 + n_size_classes),   # per step: qr_mpc_classify_kernel + one qr_mpc_fused_kernel per size class
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "parity": parity_rec,
         "latency": lat,
+        "strong": strong,
     }
     if extra:
         line.update(extra)

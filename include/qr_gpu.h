@@ -118,6 +118,27 @@ int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_options* opt
                                 float* grf_out, float* u_out, int32_t* status_out,
                                 int32_t* iters_out);
 
+/* Fused post-processing of the first 12 forces, done by the solve kernel itself while the instance's rows are still in
+ * shared memory (qr_gpu_mpc_solve_batch_ex): what SolveDenseMPC and GetAction do after GetMPCSolution
+ * (qr_mpc_stance_leg_controller.cpp:402-409, 139-141): f_ff = -R_base^T f (the force the leg exerts, base frame),
+ * tau_leg = J_leg^T f_ff (qrRobot::MapContactForceToJointTorques, src/robots/qr_robot.cpp:241-251, analytic Jacobian
+ * :148-172) and wbcData.Fr_des = f. */
+typedef struct {
+    float hip_len, upper_len, lower_len;
+    const float* q;       /* [batch][12] motor angles (needed for f_ff_out / tau_out) */
+    float* f_ff_out;      /* [batch][12] or NULL */
+    float* tau_out;       /* [batch][12] or NULL */
+    float* wbc_cmd_io;    /* [batch][66] qrWbcCtrlData rows of qr_gpu_wbc_solve_batch, or NULL: Fr_des (entries 51..62) is written */
+} qr_mpc_epilogue;
+
+/* qr_gpu_mpc_solve_batch with the epilogue above (epilogue may be NULL: identical to qr_gpu_mpc_solve_batch). */
+int qr_gpu_mpc_solve_batch_ex(const qr_mpc_params* P, const qr_qp_options* opt, int batch,
+                              const float* p, const float* v, const float* quat, const float* w,
+                              const float* r_feet, const float* rpy, const float* traj,
+                              const float* gait, const float* mu_i, const float* fmax_i,
+                              float* grf_out, float* u_out, int32_t* status_out, int32_t* iters_out,
+                              const qr_mpc_epilogue* epilogue, void* cuda_stream);
+
 /* The same host-buffer call sharded over several GPUs of this process (BASELINE.json configs[2]: "batch 65536
  * sharded across 8 B200"; the reference's seam is the single SolveDenseMPC call,
  * qr_mpc_stance_leg_controller.cpp:385-410).  The batch is cut into contiguous shards [g*B/G, (g+1)*B/G), one per
@@ -172,6 +193,71 @@ int qr_gpu_mpc_inputs_batch(int horizon, int num_horizon_l, float dt_mpc, int ba
  *   f_ff_out [batch][12] or NULL, tau_out [batch][12] */
 int qr_gpu_mpc_leg_torque_batch(float hip_len, float upper_len, float lower_len, int batch, const float* quat,
                                 const float* q, const float* grf, float* f_ff_out, float* tau_out, void* cuda_stream);
+
+/* qr_gpu_mpc_lever_arms_batch -- the r_feet rows of qr_gpu_mpc_solve_batch from what the controller holds:
+ * foot2ComInWorldFrame = baseRMat * (footPosInBaseFrame.colwise() - comOffset)  (SolveDenseMPC,
+ * qr_mpc_stance_leg_controller.cpp:396; baseRMat = quaternionToRotationMatrix(q)^T, src/robots/qr_robot.cpp:70).
+ *   quat [batch][4] (w,x,y,z), foot_base [batch][12] (3x4 column-major), com_offset [3] HOST values, r_feet_out [batch][12] */
+int qr_gpu_mpc_lever_arms_batch(int batch, const float* quat, const float* foot_base, const float* com_offset,
+                                float* r_feet_out, void* cuda_stream);
+
+/* Leg geometry of qrRobot: hipLength, upperLegLength, lowerLegLength and hipOffset (3x4, column-major m[3*leg + axis]). */
+typedef struct {
+    float hip_len, upper_len, lower_len;
+    float hip_offset[12];
+} qr_leg_geometry;
+
+/* qr_gpu_leg_kinematics_batch -- replaces qrRobot::FootPositionsInBaseFrame / FootPositionInHipFrame, ComputeJacobian /
+ * AnalyticalLegJacobian and ComputeFootVelocitiesInBaseFrame (src/robots/qr_robot.cpp:125-197, 230-236) for `batch`
+ * robots.  q, qd [batch][12]; foot_base_out [batch][12] (3x4 column-major), jac_out [batch][4][9] row-major,
+ * foot_vel_out [batch][12]; any output may be NULL (qd may be NULL when foot_vel_out is). */
+int qr_gpu_leg_kinematics_batch(const qr_leg_geometry* geom, int batch, const float* q, const float* qd,
+                                float* foot_base_out, float* jac_out, float* foot_vel_out, void* cuda_stream);
+
+/* qr_gpu_leg_ik_batch -- replaces qrRobot::ComputeMotorAnglesFromFootLocalPosition (FootPositionInHipFrameToJointAngle)
+ * and ComputeMotorVelocityFromFootLocalVelocity (src/robots/qr_robot.cpp:106-122, 200-218).  foot_base [batch][12] foot
+ * positions in the base frame, foot_vel [batch][12] or NULL, leg_mask [batch][4] or NULL (0: leave that leg's outputs
+ * untouched); q_out [batch][12], qd_out [batch][12] or NULL. */
+int qr_gpu_leg_ik_batch(const qr_leg_geometry* geom, int batch, const float* foot_base, const float* foot_vel,
+                        const int32_t* leg_mask, float* q_out, float* qd_out, void* cuda_stream);
+
+/* qr_gpu_swing_targets_batch -- replaces the MPC-mode (LocomotionMode::ADVANCED_TROT) branch of
+ * qrRaibertSwingLegController::GetAction (src/controllers/qr_swing_leg_controller.cpp:361-409) and its joint targets
+ * (:407-410) for the swing legs of `batch` robots: parabola from the lift-off position to the planned foothold
+ * (SwingFootTrajectory, height 0.1), and the pFoot_des / vFoot_des / aFoot_des rows of qrWbcCtrlData written straight
+ * into the WBC command rows qr_gpu_wbc_solve_batch reads.
+ *   base_pos [batch][3], quat [batch][4], v_world [batch][3]  robot->basePosition, GetBaseOrientation(), baseVInWorldFrame
+ *   foothold [batch][12]      footholdPlanner->desiredFootholds (output of qr_gpu_foothold_heuristic_batch)
+ *   planner_phase [batch][4]  footholdPlanner->phase;  switch_pos [batch][12] phaseSwitchFootGlobalPos
+ *   swing_duration [batch][4] gaitGenerator->swingDuration;  swing_mask [batch][4] int32
+ *   horizontal_terrain        != 0: robotBaseR is the identity (:262-265)
+ *   wbc_cmd_io [batch][66]    entries 15+3*leg.., 27+3*leg.., 39+3*leg.. of the swing legs are written
+ *   foot_base_des_out, q_des_out, qd_des_out [batch][12] or NULL; valid_out [batch][4] or NULL (0: stance leg, or the
+ *   trajectory generator rejected the phase and nothing was written) */
+int qr_gpu_swing_targets_batch(const qr_leg_geometry* geom, int batch, const float* base_pos, const float* quat,
+                               const float* v_world, const float* foothold, const float* planner_phase,
+                               const float* switch_pos, const float* swing_duration, const int32_t* swing_mask,
+                               int horizontal_terrain, float* wbc_cmd_io, float* foot_base_des_out, float* q_des_out,
+                               float* qd_des_out, int32_t* valid_out, void* cuda_stream);
+
+/* qr_gpu_gait_update_batch -- replaces qrOpenLoopGaitGenerator::Update + Schedule
+ * (src/gait/qr_openloop_gait_generator.cpp:126-247) for `batch` robots, one call per control tick, on caller-held state:
+ *   time [batch]         currentTime
+ *   cfg [batch][20]      per leg: initialLegPhase, fullCyclePeriod, initStateRadioInCycle, swingDuration, dutyFactor
+ *   contacts [batch][4]  robot->GetFootContact();  stop [batch] or NULL  robot->stop;  advanced_trot: gait == "advanced_trot"
+ *   istate_io [batch][20] curLegState[4], lastLegState[4], desiredLegState[4], legState[4], firstSwing | firstStance << 1
+ *                         (LegState values of config/qr_enum_types.h:62-68)
+ *   fstate_io [batch][4]  resetTime, lastTime, cumDt, waitTime
+ *   phase_full_io, norm_phase_io, swing_remain_io [batch][4]  phaseInFullCycle, normalizedPhase, swingTimeRemaining -- the
+ *                         rows qr_gpu_mpc_inputs_batch (progress) and qr_gpu_foothold_heuristic_batch read
+ *   allow_out [batch][4] or NULL  allowSwitchLegState
+ *   early_out [batch][4] or NULL  legState == EARLY_CONTACT (the early_contact rows of qr_gpu_mpc_inputs_batch)
+ *   swing_mask_out [batch][4] or NULL  the legs the swing-leg controller moves this tick (swingFootIds,
+ *                         src/controllers/qr_swing_leg_controller.cpp:218-228) */
+int qr_gpu_gait_update_batch(int batch, const float* time, const float* cfg, float contact_threshold,
+                             const int32_t* contacts, const int32_t* stop, int advanced_trot, int32_t* istate_io,
+                             float* fstate_io, float* phase_full_io, float* norm_phase_io, float* swing_remain_io,
+                             int32_t* allow_out, int32_t* early_out, int32_t* swing_mask_out, void* cuda_stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Whole-body control

@@ -67,6 +67,12 @@ struct traits<DiagonalView<M>> {
 
 template <class XprType>
 class CommaInitializer;
+template <class M>
+class ColwiseProxy;
+template <class M>
+class RowwiseProxy;
+template <class M>
+class QrSolveProxy;
 
 // ------------------------------------------------------------------------------------------------
 // Read-side interface shared by matrices and views.
@@ -283,6 +289,40 @@ public:
     template <class O>
     CommaInitializer<Derived> operator<<(const MatrixBase<O>& o);
 
+    // Coefficient-wise helpers, casts and broadcasting views used by the controller sources (robots/qr_robot.cpp,
+    // planner/qr_foothold_planner.cpp, gait/qr_openloop_gait_generator.cpp, controllers/mpc/qr_mpc_stance_leg_controller.cpp).
+    Scalar x() const { return coeff(0); }
+    Scalar y() const { return coeff(1); }
+    Scalar z() const { return coeff(2); }
+    Scalar& x() { return coeffRef(0); }
+    Scalar& y() { return coeffRef(1); }
+    Scalar& z() { return coeffRef(2); }
+    Derived& setOnes() { return setConstant(Scalar(1)); }
+    template <class T>
+    Matrix<T, RowsAtCompileTime, ColsAtCompileTime> cast() const {
+        Matrix<T, RowsAtCompileTime, ColsAtCompileTime> out(rows(), cols());
+        for (int j = 0; j < cols(); ++j)
+            for (int i = 0; i < rows(); ++i) out.coeffRef(i, j) = T(coeff(i, j));
+        return out;
+    }
+    template <class O>
+    PlainObject cwiseProduct(const MatrixBase<O>& o) const {
+        PlainObject out(rows(), cols());
+        for (int j = 0; j < cols(); ++j)
+            for (int i = 0; i < rows(); ++i) out.coeffRef(i, j) = coeff(i, j) * o.coeff(i, j);
+        return out;
+    }
+    template <class O>
+    PlainObject cwiseQuotient(const MatrixBase<O>& o) const {
+        PlainObject out(rows(), cols());
+        for (int j = 0; j < cols(); ++j)
+            for (int i = 0; i < rows(); ++i) out.coeffRef(i, j) = coeff(i, j) / o.coeff(i, j);
+        return out;
+    }
+    ColwiseProxy<const Derived> colwise() const { return ColwiseProxy<const Derived>(derived()); }
+    RowwiseProxy<const Derived> rowwise() const { return RowwiseProxy<const Derived>(derived()); }
+    QrSolveProxy<Derived> colPivHouseholderQr() const { return QrSolveProxy<Derived>(derived()); }
+
     // Closed-form inverse of a 3x3 / general Gauss-Jordan otherwise (cofactors over the determinant).
     PlainObject inverse() const;
     // Scaling-and-squaring Pade exponential (unsupported/Eigen/MatrixFunctions), see mini_eigen_expm.h.
@@ -364,6 +404,10 @@ public:
     void assign(const MatrixBase<O>& o) {
         if (Rows_ == Dynamic || Cols_ == Dynamic) {
             if (rows() != o.rows() || cols() != o.cols()) st.resize(o.rows(), o.cols());
+        } else if ((Rows_ == 1 || Cols_ == 1) && o.rows() == Cols_ && o.cols() == Rows_ && Rows_ != Cols_) {
+            // Eigen transposes implicitly when a row vector is assigned to a column vector (and vice versa)
+            for (int k = 0; k < Rows_ * Cols_; ++k) st.data()[k] = o.coeff(k);
+            return;
         } else {
             assert(o.rows() == Rows_ && o.cols() == Cols_);
         }
@@ -452,8 +496,13 @@ public:
     using Base::coeffRef;
     template <class O>
     Block& operator=(const MatrixBase<O>& o) {
-        assert(o.rows() == nr && o.cols() == nc);
         typename MatrixBase<O>::PlainObject t = o.eval();   // the source may alias this view
+        if ((nr == 1 || nc == 1) && o.rows() == nc && o.cols() == nr && nr != nc) {
+            // Eigen transposes implicitly when a column vector is assigned to a row view (and vice versa)
+            for (int k = 0; k < nr * nc; ++k) coeffRef(nc == 1 ? k : 0, nc == 1 ? 0 : k) = t.coeff(k);
+            return *this;
+        }
+        assert(o.rows() == nr && o.cols() == nc);
         for (int j = 0; j < nc; ++j)
             for (int i = 0; i < nr; ++i) coeffRef(i, j) = t.coeff(i, j);
         return *this;
@@ -651,6 +700,64 @@ typename MatrixBase<D>::PlainObject MatrixBase<D>::inverse() const {
     return out;
 }
 
+// `m.colwise() - v` / `m.colwise() + v` (v broadcast over the columns), `m.rowwise().sum()`, and
+// `A.colPivHouseholderQr().solve(b)` (here: Gaussian elimination with partial pivoting).
+template <class M>
+class ColwiseProxy {
+    const M& m;
+
+public:
+    typedef typename traits<M>::Scalar Scalar;
+    typedef Matrix<Scalar, traits<M>::Rows, traits<M>::Cols> Plain;
+    explicit ColwiseProxy(const M& mm) : m(mm) {}
+    template <class O>
+    Plain operator-(const MatrixBase<O>& v) const {
+        Plain out(m.rows(), m.cols());
+        for (int j = 0; j < m.cols(); ++j)
+            for (int i = 0; i < m.rows(); ++i) out.coeffRef(i, j) = m.coeff(i, j) - v.coeff(i);
+        return out;
+    }
+    template <class O>
+    Plain operator+(const MatrixBase<O>& v) const {
+        Plain out(m.rows(), m.cols());
+        for (int j = 0; j < m.cols(); ++j)
+            for (int i = 0; i < m.rows(); ++i) out.coeffRef(i, j) = m.coeff(i, j) + v.coeff(i);
+        return out;
+    }
+};
+template <class M>
+class RowwiseProxy {
+    const M& m;
+
+public:
+    typedef typename traits<M>::Scalar Scalar;
+    explicit RowwiseProxy(const M& mm) : m(mm) {}
+    Matrix<Scalar, traits<M>::Rows, 1> sum() const {
+        Matrix<Scalar, traits<M>::Rows, 1> out(m.rows(), 1);
+        for (int i = 0; i < m.rows(); ++i) {
+            Scalar s = 0;
+            for (int j = 0; j < m.cols(); ++j) s += m.coeff(i, j);
+            out.coeffRef(i, 0) = s;
+        }
+        return out;
+    }
+};
+template <class M>
+class QrSolveProxy {
+    const M& m;
+
+public:
+    typedef typename traits<M>::Scalar Scalar;
+    explicit QrSolveProxy(const M& mm) : m(mm) {}
+    template <class O>
+    typename MatrixBase<O>::PlainObject solve(const MatrixBase<O>& b) const {
+        Matrix<Scalar, Dynamic, Dynamic> a = m.eval();
+        typename MatrixBase<O>::PlainObject x = b.eval();
+        mini_lu_solve<Scalar>(a.rows(), x.cols(), a.data(), x.data());
+        return x;
+    }
+};
+
 // ------------------------------------------------------------------------------------------------
 // Geometry: just the quaternion members the MPC path touches.
 template <class T>
@@ -801,14 +908,43 @@ public:
 
 template <class T, int Dim, int Mode>
 class Transform {
+    // Isometry3 with Eigen's semantics: translate() and rotate() post-multiply (T <- T * Translation(v), T <- T * R),
+    // a point is mapped to linear * p + translation.
+    Matrix<T, 3, 3> lin;
+    Matrix<T, 3, 1> tr;
+
 public:
+    Transform() {
+        lin.setIdentity();
+        tr.setZero();
+    }
     static Transform Identity() { return Transform(); }
     template <class V>
-    Transform& translate(const V&) { return *this; }
-    template <class Q>
-    Transform& rotate(const Q&) { return *this; }
+    Transform& translate(const V& v) {
+        Matrix<T, 3, 1> vv;
+        for (int i = 0; i < 3; ++i) vv(i) = v[i];
+        Matrix<T, 3, 1> d = lin * vv;
+        tr += d;
+        return *this;
+    }
+    Transform& rotate(const Quaternion<T>& q) {
+        Matrix<T, 3, 3> r = q.toRotationMatrix();
+        lin = (lin * r).eval();
+        return *this;
+    }
+    const Matrix<T, 3, 3>& linear() const { return lin; }
+    const Matrix<T, 3, 1>& translation() const { return tr; }
     template <class P>
-    P operator*(const P& p) const { return p; }
+    P operator*(const P& p) const {
+        P out = p;
+        for (int j = 0; j < p.cols(); ++j)
+            for (int i = 0; i < 3; ++i) {
+                T s = 0;
+                for (int k = 0; k < 3; ++k) s += lin(i, k) * p(k, j);
+                out(i, j) = s + tr(i);
+            }
+        return out;
+    }
 };
 
 }   // namespace Eigen

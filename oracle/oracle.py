@@ -29,7 +29,7 @@ def build(force: bool = False) -> str:
     have_ref = os.path.isdir("/root/reference/quadruped/extern/qpOASES/src")
     if force or not os.path.exists(so) or have_ref:
         if have_ref:
-            subprocess.run(["make", "-s", "-j8", "-C", _HERE, "all", "refmpc", "refwbc"], check=True,
+            subprocess.run(["make", "-s", "-j8", "-C", _HERE, "all", "refmpc", "refwbc", "refctl"], check=True,
                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         elif not os.path.exists(so):
             raise RuntimeError("oracle/libqr_oracle.so missing and /root/reference not available to build it")
@@ -505,3 +505,136 @@ def quadprog_ineq(G, g0, Cm, c0):
     f.restype = C.c_double
     cost = f(n, m, _dp(G), _dp(g0), _dp(Cm), _dp(c0), _dp(x))
     return x, cost
+
+
+# ------------------------------------------------------------------------------------------------
+# Controller code compiled from the reference itself (oracle/_ref/libqr_ctl_ref.so, ref_ctl_shim.cpp): leg kinematics,
+# contact table / reference trajectory, SolveDenseMPC (lever arms, f_ff), swing parabola, foothold heuristic,
+# MPC-mode swing targets, open-loop gait phase, force-balance QP.
+# ------------------------------------------------------------------------------------------------
+_REFCTL = None
+
+
+def ref_ctl_available() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libqr_ctl_ref.so"))
+
+
+def _ref_ctl():
+    global _REFCTL
+    if _REFCTL is None:
+        _REFCTL = C.CDLL(os.path.join(_HERE, "_ref", "libqr_ctl_ref.so"))
+    return _REFCTL
+
+
+def robot_geom(robot) -> np.ndarray:
+    """geom[18] of ref_ctl_shim.cpp: hip_len, upper_len, lower_len, hipOffset (3x4 column-major = abad positions), comOffset."""
+    hips = np.array(robot.hip_positions, np.float64)
+    abad = hips.copy()
+    abad[:, 1] -= np.sign(hips[:, 1]) * robot.hip_len
+    return np.concatenate([[robot.hip_len, robot.upper_len, robot.lower_len], abad.reshape(12), robot.com_offset]).astype(np.float32)
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, np.float32)
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, np.int32)
+
+
+def _opt_fp(a):
+    return None if a is None else _fp(a)
+
+
+def ref_leg_kinematics(robot, q, qd=None, f_leg=None):
+    """qrRobot leg kinematics (src/robots/qr_robot.cpp:106-251) for one robot: dict(foot_base[12] column-major 3x4, jac[4,3,3],
+    foot_vel[12], tau[12], ik_q[12], ik_qd[12])."""
+    geom = robot_geom(robot)
+    q, qd, f_leg = _f32(q), _f32(qd if qd is not None else np.zeros(12)), _f32(f_leg if f_leg is not None else np.zeros(12))
+    out = {k: np.zeros(n, np.float32) for k, n in (("foot_base", 12), ("jac", 36), ("foot_vel", 12), ("tau", 12), ("ik_q", 12), ("ik_qd", 12))}
+    _ref_ctl().qr_ref_leg_kinematics(_fp(geom), _fp(q), _fp(qd), _fp(f_leg), _fp(out["foot_base"]), _fp(out["jac"]),
+                                     _fp(out["foot_vel"]), _fp(out["tau"]), _fp(out["ik_q"]), _fp(out["ik_qd"]))
+    out["jac"] = out["jac"].reshape(4, 3, 3)
+    return out
+
+
+def ref_mpc_inputs(h, n_horizon_l, dt, progress, duty, leg_state=None, contacts=None, init=None, base_xy=None):
+    """mpcTable [h,4] and trajAll [12h] from the reference's own lines (qr_mpc_stance_leg_controller.cpp:282-303, 344-376)."""
+    progress, duty = _f32(progress), _f32(duty)
+    ls, ct = _i32(leg_state), _i32(contacts)
+    table = np.zeros(4 * h, np.float32)
+    traj = np.zeros(12 * h, np.float32) if init is not None else None
+    init, base_xy = _f32(init), _f32(base_xy)
+    _ref_ctl().qr_ref_mpc_inputs(h, n_horizon_l, C.c_float(dt), _fp(progress), _fp(duty), None if ls is None else _ip(ls),
+                                 None if ct is None else _ip(ct), _opt_fp(init), _opt_fp(base_xy), _fp(table), _opt_fp(traj))
+    return table.reshape(h, 4), traj
+
+
+def ref_solve_dense_mpc(P: MpcParams, robot, rpy, pos, quat, v_world, w_world, foot_base, traj, table):
+    """SolveDenseMPC (qr_mpc_stance_leg_controller.cpp:385-410) through the reference's own SolveMPCKernel / GetMPCSolution:
+    dict(lever[12] column-major 3x4, f[12], f_ff[12], fr_des[12])."""
+    setup = np.array([P.dt, P.mu, P.f_max, P.mass, P.alpha] + list(P.inertia[:]) + list(P.weights[:]), np.float64)
+    geom = robot_geom(robot)
+    args = [_f32(a) for a in (rpy, pos, quat, v_world, w_world, foot_base, traj, np.asarray(table).reshape(-1))]
+    out = {k: np.zeros(12, np.float32) for k in ("lever", "f", "f_ff", "fr_des")}
+    _ref_ctl().qr_ref_solve_dense_mpc(P.horizon, _dp(setup), _fp(geom), *[_fp(a) for a in args], _fp(out["lever"]), _fp(out["f"]),
+                                      _fp(out["f_ff"]), _fp(out["fr_des"]))
+    return out
+
+
+def ref_swing_parabola(start, end, height, t, phase_module=False):
+    start, end = _f32(start), _f32(end)
+    pos, vel, acc = np.zeros(3, np.float32), np.zeros(3, np.float32), np.zeros(3, np.float32)
+    ok = _ref_ctl().qr_ref_swing_parabola(_fp(start), _fp(end), C.c_float(height), C.c_float(t), int(phase_module), _fp(pos), _fp(vel), _fp(acc))
+    return pos, vel, acc, bool(ok)
+
+
+def ref_foothold(robot, params: dict, b: dict, i: int, foothold_io, phase_io, q=None):
+    """ComputeHeuristicFootHold (qr_foothold_planner.cpp:112-240) for robot i of a make_foothold_batch dict."""
+    geom = robot_geom(robot)
+    geom[3:15] = np.asarray(params["hip_offset"], np.float32)
+    state_des = np.zeros(12, np.float32)
+    state_des[6:9] = b["des_speed"][i]
+    state_des[11] = b["des_twist"][i]
+    clearance = 0.01
+    state_des[2] = b["des_height"][i] + np.float32(clearance)
+    fh, ph = np.array(foothold_io, np.float32, copy=True), np.array(phase_io, np.float32, copy=True)
+    _ref_ctl().qr_ref_foothold(_fp(geom), _fp(_f32(params["hip_pos"])), _fp(_f32(params["swing_kp"])), _fp(_f32(b["com_vel"][i])),
+                               _fp(_f32(b["rpy_rate"][i])), _fp(_f32(b["dR"][i])), _fp(_f32(b["base_R"][i])), _fp(_f32(b["rpy"][i])),
+                               _fp(_f32(b["foot_base"][i])), _opt_fp(_f32(q)), _fp(state_des), C.c_float(clearance),
+                               _fp(_f32(b["swing_remain"][i])), _fp(_f32(b["norm_phase"][i])), _ip(_i32(b["allow_switch"][i])),
+                               _ip(_i32(b["swing_mask"][i])), _fp(fh), _fp(ph))
+    return fh, ph
+
+
+def ref_swing_targets(robot, base_pos, quat, v_world, foothold, planner_phase, switch_pos, swing_duration, swing_mask,
+                      horizontal_terrain=True):
+    """MPC-mode swing targets (qr_swing_leg_controller.cpp:361-409, 417-420): dict(p_foot_des, v_foot_des, a_foot_des,
+    foot_base_des, q_des, qd_des), [12] each, rows of stance legs left at zero."""
+    geom = robot_geom(robot)
+    out = {k: np.zeros(12, np.float32) for k in ("p_foot_des", "v_foot_des", "a_foot_des", "foot_base_des", "q_des", "qd_des")}
+    _ref_ctl().qr_ref_swing_targets(_fp(geom), _fp(_f32(base_pos)), _fp(_f32(quat)), _fp(_f32(v_world)), _fp(_f32(foothold)),
+                                    _fp(_f32(planner_phase)), _fp(_f32(switch_pos)), _fp(_f32(swing_duration)), _ip(_i32(swing_mask)),
+                                    int(horizontal_terrain), *[_fp(out[k]) for k in ("p_foot_des", "v_foot_des", "a_foot_des", "foot_base_des", "q_des", "qd_des")])
+    return out
+
+
+def ref_gait_update(t, cfg, contacts, istate, fstate, out, contact_threshold=0.1, stop=False, advanced_trot=False):
+    """One qrOpenLoopGaitGenerator::Update(t) (qr_openloop_gait_generator.cpp:126-247) on caller-held state; returns updated
+    copies (istate[20] int32, fstate[4], out[12], allow[4])."""
+    istate, fstate, out = np.array(istate, np.int32, copy=True), np.array(fstate, np.float32, copy=True), np.array(out, np.float32, copy=True)
+    allow = np.zeros(4, np.int32)
+    _ref_ctl().qr_ref_gait_update(C.c_float(t), _fp(_f32(cfg)), C.c_float(contact_threshold), _ip(_i32(contacts)), int(stop),
+                                  int(advanced_trot), _ip(istate), _fp(fstate), _fp(out), _ip(allow))
+    return istate, fstate, out, allow
+
+
+def ref_contact_force_world(params: dict, quat, foot_base, acc, contact, n=(0, 0, 1), t1=(1, 0, 0), t2=(0, 1, 0)):
+    """Quadruped::ComputeContactForce, world-frame overload (qr_qp_torque_optimizer.cpp:304-400) with the reference's own
+    matrix builders and QuadProg++.  Returns the 3x4 result as [12] column-major (leg columns)."""
+    out = np.zeros(12, np.float32)
+    _ref_ctl().qr_ref_contact_force_world(C.c_float(params["mass"]), _fp(_f32(np.asarray(params["inertia"]).reshape(9))), _fp(_f32(quat)),
+                                          _fp(_f32(foot_base)), _fp(_f32(acc)), _ip(_i32(contact)), _fp(_f32(n)), _fp(_f32(t1)),
+                                          _fp(_f32(t2)), _fp(_f32(params["acc_weight"])), _fp(_f32(params["fmin_ratio"])),
+                                          _fp(_f32(params["fmax_ratio"])), C.c_float(params["reg_weight"]), C.c_float(params["mu"]), _fp(out))
+    return out

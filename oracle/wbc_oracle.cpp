@@ -647,7 +647,8 @@ extern "C" int qro_swing_parabola(const float* start, const float* end, float he
     coefa = (deltaOne - deltaTwo * mid_phase) / deltaThree;
     coefb = (deltaTwo * pow(mid_phase, 2) - deltaOne) / deltaThree;
     coefc = start[2];
-    const float z = coefa * pow(phase, 2) + coefb * phase + coefc;
+    float z = coefa * pow(phase, 2) + coefb * phase + coefc;
+    if (phase - initialTime < 0.) z = 0.f;   // getPoint returns false for dt < 0 and leaves `out` at its default (x = 0), qr_geometry.cpp:171-173
     pos[0] = x; pos[1] = y; pos[2] = z;
     return 1;
 }

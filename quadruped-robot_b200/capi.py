@@ -40,7 +40,9 @@ EXPORTS = ["qr_gpu_init", "qr_gpu_shutdown", "qr_gpu_last_error", "qr_gpu_mpc_oc
            "qr_gpu_mpc_solve_batch", "qr_gpu_mpc_solve_batch_host", "qr_gpu_mpc_condense_batch",
            "qr_gpu_qp_solve_batch", "qr_gpu_wbc_solve_batch", "qr_gpu_wbc_solve_batch_f64",
            "qr_gpu_swing_parabola_batch", "qr_gpu_mpc_inputs_batch", "qr_gpu_mpc_leg_torque_batch", "qr_gpu_force_balance_batch", "qr_gpu_wbc_solve_batch_host", "qr_gpu_swing_bspline_batch",
-           "qr_gpu_foothold_heuristic_batch", "qr_gpu_mpc_solve_batch_host_multi"]
+           "qr_gpu_foothold_heuristic_batch", "qr_gpu_mpc_solve_batch_host_multi", "qr_gpu_mpc_solve_batch_ex",
+           "qr_gpu_mpc_lever_arms_batch", "qr_gpu_leg_kinematics_batch", "qr_gpu_leg_ik_batch", "qr_gpu_swing_targets_batch",
+           "qr_gpu_gait_update_batch"]
 
 
 class WbcModel(C.Structure):
@@ -280,3 +282,77 @@ def foothold_heuristic_batch_device(P: FootholdParams, d: dict, foothold, phase,
         _vp(d["foot_base"]), _vp(d["des_speed"]), _vp(d["des_twist"]), _vp(d["des_height"]), _vp(d["swing_remain"]),
         _vp(d["norm_phase"]), _vp(d["allow_switch"]), _vp(d["swing_mask"]), _vp(foothold), _vp(phase), C.c_void_p(stream_ptr))
     _check(rc, "qr_gpu_foothold_heuristic_batch")
+
+
+class MpcEpilogue(C.Structure):
+    """qr_mpc_epilogue of include/qr_gpu.h."""
+    _fields_ = [("hip_len", C.c_float), ("upper_len", C.c_float), ("lower_len", C.c_float), ("q", C.c_void_p),
+                ("f_ff_out", C.c_void_p), ("tau_out", C.c_void_p), ("wbc_cmd_io", C.c_void_p)]
+
+
+def _ptr(x):
+    return None if x is None else x.data_ptr()
+
+
+def mpc_solve_batch_device_ex(P: MpcParams, dev: dict, out: dict, stream_ptr: int, robot, q=None, f_ff=None, tau=None,
+                              wbc_cmd=None, opt: QpOptions | None = None, per_instance_mu=False):
+    """qr_gpu_mpc_solve_batch_ex: the solve with its fused post-processing (leg forces, joint torques, Fr_des rows)."""
+    ep = MpcEpilogue(robot.hip_len, robot.upper_len, robot.lower_len, _ptr(q), _ptr(f_ff), _ptr(tau), _ptr(wbc_cmd))
+    B = dev["p"].shape[0]
+    rc = lib().qr_gpu_mpc_solve_batch_ex(
+        C.byref(P), C.byref(opt) if opt is not None else None, B, *[_vp(dev[k]) for k in _KEYS],
+        _vp(dev["mu"]) if per_instance_mu else None, None, _vp(out["grf"]), _vp(out.get("u")),
+        _vp(out.get("status")), _vp(out.get("iters")), C.byref(ep), C.c_void_p(stream_ptr))
+    _check(rc, "qr_gpu_mpc_solve_batch_ex")
+
+
+class LegGeometry(C.Structure):
+    """qr_leg_geometry of include/qr_gpu.h."""
+    _fields_ = [("hip_len", C.c_float), ("upper_len", C.c_float), ("lower_len", C.c_float), ("hip_offset", C.c_float * 12)]
+
+
+def leg_geometry_of(robot) -> LegGeometry:
+    """hipOffset = the abad joint positions (hip positions moved inwards by the hip length), 3x4 column-major."""
+    g = LegGeometry()
+    g.hip_len, g.upper_len, g.lower_len = robot.hip_len, robot.upper_len, robot.lower_len
+    hips = np.array(robot.hip_positions, np.float64)
+    abad = hips.copy()
+    abad[:, 1] -= np.sign(hips[:, 1]) * robot.hip_len
+    g.hip_offset[:] = [float(v) for v in abad.astype(np.float32).reshape(12)]
+    return g
+
+
+def mpc_lever_arms_batch_device(robot, quat, foot_base, r_feet, stream_ptr: int):
+    com = (C.c_float * 3)(*[float(v) for v in robot.com_offset])
+    rc = lib().qr_gpu_mpc_lever_arms_batch(quat.shape[0], _vp(quat), _vp(foot_base), com, _vp(r_feet), C.c_void_p(stream_ptr))
+    _check(rc, "qr_gpu_mpc_lever_arms_batch")
+
+
+def leg_kinematics_batch_device(G: LegGeometry, q, qd, foot_base, jac, foot_vel, stream_ptr: int):
+    rc = lib().qr_gpu_leg_kinematics_batch(C.byref(G), q.shape[0], _vp(q), _vp(qd), _vp(foot_base), _vp(jac), _vp(foot_vel),
+                                           C.c_void_p(stream_ptr))
+    _check(rc, "qr_gpu_leg_kinematics_batch")
+
+
+def leg_ik_batch_device(G: LegGeometry, foot_base, foot_vel, leg_mask, q_out, qd_out, stream_ptr: int):
+    rc = lib().qr_gpu_leg_ik_batch(C.byref(G), foot_base.shape[0], _vp(foot_base), _vp(foot_vel), _vp(leg_mask), _vp(q_out),
+                                   _vp(qd_out), C.c_void_p(stream_ptr))
+    _check(rc, "qr_gpu_leg_ik_batch")
+
+
+def swing_targets_batch_device(G: LegGeometry, base_pos, quat, v_world, foothold, planner_phase, switch_pos, swing_duration,
+                               swing_mask, horizontal_terrain: bool, wbc_cmd, stream_ptr: int, foot_base_des=None, q_des=None,
+                               qd_des=None, valid=None):
+    rc = lib().qr_gpu_swing_targets_batch(C.byref(G), base_pos.shape[0], _vp(base_pos), _vp(quat), _vp(v_world), _vp(foothold),
+                                          _vp(planner_phase), _vp(switch_pos), _vp(swing_duration), _vp(swing_mask),
+                                          int(horizontal_terrain), _vp(wbc_cmd), _vp(foot_base_des), _vp(q_des), _vp(qd_des),
+                                          _vp(valid), C.c_void_p(stream_ptr))
+    _check(rc, "qr_gpu_swing_targets_batch")
+
+
+def gait_update_batch_device(time, cfg, contact_threshold: float, contacts, stop, advanced_trot: bool, istate, fstate,
+                             phase_full, norm_phase, swing_remain, stream_ptr: int, allow=None, early=None, swing_mask=None):
+    rc = lib().qr_gpu_gait_update_batch(time.shape[0], _vp(time), _vp(cfg), C.c_float(contact_threshold), _vp(contacts), _vp(stop),
+                                        int(advanced_trot), _vp(istate), _vp(fstate), _vp(phase_full), _vp(norm_phase),
+                                        _vp(swing_remain), _vp(allow), _vp(early), _vp(swing_mask), C.c_void_p(stream_ptr))
+    _check(rc, "qr_gpu_gait_update_batch")

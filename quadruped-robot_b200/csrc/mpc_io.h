@@ -53,46 +53,61 @@ QR_DEV float qr_sinf_cr(float x) { return (float)sin((double)x); }
 QR_DEV float qr_cosf_cr(float x) { return (float)cos((double)x); }
 QR_DEV float qr_sqrtf_cr(float x) { return (float)sqrt((double)x); }
 
-// quat (w,x,y,z), q[12], f_world[12] -> f_ff[12] (may be null), tau[12].
-QR_DEV void qr_mpc_grf_to_torque(float hip_len, float upper_len, float lower_len, const float* quat, const float* q,
-                                 const float* f_world, float* f_ff_out, float* tau) {
-    const float e0 = quat[0], e1 = quat[1], e2 = quat[2], e3 = quat[3];
+// One leg: f_ff = -R_base^T f (Rb = baseRMat row-major) and tau = J_leg^T f_ff.  t = the leg's three motor angles.
+QR_DEV void qr_mpc_leg_force_torque(float hip_len, float upper_len, float lower_len, const float* Rb, int leg, const float* t,
+                                    const float* f, float* ff, float* tau) {
 #define QR_M(a, b) QR_FMUL(a, b)
 #define QR_A(a, b) QR_FADD(a, b)
 #define QR_S(a, b) QR_FSUB(a, b)
-    const float Rb[9] = {
-        QR_S(1.f, QR_M(2.f, QR_A(QR_M(e2, e2), QR_M(e3, e3)))), QR_M(2.f, QR_S(QR_M(e1, e2), QR_M(e0, e3))), QR_M(2.f, QR_A(QR_M(e1, e3), QR_M(e0, e2))),
-        QR_M(2.f, QR_A(QR_M(e1, e2), QR_M(e0, e3))), QR_S(1.f, QR_M(2.f, QR_A(QR_M(e1, e1), QR_M(e3, e3)))), QR_M(2.f, QR_S(QR_M(e2, e3), QR_M(e0, e1))),
-        QR_M(2.f, QR_S(QR_M(e1, e3), QR_M(e0, e2))), QR_M(2.f, QR_A(QR_M(e2, e3), QR_M(e0, e1))), QR_S(1.f, QR_M(2.f, QR_A(QR_M(e1, e1), QR_M(e2, e2))))};
-    for (int leg = 0; leg < 4; ++leg) {
-        const float* f = f_world + 3 * leg;
-        float ff[3];
-        for (int a = 0; a < 3; ++a)
-            ff[a] = QR_A(QR_A(QR_M(-Rb[a], f[0]), QR_M(-Rb[3 + a], f[1])), QR_M(-Rb[6 + a], f[2]));
-        const float* t = q + 3 * leg;
-        const float sh = (leg & 1) ? hip_len : -hip_len;   // hipLength * pow(-1, leg_id + 1)
-        const float s0 = qr_sinf_cr(t[0]), c0 = qr_cosf_cr(t[0]), s2 = qr_sinf_cr(t[2]), c2 = qr_cosf_cr(t[2]);
-        const float uu = QR_M(upper_len, upper_len), ll = QR_M(lower_len, lower_len);
-        const float lEff = qr_sqrtf_cr(QR_A(QR_A(uu, ll), QR_M(QR_M(QR_M(2.f, upper_len), lower_len), c2)));
-        const float tEff = QR_A(t[1], QR_FDIV(t[2], 2.f));
-        const float sE = qr_sinf_cr(tEff), cE = qr_cosf_cr(tEff);
-        const float lu = QR_M(lower_len, upper_len);
-        float J[9];
-        J[0] = 0.f;
-        J[1] = QR_M(-lEff, cE);
-        J[2] = QR_S(QR_FDIV(QR_M(QR_M(lu, s2), sE), lEff), QR_FDIV(QR_M(lEff, cE), 2.f));
-        J[3] = QR_A(QR_M(-sh, s0), QR_M(QR_M(lEff, c0), cE));
-        J[4] = QR_M(QR_M(-lEff, s0), sE);
-        J[5] = QR_S(QR_FDIV(QR_M(QR_M(QR_M(-lu, s0), s2), cE), lEff), QR_FDIV(QR_M(QR_M(lEff, s0), sE), 2.f));
-        J[6] = QR_A(QR_M(sh, c0), QR_M(QR_M(lEff, s0), cE));
-        J[7] = QR_M(QR_M(lEff, sE), c0);
-        J[8] = QR_A(QR_FDIV(QR_M(QR_M(QR_M(lu, s2), c0), cE), lEff), QR_FDIV(QR_M(QR_M(lEff, sE), c0), 2.f));
-        for (int a = 0; a < 3; ++a) {
-            tau[3 * leg + a] = QR_A(QR_A(QR_M(J[a], ff[0]), QR_M(J[3 + a], ff[1])), QR_M(J[6 + a], ff[2]));
-            if (f_ff_out) f_ff_out[3 * leg + a] = ff[a];
-        }
-    }
+    for (int a = 0; a < 3; ++a)
+        ff[a] = QR_A(QR_A(QR_M(-Rb[a], f[0]), QR_M(-Rb[3 + a], f[1])), QR_M(-Rb[6 + a], f[2]));
+    const float sh = (leg & 1) ? hip_len : -hip_len;   // hipLength * pow(-1, leg_id + 1)
+    const float s0 = qr_sinf_cr(t[0]), c0 = qr_cosf_cr(t[0]), s2 = qr_sinf_cr(t[2]), c2 = qr_cosf_cr(t[2]);
+    const float uu = QR_M(upper_len, upper_len), ll = QR_M(lower_len, lower_len);
+    const float lEff = qr_sqrtf_cr(QR_A(QR_A(uu, ll), QR_M(QR_M(QR_M(2.f, upper_len), lower_len), c2)));
+    const float tEff = QR_A(t[1], QR_FDIV(t[2], 2.f));
+    const float sE = qr_sinf_cr(tEff), cE = qr_cosf_cr(tEff);
+    const float lu = QR_M(lower_len, upper_len);
+    float J[9];
+    J[0] = 0.f;
+    J[1] = QR_M(-lEff, cE);
+    J[2] = QR_S(QR_FDIV(QR_M(QR_M(lu, s2), sE), lEff), QR_FDIV(QR_M(lEff, cE), 2.f));
+    J[3] = QR_A(QR_M(-sh, s0), QR_M(QR_M(lEff, c0), cE));
+    J[4] = QR_M(QR_M(-lEff, s0), sE);
+    J[5] = QR_S(QR_FDIV(QR_M(QR_M(QR_M(-lu, s0), s2), cE), lEff), QR_FDIV(QR_M(QR_M(lEff, s0), sE), 2.f));
+    J[6] = QR_A(QR_M(sh, c0), QR_M(QR_M(lEff, s0), cE));
+    J[7] = QR_M(QR_M(lEff, sE), c0);
+    J[8] = QR_A(QR_FDIV(QR_M(QR_M(QR_M(lu, s2), c0), cE), lEff), QR_FDIV(QR_M(QR_M(lEff, sE), c0), 2.f));
+    for (int a = 0; a < 3; ++a)
+        tau[a] = QR_A(QR_A(QR_M(J[a], ff[0]), QR_M(J[3 + a], ff[1])), QR_M(J[6 + a], ff[2]));
 #undef QR_M
 #undef QR_A
 #undef QR_S
+}
+
+// baseRMat = quaternionToRotationMatrix(q)^T (qr_robot.cpp:70, qr_se3.h:186-203), row-major
+QR_DEV void qr_mpc_base_rmat(const float* quat, float* Rb) {
+    const float e0 = quat[0], e1 = quat[1], e2 = quat[2], e3 = quat[3];
+    Rb[0] = QR_FSUB(1.f, QR_FMUL(2.f, QR_FADD(QR_FMUL(e2, e2), QR_FMUL(e3, e3))));
+    Rb[1] = QR_FMUL(2.f, QR_FSUB(QR_FMUL(e1, e2), QR_FMUL(e0, e3)));
+    Rb[2] = QR_FMUL(2.f, QR_FADD(QR_FMUL(e1, e3), QR_FMUL(e0, e2)));
+    Rb[3] = QR_FMUL(2.f, QR_FADD(QR_FMUL(e1, e2), QR_FMUL(e0, e3)));
+    Rb[4] = QR_FSUB(1.f, QR_FMUL(2.f, QR_FADD(QR_FMUL(e1, e1), QR_FMUL(e3, e3))));
+    Rb[5] = QR_FMUL(2.f, QR_FSUB(QR_FMUL(e2, e3), QR_FMUL(e0, e1)));
+    Rb[6] = QR_FMUL(2.f, QR_FSUB(QR_FMUL(e1, e3), QR_FMUL(e0, e2)));
+    Rb[7] = QR_FMUL(2.f, QR_FADD(QR_FMUL(e2, e3), QR_FMUL(e0, e1)));
+    Rb[8] = QR_FSUB(1.f, QR_FMUL(2.f, QR_FADD(QR_FMUL(e1, e1), QR_FMUL(e2, e2))));
+}
+
+// quat (w,x,y,z), q[12], f_world[12] -> f_ff[12] (may be null), tau[12].
+QR_DEV void qr_mpc_grf_to_torque(float hip_len, float upper_len, float lower_len, const float* quat, const float* q,
+                                 const float* f_world, float* f_ff_out, float* tau) {
+    float Rb[9];
+    qr_mpc_base_rmat(quat, Rb);
+    for (int leg = 0; leg < 4; ++leg) {
+        float ff[3];
+        qr_mpc_leg_force_torque(hip_len, upper_len, lower_len, Rb, leg, q + 3 * leg, f_world + 3 * leg, ff, tau + 3 * leg);
+        if (f_ff_out)
+            for (int a = 0; a < 3; ++a) f_ff_out[3 * leg + a] = ff[a];
+    }
 }

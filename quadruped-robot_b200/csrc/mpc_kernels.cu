@@ -544,7 +544,7 @@ namespace {
 int mpc_enqueue(Ctx& cx, const qr_mpc_params* P, const qr_qp_options* opt, int batch, const float* p, const float* v,
                 const float* quat, const float* w, const float* r_feet, const float* rpy, const float* traj,
                 const float* gait, const float* mu_i, const float* fmax_i, float* grf_out, float* u_out,
-                int32_t* status_out, int32_t* iters_out, cudaStream_t st) {
+                int32_t* status_out, int32_t* iters_out, cudaStream_t st, const qr_mpc_epilogue* ep = nullptr) {
     int rc = check_params(P, batch);
     if (rc) return rc;
     if (batch == 0) return QR_OK;
@@ -559,6 +559,11 @@ int mpc_enqueue(Ctx& cx, const qr_mpc_params* P, const qr_qp_options* opt, int b
     A.p = p; A.v = v; A.quat = quat; A.w = w; A.r_feet = r_feet; A.rpy = rpy; A.traj = traj; A.gait = gait;
     A.mu_i = mu_i; A.fmax_i = fmax_i;
     A.grf_out = grf_out; A.u_out = u_out; A.status_out = status_out; A.iters_out = iters_out;
+    if (ep) {
+        if ((ep->f_ff_out || ep->tau_out) && !ep->q) return fail(QR_EINVAL, "epilogue: leg forces / torques need the motor angles");
+        A.ep_q = ep->q; A.ep_ff = ep->f_ff_out; A.ep_tau = ep->tau_out; A.ep_cmd = ep->wbc_cmd_io;
+        A.ep_hip = ep->hip_len; A.ep_upper = ep->upper_len; A.ep_lower = ep->lower_len;
+    }
     Lane* lane = nullptr;
     if (batch <= cx.sm_count) {
         // Latency path: the grid cannot fill the device anyway, so skip the classification and launch the
@@ -633,6 +638,20 @@ extern "C" int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_option
     if (!cx) return QR_ECUDA;
     return mpc_enqueue(*cx, P, opt, batch, p, v, quat, w, r_feet, rpy, traj, gait, mu_i, fmax_i, grf_out, u_out,
                        status_out, iters_out, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int qr_gpu_mpc_solve_batch_ex(const qr_mpc_params* P, const qr_qp_options* opt, int batch,
+                                         const float* p, const float* v, const float* quat,
+                                         const float* w, const float* r_feet, const float* rpy,
+                                         const float* traj, const float* gait, const float* mu_i,
+                                         const float* fmax_i, float* grf_out, float* u_out,
+                                         int32_t* status_out, int32_t* iters_out, const qr_mpc_epilogue* epilogue,
+                                         void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    Ctx* cx = current_ctx();
+    if (!cx) return QR_ECUDA;
+    return mpc_enqueue(*cx, P, opt, batch, p, v, quat, w, r_feet, rpy, traj, gait, mu_i, fmax_i, grf_out, u_out,
+                       status_out, iters_out, (cudaStream_t)cuda_stream, epilogue);
 }
 
 extern "C" int qr_gpu_mpc_condense_batch(const qr_mpc_params* P, int batch, const float* p,
@@ -1244,4 +1263,192 @@ extern "C" int qr_gpu_foothold_heuristic_batch(const qr_foothold_params* P, int 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_foothold_kernel", e);
     return QR_OK;
+}
+
+// ==================================================================================================
+// Controller arithmetic around the two solvers: lever arms, leg kinematics, MPC-mode swing targets, gait phase
+// ==================================================================================================
+#include "ctl_extra.h"
+
+namespace {
+
+__global__ void qr_mpc_lever_arms_kernel(int batch, const float* quat, const float* foot_base, float cx, float cy, float cz,
+                                         float* r_feet) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    const float com[3] = {cx, cy, cz};
+    qr_mpc_lever_arms(quat + 4 * (size_t)i, foot_base + 12 * (size_t)i, com, r_feet + 12 * (size_t)i);
+}
+
+// one thread per leg
+__global__ void qr_leg_kinematics_kernel(const QrLegGeom G, int batch, const float* q, const float* qd, float* foot_base,
+                                         float* jac, float* foot_vel) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = idx >> 2, leg = idx & 3;
+    if (i >= batch) return;
+    const float* t = q + 12 * (size_t)i + 3 * leg;
+    if (foot_base) qr_leg_fk(G, leg, t, foot_base + 12 * (size_t)i + 3 * leg);
+    if (jac || foot_vel) {
+        float J[9];
+        qr_leg_jacobian(G, leg, t, J);
+        if (jac)
+            for (int e = 0; e < 9; ++e) jac[36 * (size_t)i + 9 * leg + e] = J[e];
+        if (foot_vel && qd) qr_mat3_vec(J, qd + 12 * (size_t)i + 3 * leg, foot_vel + 12 * (size_t)i + 3 * leg);
+    }
+}
+
+__global__ void qr_leg_ik_kernel(const QrLegGeom G, int batch, const float* foot_base, const float* foot_vel,
+                                 const int32_t* leg_mask, float* q_out, float* qd_out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = idx >> 2, leg = idx & 3;
+    if (i >= batch || (leg_mask && !leg_mask[4 * (size_t)i + leg])) return;
+    float t[3];
+    qr_leg_ik(G, leg, foot_base + 12 * (size_t)i + 3 * leg, t);
+    for (int a = 0; a < 3; ++a) q_out[12 * (size_t)i + 3 * leg + a] = t[a];
+    if (qd_out && foot_vel) qr_leg_ik_velocity(G, leg, t, foot_vel + 12 * (size_t)i + 3 * leg, qd_out + 12 * (size_t)i + 3 * leg);
+}
+
+struct QrSwingRows {
+    const float *base_pos, *quat, *v_world, *foothold, *planner_phase, *switch_pos, *swing_duration;
+    const int32_t* swing_mask;
+    float *cmd, *foot_base_des, *q_des, *qd_des;
+    int32_t* valid;
+};
+__global__ void qr_swing_targets_kernel(const QrLegGeom G, int batch, int horizontal_terrain, const QrSwingRows R) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = idx >> 2, leg = idx & 3;
+    if (i >= batch) return;
+    const size_t l = 4 * (size_t)i + leg;
+    if (!R.swing_mask[l]) { if (R.valid) R.valid[l] = 0; return; }
+    float* cmd = R.cmd + 66 * (size_t)i;
+    const int ok = qr_swing_targets_leg(G, leg, R.base_pos + 3 * (size_t)i, R.quat + 4 * (size_t)i, R.v_world + 3 * (size_t)i,
+                                        R.foothold + 3 * l, R.planner_phase[l], R.switch_pos + 3 * l, R.swing_duration[l],
+                                        horizontal_terrain, cmd + 15 + 3 * leg, cmd + 27 + 3 * leg, cmd + 39 + 3 * leg,
+                                        R.foot_base_des ? R.foot_base_des + 3 * l : nullptr, R.q_des ? R.q_des + 3 * l : nullptr,
+                                        R.qd_des ? R.qd_des + 3 * l : nullptr);
+    if (R.valid) R.valid[l] = ok;
+}
+
+struct QrGaitRows {
+    const float *time, *cfg;
+    const int32_t *contacts, *stop;
+    int32_t* istate;
+    float *fstate, *phase_full, *norm_phase, *swing_remain;
+    int32_t *allow, *early, *swing_mask;
+};
+__global__ void qr_gait_update_kernel(int batch, float contact_threshold, int advanced_trot, const QrGaitRows R) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    const size_t r4 = 4 * (size_t)i;
+    int32_t al[4];
+    float out[12];
+    for (int l = 0; l < 4; ++l) {
+        out[l] = R.phase_full[r4 + l];
+        out[4 + l] = R.norm_phase[r4 + l];
+        out[8 + l] = R.swing_remain[r4 + l];
+    }
+    int32_t* ist = R.istate + 20 * (size_t)i;
+    qr_gait_update(R.time[i], R.cfg + 20 * (size_t)i, contact_threshold, R.contacts + r4, R.stop ? R.stop[i] : 0, advanced_trot,
+                   ist, R.fstate + r4, out, al);
+    for (int l = 0; l < 4; ++l) {
+        R.phase_full[r4 + l] = out[l];
+        R.norm_phase[r4 + l] = out[4 + l];
+        R.swing_remain[r4 + l] = out[8 + l];
+        const int ls = ist[12 + l];
+        if (R.allow) R.allow[r4 + l] = al[l];
+        if (R.early) R.early[r4 + l] = ls == 2;
+        // the legs the swing controller moves (qr_swing_leg_controller.cpp:218-228)
+        if (R.swing_mask) R.swing_mask[r4 + l] = !((ls == 1 && al[l]) || ls == 2);
+    }
+}
+
+QrLegGeom leg_geom_of(const qr_leg_geometry* g) {
+    QrLegGeom G;
+    G.hip_len = g->hip_len; G.upper_len = g->upper_len; G.lower_len = g->lower_len;
+    for (int k = 0; k < 12; ++k) G.hip_offset[k] = g->hip_offset[k];
+    return G;
+}
+
+int launch_check(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(QR_ECUDA, what, e);
+    return QR_OK;
+}
+
+}  // namespace
+
+extern "C" int qr_gpu_mpc_lever_arms_batch(int batch, const float* quat, const float* foot_base, const float* com_offset,
+                                           float* r_feet_out, void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    Ctx* cx = current_ctx();
+    if (!cx) return QR_ECUDA;
+    if (batch < 0) return fail(QR_EINVAL, "negative batch");
+    if (batch == 0) return QR_OK;
+    if (!quat || !foot_base || !com_offset || !r_feet_out) return fail(QR_EINVAL, "null pointer");
+    qr_mpc_lever_arms_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(batch, quat, foot_base, com_offset[0],
+                                                                                       com_offset[1], com_offset[2], r_feet_out);
+    return launch_check("launch qr_mpc_lever_arms_kernel");
+}
+
+extern "C" int qr_gpu_leg_kinematics_batch(const qr_leg_geometry* geom, int batch, const float* q, const float* qd,
+                                           float* foot_base_out, float* jac_out, float* foot_vel_out, void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    Ctx* cx = current_ctx();
+    if (!cx) return QR_ECUDA;
+    if (!geom || batch < 0) return fail(QR_EINVAL, "null geometry or negative batch");
+    if (batch == 0) return QR_OK;
+    if (!q || (foot_vel_out && !qd)) return fail(QR_EINVAL, "null pointer");
+    qr_leg_kinematics_kernel<<<(4 * batch + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(leg_geom_of(geom), batch, q, qd,
+                                                                                           foot_base_out, jac_out, foot_vel_out);
+    return launch_check("launch qr_leg_kinematics_kernel");
+}
+
+extern "C" int qr_gpu_leg_ik_batch(const qr_leg_geometry* geom, int batch, const float* foot_base, const float* foot_vel,
+                                   const int32_t* leg_mask, float* q_out, float* qd_out, void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    Ctx* cx = current_ctx();
+    if (!cx) return QR_ECUDA;
+    if (!geom || batch < 0) return fail(QR_EINVAL, "null geometry or negative batch");
+    if (batch == 0) return QR_OK;
+    if (!foot_base || !q_out || (qd_out && !foot_vel)) return fail(QR_EINVAL, "null pointer");
+    qr_leg_ik_kernel<<<(4 * batch + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(leg_geom_of(geom), batch, foot_base, foot_vel,
+                                                                                   leg_mask, q_out, qd_out);
+    return launch_check("launch qr_leg_ik_kernel");
+}
+
+extern "C" int qr_gpu_swing_targets_batch(const qr_leg_geometry* geom, int batch, const float* base_pos, const float* quat,
+                                          const float* v_world, const float* foothold, const float* planner_phase,
+                                          const float* switch_pos, const float* swing_duration, const int32_t* swing_mask,
+                                          int horizontal_terrain, float* wbc_cmd_io, float* foot_base_des_out, float* q_des_out,
+                                          float* qd_des_out, int32_t* valid_out, void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    Ctx* cx = current_ctx();
+    if (!cx) return QR_ECUDA;
+    if (!geom || batch < 0) return fail(QR_EINVAL, "null geometry or negative batch");
+    if (batch == 0) return QR_OK;
+    if (!base_pos || !quat || !v_world || !foothold || !planner_phase || !switch_pos || !swing_duration || !swing_mask || !wbc_cmd_io)
+        return fail(QR_EINVAL, "null pointer");
+    if (qd_des_out && !q_des_out) return fail(QR_EINVAL, "joint velocities need the joint angles output");
+    QrSwingRows R{base_pos, quat, v_world, foothold, planner_phase, switch_pos, swing_duration, swing_mask,
+                  wbc_cmd_io, foot_base_des_out, q_des_out, qd_des_out, valid_out};
+    qr_swing_targets_kernel<<<(4 * batch + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(leg_geom_of(geom), batch,
+                                                                                          horizontal_terrain, R);
+    return launch_check("launch qr_swing_targets_kernel");
+}
+
+extern "C" int qr_gpu_gait_update_batch(int batch, const float* time, const float* cfg, float contact_threshold,
+                                        const int32_t* contacts, const int32_t* stop, int advanced_trot, int32_t* istate_io,
+                                        float* fstate_io, float* phase_full_io, float* norm_phase_io, float* swing_remain_io,
+                                        int32_t* allow_out, int32_t* early_out, int32_t* swing_mask_out, void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    Ctx* cx = current_ctx();
+    if (!cx) return QR_ECUDA;
+    if (batch < 0) return fail(QR_EINVAL, "negative batch");
+    if (batch == 0) return QR_OK;
+    if (!time || !cfg || !contacts || !istate_io || !fstate_io || !phase_full_io || !norm_phase_io || !swing_remain_io)
+        return fail(QR_EINVAL, "null pointer");
+    QrGaitRows R{time, cfg, contacts, stop, istate_io, fstate_io, phase_full_io, norm_phase_io, swing_remain_io,
+                 allow_out, early_out, swing_mask_out};
+    qr_gait_update_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(batch, contact_threshold, advanced_trot, R);
+    return launch_check("launch qr_gait_update_kernel");
 }

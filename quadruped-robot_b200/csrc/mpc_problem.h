@@ -4,6 +4,7 @@
 #pragma once
 
 #include "mpc_condense.h"
+#include "mpc_io.h"
 #include "qp_solver.h"
 
 // Arguments common to all kernels (passed by value).
@@ -33,6 +34,13 @@ struct QrMpcArgs {
     const float *H_in, *g_in, *ub_in;
     float* x_out;
     double* x_out_f64;
+    // fused post-processing of the step-0 forces (qr_gpu_mpc_solve_batch_ex): leg forces and joint torques of
+    // MPCStanceLegController (f_ff = -R_base^T f, tau = J_leg^T f_ff) and Fr_des of the WBC command rows
+    const float* ep_q;       // [batch][12] motor angles, or null: no epilogue
+    float* ep_ff;            // [batch][12] or null
+    float* ep_tau;           // [batch][12] or null
+    float* ep_cmd;           // [batch][66] qrWbcCtrlData rows: Fr_des (entries 51..62) is written, or null
+    float ep_hip, ep_upper, ep_lower;
 };
 
 QR_HD int qr_ntri(int nf) { return (nf * (nf + 1)) / 2; }
@@ -307,6 +315,26 @@ QR_DEV void qr_mpc_scatter(const QrMpcArgs& A, int prob, QrMpcSmem& S, const dou
         if (i < 12 && A.grf_out) A.grf_out[(size_t)prob * 12 + i] = val;
         if (A.x_out) A.x_out[(size_t)prob * 12 * h + i] = val;
         if (A.x_out_f64) A.x_out_f64[(size_t)prob * 12 * h + i] = v64;
+    }
+    // epilogue, one thread per leg: what SolveDenseMPC / GetAction do with the first 12 forces
+    // (qr_mpc_stance_leg_controller.cpp:402-409, 139-141; qr_robot.cpp:241-251)
+    if (A.ep_q || A.ep_cmd) {
+        QR_FOR(leg, 4) {
+            const int sl = S.slot[leg];   // foot-step `leg` of step 0
+            float f[3];
+            for (int a = 0; a < 3; ++a) f[a] = (sl >= 0 && valid) ? (float)x[3 * sl + a] : 0.f;
+            if (A.ep_cmd)
+                for (int a = 0; a < 3; ++a) A.ep_cmd[(size_t)prob * 66 + 51 + 3 * leg + a] = f[a];
+            if (A.ep_q && (A.ep_ff || A.ep_tau)) {
+                float Rb[9], ff[3], tau[3];
+                qr_mpc_base_rmat(S.state + 6, Rb);
+                qr_mpc_leg_force_torque(A.ep_hip, A.ep_upper, A.ep_lower, Rb, leg, A.ep_q + (size_t)prob * 12 + 3 * leg, f, ff, tau);
+                for (int a = 0; a < 3; ++a) {
+                    if (A.ep_ff) A.ep_ff[(size_t)prob * 12 + 3 * leg + a] = ff[a];
+                    if (A.ep_tau) A.ep_tau[(size_t)prob * 12 + 3 * leg + a] = tau[a];
+                }
+            }
+        }
     }
     QR_THREADS(t) {
         if (t == 0) {

@@ -853,6 +853,9 @@ QR_DEV int qr_swing_parabola(const float* start, const float* end, float height,
     const float cb = (float)(QR_DADD(QR_DMUL((double)d2, 0.25), -(double)d1) / (double)d3);
     const float cbt = QR_FMUL(cb, phase);
     const double z = QR_DADD(QR_DADD(QR_DMUL((double)ca, QR_DMUL((double)phase, (double)phase)), (double)cbt), (double)start[2]);
-    pos[0] = x; pos[1] = y; pos[2] = (float)z;
+    // -1e-3 <= phase < 0: the generator accepts the sample (qr_foot_trajectory_generator.cpp:194) but getPoint refuses
+    // it (dt < 0, qr_geometry.cpp:171-173) and leaves its output Point at the default x = 0, which the generator
+    // then returns as the foot height.  Found by pinning against the reference-compiled generator.
+    pos[0] = x; pos[1] = y; pos[2] = (phase < 0.f) ? 0.f : (float)z;
     return 1;
 }

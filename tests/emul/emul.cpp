@@ -12,6 +12,7 @@
 #include "../../quadruped-robot_b200/csrc/mpc_io.h"
 #include "../../quadruped-robot_b200/csrc/fb_problem.h"
 #include "../../quadruped-robot_b200/csrc/swing_extra.h"
+#include "../../quadruped-robot_b200/csrc/ctl_extra.h"
 
 static qr_qp_options emul_default_options() {
     qr_qp_options o;
@@ -190,4 +191,62 @@ extern "C" int qr_emul_small_qp(int n, int m, const double* G, const double* g0,
                                 int* iters) {
     QrSmallQpWork W;
     return qr_small_qp_solve(n, m, G, g0, C, c0, x, W, iters);
+}
+
+// ---- csrc/ctl_extra.h: lever arms, leg kinematics, MPC-mode swing targets, gait phase (one robot per call)
+static QrLegGeom emul_geom(const qr_leg_geometry* g) {
+    QrLegGeom G;
+    G.hip_len = g->hip_len; G.upper_len = g->upper_len; G.lower_len = g->lower_len;
+    for (int k = 0; k < 12; ++k) G.hip_offset[k] = g->hip_offset[k];
+    return G;
+}
+extern "C" void qr_emul_lever_arms(const float* quat, const float* foot_base, const float* com, float* r_feet) {
+    qr_mpc_lever_arms(quat, foot_base, com, r_feet);
+}
+extern "C" void qr_emul_leg_kinematics(const qr_leg_geometry* g, const float* q, const float* qd, float* foot_base, float* jac,
+                                       float* foot_vel, float* ik_q, float* ik_qd) {
+    const QrLegGeom G = emul_geom(g);
+    for (int leg = 0; leg < 4; ++leg) {
+        qr_leg_fk(G, leg, q + 3 * leg, foot_base + 3 * leg);
+        qr_leg_jacobian(G, leg, q + 3 * leg, jac + 9 * leg);
+        qr_mat3_vec(jac + 9 * leg, qd + 3 * leg, foot_vel + 3 * leg);
+        qr_leg_ik(G, leg, foot_base + 3 * leg, ik_q + 3 * leg);
+        qr_leg_ik_velocity(G, leg, ik_q + 3 * leg, foot_vel + 3 * leg, ik_qd + 3 * leg);
+    }
+}
+extern "C" void qr_emul_swing_targets(const qr_leg_geometry* g, const float* base_pos, const float* quat, const float* v_world,
+                                      const float* foothold, const float* planner_phase, const float* switch_pos,
+                                      const float* swing_duration, const int32_t* swing_mask, int horizontal, float* cmd,
+                                      float* foot_base_des, float* q_des, float* qd_des, int32_t* valid) {
+    const QrLegGeom G = emul_geom(g);
+    for (int leg = 0; leg < 4; ++leg) {
+        valid[leg] = 0;
+        if (!swing_mask[leg]) continue;
+        valid[leg] = qr_swing_targets_leg(G, leg, base_pos, quat, v_world, foothold + 3 * leg, planner_phase[leg], switch_pos + 3 * leg,
+                                          swing_duration[leg], horizontal, cmd + 15 + 3 * leg, cmd + 27 + 3 * leg, cmd + 39 + 3 * leg,
+                                          foot_base_des + 3 * leg, q_des + 3 * leg, qd_des + 3 * leg);
+    }
+}
+extern "C" void qr_emul_gait_update(float t, const float* cfg, float thr, const int32_t* contacts, int stop, int advanced,
+                                    int32_t* istate, float* fstate, float* out, int32_t* allow) {
+    qr_gait_update(t, cfg, thr, contacts, stop, advanced, istate, fstate, out, allow);
+}
+
+// the fused solve with its post-processing epilogue (qr_gpu_mpc_solve_batch_ex)
+extern "C" int qr_emul_mpc_solve_batch_ex(const qr_mpc_params* P, int batch, const float* p, const float* v, const float* quat,
+                                          const float* w, const float* r_feet, const float* rpy, const float* traj,
+                                          const float* gait, float hip, float upper, float lower, const float* q,
+                                          float* grf_out, float* ff_out, float* tau_out, float* cmd_io, int32_t* status_out) {
+    QrMpcArgs A;
+    memset(&A, 0, sizeof(A));
+    A.P = *P; A.opt = emul_default_options(); A.batch = batch;
+    A.p = p; A.v = v; A.quat = quat; A.w = w; A.r_feet = r_feet; A.rpy = rpy; A.traj = traj; A.gait = gait;
+    A.grf_out = grf_out; A.status_out = status_out;
+    A.ep_q = q; A.ep_ff = ff_out; A.ep_tau = tau_out; A.ep_cmd = cmd_io; A.ep_hip = hip; A.ep_upper = upper; A.ep_lower = lower;
+    for (int i = 0; i < batch; ++i) {
+        A.nfcap = class_cap_of(gait + (size_t)i * 4 * P->horizon, P->f_max, P->horizon);
+        EmulTeam team(A.nfcap, P->horizon);
+        qr_mpc_solve_problem<128>(A, i, team.S);
+    }
+    return 0;
 }

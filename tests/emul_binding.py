@@ -157,6 +157,20 @@ def small_qp(self, G, g0, Cm, c0):
     return x, st, it.value
 
 
+def solve_ex(self, P, batch, robot, q, cmd):
+    """The fused solve with the leg-force / torque / Fr_des epilogue: dict(grf, f_ff, tau, cmd, status)."""
+    B = batch["p"].shape[0]
+    grf, ff, tau = (np.zeros((B, 12), np.float32) for _ in range(3))
+    st = np.zeros(B, np.int32)
+    q = np.ascontiguousarray(q, np.float32)
+    cmd = np.ascontiguousarray(cmd, np.float32)
+    self.lib.qr_emul_mpc_solve_batch_ex(C.byref(P), B, *[self._fp(batch[k]) for k in _KEYS], C.c_float(robot.hip_len),
+                                        C.c_float(robot.upper_len), C.c_float(robot.lower_len), self._fp(q), self._fp(grf),
+                                        self._fp(ff), self._fp(tau), self._fp(cmd), st.ctypes.data_as(C.POINTER(C.c_int)))
+    return dict(grf=grf, f_ff=ff, tau=tau, cmd=cmd, status=st)
+
+
+Emul.solve_ex = solve_ex
 Emul.small_qp = small_qp
 Emul.swing_bspline = swing_bspline
 Emul.foothold = foothold
