@@ -266,10 +266,7 @@ int qr_ref_mpc_inputs(int h, int num_horizon_l, float dt_mpc, const float* progr
         gg.legState[j] = leg_state ? leg_state[j] : LegState::STANCE;
         c.contactState[j] = contacts ? contacts[j] != 0 : false;
     }
-    c.FillTable();
-    if (!contacts) {   // the caller's table has no measured-contact override: undo :301-303 by recomputing row 0
-        for (int j = 0; j < 4; ++j) c.contactState[j] = false;
-    }
+    c.FillTable();   // (row 0 is always overwritten with contactState, :301-303: callers pass the contact flags)
     for (int k = 0; k < 4 * h; ++k) table_out[k] = c.mpcTable.d[k];
     if (traj_out) {
         c.rpyComp = Vec3<float>(init[0], init[1], 0.f);

@@ -73,7 +73,8 @@ def test_full_tick_chain_against_reference_builds(gpu, oracle, pkg, monkeypatch)
                                  allow=d_allow, early=d_early, swing_mask=d_mask)
     d_duty = dev(np.full((B, 4), duty, F32))
     gait = torch.empty((B, 4 * h), device="cuda"); traj = torch.empty((B, 12 * h), device="cuda")
-    gpu.mpc_inputs_batch_device(h, nhl, dt, d_pf, d_duty, d_early, None, dev(init), dev(pos[:, :2]), gait, traj, st)
+    contact_state = (1 - d_mask).to(torch.int32).contiguous()   # the legs the controllers treat as contacts this tick
+    gpu.mpc_inputs_batch_device(h, nhl, dt, d_pf, d_duty, d_early, contact_state, dev(init), dev(pos[:, :2]), gait, traj, st)
     foot_base = torch.empty((B, 12), device="cuda")
     gpu.leg_kinematics_batch_device(G, dev(q), None, foot_base, None, None, st)
     r_feet = torch.empty((B, 12), device="cuda")
@@ -93,7 +94,6 @@ def test_full_tick_chain_against_reference_builds(gpu, oracle, pkg, monkeypatch)
     gpu.foothold_heuristic_batch_device(fP, fd, foothold, planner_phase, st)
     gpu.swing_targets_batch_device(G, dev(pos), dev(quat), dev(v_world), foothold, planner_phase, dev(switch_pos), dev(swing_dur),
                                    d_mask, True, cmd, st)
-    contact_state = (1 - d_mask).to(torch.int32).contiguous()   # the WBC treats every non-swing leg as a contact
     tau = torch.empty((B, 12), dtype=torch.float64, device="cuda"); wst = torch.empty(B, dtype=torch.int32, device="cuda")
     gpu.wbc_solve_batch_device_f64(gpu.wbc_model_of(rb), dev(state), cmd, contact_state, tau, st, status=wst)
     torch.cuda.synchronize()
@@ -117,7 +117,7 @@ def test_full_tick_chain_against_reference_builds(gpu, oracle, pkg, monkeypatch)
         assert np.array_equal(g["pf"][i], ro[:4]) and np.array_equal(g["early"][i], (ls == 2).astype(np.int32))
         swing = (~(((ls == 1) & (ra == 1)) | (ls == 2))).astype(np.int32)
         assert np.array_equal(g["mask"][i], swing)
-        tab, trj = oracle.ref_mpc_inputs(h, nhl, dt, ro[:4], np.full(4, duty, F32), ls, None, init[i], pos[i, :2])
+        tab, trj = oracle.ref_mpc_inputs(h, nhl, dt, ro[:4], np.full(4, duty, F32), ls, 1 - swing, init[i], pos[i, :2])
         assert np.array_equal(g["gait"][i].reshape(h, 4), tab) and np.array_equal(g["traj"][i], trj)
         k = oracle.ref_leg_kinematics(rb, q[i])
         np.testing.assert_allclose(g["foot_base"][i], k["foot_base"], rtol=0, atol=3e-7)
