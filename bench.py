@@ -296,43 +296,68 @@ def bench_wbc_and_full_step(pkg, capi, torch, stream, with_cpu=False, fp64_peak=
                      "qrWholeBodyImpulseCtrl + QuadProg++ compiled from /root/reference (oracle/_ref/libqr_wbc_ref.so), "
                      "controller objects built once, one recomputing tick per robot (qr_wbc_locomotion_controller.cpp:108-134)")
         out["wbc"]["cpu_baseline"] = c
-    # full tick, batch 1024
+    # full tick, batch 1024: every stage through the C ABI, nothing touched by the host in between
     B, h, dt = 1024, 10, 0.03
     mb = pkg.synth.make_mpc_batch("lite3", h, dt, B, seed=11, gait="trot")
     wb = pkg.synth.make_wbc_batch("lite3", B, seed=12)
+    fh = pkg.synth.make_foothold_batch("lite3", B, seed=16)
     P = capi.params_of(robot, h, dt)
+    G = capi.leg_geometry_of(robot)
+    fP = capi.foothold_params_of(fh["params"])
     gt = pkg.robots.GAITS["trot"]
     rng = np.random.default_rng(13)
-    progress = np.mod(rng.uniform(0, 1, (B, 1)) + np.array(gt["offsets"])[None, :], 1.0).astype(np.float32)
-    duty = np.full((B, 4), gt["duty"], np.float32)
-    traj_init = np.zeros((B, 12), np.float32)
+    F32 = np.float32
+    duty, stance = F32(gt["duty"]), F32(gt["stance_duration"])
+    period = F32(stance / duty)
+    cfg = np.zeros((B, 4, 5), F32)
+    cfg[:, :, 0] = np.array(gt["offsets"], F32)
+    cfg[:, :, 1], cfg[:, :, 2], cfg[:, :, 3], cfg[:, :, 4] = period, duty, period - stance, duty
+    istate = np.ones((B, 20), np.int32); istate[:, 16:] = 0
+    fstate = np.zeros((B, 4), F32); fstate[:, 3] = 1.0
+    traj_init = np.zeros((B, 12), F32)
     traj_init[:, 2] = mb["rpy"][:, 2]; traj_init[:, 3:5] = mb["p"][:, :2]; traj_init[:, 5] = robot.body_height
     traj_init[:, 9] = 0.5
+    state_h = wb["state"].copy()
+    state_h[:, :4], state_h[:, 4:7] = mb["quat"], mb["p"]
     d = {k: dev(mb[k]) for k in KEYS}
-    d_prog, d_duty, d_init, d_xy = dev(progress), dev(duty), dev(traj_init), dev(mb["p"][:, :2])
+    d_time = dev(rng.uniform(0, 2, B).astype(F32))
+    d_cfg, d_i, d_f = dev(cfg.reshape(B, 20)), dev(istate), dev(fstate)
+    d_pf, d_np, d_sr = (torch.zeros((B, 4), device="cuda") for _ in range(3))
+    d_allow, d_early, d_mask, d_stance = (torch.empty((B, 4), dtype=torch.int32, device="cuda") for _ in range(4))
+    d_contacts = torch.ones((B, 4), dtype=torch.int32, device="cuda")
+    d_duty, d_init, d_xy = dev(np.full((B, 4), duty, F32)), dev(traj_init), dev(mb["p"][:, :2])
     o = dict(grf=torch.empty((B, 12), device="cuda"), status=torch.empty(B, dtype=torch.int32, device="cuda"),
              iters=torch.empty((B, 2), dtype=torch.int32, device="cuda"))
-    state, cmd, contact = dev(wb["state"]), dev(wb["cmd"]), dev(wb["contact"])
+    state, cmd = dev(state_h), dev(wb["cmd"])
     q = state[:, 13:25].contiguous()
-    tau_mpc = torch.empty((B, 12), device="cuda")
+    foot_base = torch.empty((B, 12), device="cuda")
+    tau_mpc, ff = torch.empty((B, 12), device="cuda"), torch.empty((B, 12), device="cuda")
     tau = torch.empty((B, 12), device="cuda")
     st = torch.empty(B, dtype=torch.int32, device="cuda")
-    sw_start, sw_end = dev(rng.uniform(-0.1, 0.1, (4 * B, 3)).astype(np.float32)), dev(rng.uniform(-0.1, 0.1, (4 * B, 3)).astype(np.float32))
-    sw_h, sw_ph = dev(np.full(4 * B, 0.08, np.float32)), dev(rng.uniform(0, 1, 4 * B).astype(np.float32))
-    sw_pos = torch.empty((4 * B, 3), device="cuda")
+    fd = {k: dev(v) for k, v in fh.items() if isinstance(v, np.ndarray)}
+    fd["swing_remain"], fd["norm_phase"], fd["allow_switch"], fd["swing_mask"], fd["foot_base"] = d_sr, d_np, d_allow, d_mask, foot_base
+    foothold, planner_phase = torch.zeros((B, 12), device="cuda"), torch.zeros((B, 4), device="cuda")
+    switch_pos = dev((np.array(robot.hip_positions)[None] + np.array([0, 0, -robot.body_height]) + rng.uniform(-0.06, 0.06, (B, 4, 3))).astype(F32).reshape(B, 12))
+    swing_dur = dev(cfg[:, :, 3].copy())
     nhl = pkg.synth.num_horizon_l(gt)
+    TICK_KERNELS = 9 + (4 * h + 7) // 8   # gait, table/trajectory, FK, lever arms, classify + fused classes, foothold, swing targets, WBC
 
     def tick():
-        capi.mpc_inputs_batch_device(h, nhl, dt, d_prog, d_duty, None, None, d_init, d_xy, d["gait"], d["traj"], stream)
-        capi.mpc_solve_batch_device(P, d, o, stream)
-        capi.mpc_leg_torque_batch_device(robot, d["quat"], q, o["grf"], None, tau_mpc, stream)
-        capi.swing_parabola_batch_device(sw_start, sw_end, sw_h, sw_ph, False, sw_pos, None, stream)
-        cmd[:, 51:63] = o["grf"]   # Fr_des of qrWbcCtrlData <- MPC forces (a torch copy kernel, not one of ours)
-        capi.wbc_solve_batch_device(M, state, cmd, contact, tau, stream, status=st)
+        capi.gait_update_batch_device(d_time, d_cfg, 0.1, d_contacts, None, False, d_i, d_f, d_pf, d_np, d_sr, stream,
+                                      allow=d_allow, early=d_early, swing_mask=d_mask, stance_mask=d_stance)
+        capi.mpc_inputs_batch_device(h, nhl, dt, d_pf, d_duty, d_early, d_stance, d_init, d_xy, d["gait"], d["traj"], stream)
+        capi.leg_kinematics_batch_device(G, q, None, foot_base, None, None, stream)
+        capi.mpc_lever_arms_batch_device(robot, d["quat"], foot_base, d["r_feet"], stream)
+        capi.mpc_solve_batch_device_ex(P, d, o, stream, robot, q=q, f_ff=ff, tau=tau_mpc, wbc_cmd=cmd)   # epilogue: f_ff, tau, Fr_des
+        capi.foothold_heuristic_batch_device(fP, fd, foothold, planner_phase, stream)
+        capi.swing_targets_batch_device(G, d["p"], d["quat"], d["v"], foothold, planner_phase, switch_pos, swing_dur, d_mask, True, cmd, stream)
+        capi.wbc_solve_batch_device(M, state, cmd, d_stance, tau, stream, status=st)
 
     ms = _time_ms(torch, tick, 20)
-    out["full_step"] = {"workload": "Lite3 trot h=10 dt=0.03: contact table + reference trajectory -> MPC -> leg torques, "
-                                    "swing parabola, WBIC (BASELINE configs[1]), batch 1024 on the device",
+    out["full_step"] = {"workload": "Lite3 trot h=10 dt=0.03, one control tick: gait phase -> contact table + reference trajectory -> leg FK -> "
+                                    "lever arms -> MPC with the fused leg-force / torque / Fr_des epilogue -> foothold -> swing targets -> WBIC "
+                                    "(BASELINE configs[1]), batch 1024 on the device, no host work between the stages",
+                        "kernels_per_tick": TICK_KERNELS,
                         "value": B / ms * 1e3, "unit": "robot ticks/s", "ms_per_step": ms,
                         "mpc_not_converged": int((o["status"] != 0).sum()), "wbc_status_nonzero": int((st != 0).sum())}
     if with_cpu:

@@ -253,11 +253,14 @@ int qr_gpu_swing_targets_batch(const qr_leg_geometry* geom, int batch, const flo
  *   allow_out [batch][4] or NULL  allowSwitchLegState
  *   early_out [batch][4] or NULL  legState == EARLY_CONTACT (the early_contact rows of qr_gpu_mpc_inputs_batch)
  *   swing_mask_out [batch][4] or NULL  the legs the swing-leg controller moves this tick (swingFootIds,
- *                         src/controllers/qr_swing_leg_controller.cpp:218-228) */
+ *                         src/controllers/qr_swing_leg_controller.cpp:218-228)
+ *   stance_mask_out [batch][4] or NULL  its complement: the contact_state rows of qr_gpu_wbc_solve_batch and the
+ *                         `contacts` rows (row 0 of the contact table) of qr_gpu_mpc_inputs_batch */
 int qr_gpu_gait_update_batch(int batch, const float* time, const float* cfg, float contact_threshold,
                              const int32_t* contacts, const int32_t* stop, int advanced_trot, int32_t* istate_io,
                              float* fstate_io, float* phase_full_io, float* norm_phase_io, float* swing_remain_io,
-                             int32_t* allow_out, int32_t* early_out, int32_t* swing_mask_out, void* cuda_stream);
+                             int32_t* allow_out, int32_t* early_out, int32_t* swing_mask_out, int32_t* stance_mask_out,
+                             void* cuda_stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Whole-body control

@@ -351,8 +351,9 @@ def swing_targets_batch_device(G: LegGeometry, base_pos, quat, v_world, foothold
 
 
 def gait_update_batch_device(time, cfg, contact_threshold: float, contacts, stop, advanced_trot: bool, istate, fstate,
-                             phase_full, norm_phase, swing_remain, stream_ptr: int, allow=None, early=None, swing_mask=None):
+                             phase_full, norm_phase, swing_remain, stream_ptr: int, allow=None, early=None, swing_mask=None,
+                             stance_mask=None):
     rc = lib().qr_gpu_gait_update_batch(time.shape[0], _vp(time), _vp(cfg), C.c_float(contact_threshold), _vp(contacts), _vp(stop),
                                         int(advanced_trot), _vp(istate), _vp(fstate), _vp(phase_full), _vp(norm_phase),
-                                        _vp(swing_remain), _vp(allow), _vp(early), _vp(swing_mask), C.c_void_p(stream_ptr))
+                                        _vp(swing_remain), _vp(allow), _vp(early), _vp(swing_mask), _vp(stance_mask), C.c_void_p(stream_ptr))
     _check(rc, "qr_gpu_gait_update_batch")

@@ -1334,7 +1334,7 @@ struct QrGaitRows {
     const int32_t *contacts, *stop;
     int32_t* istate;
     float *fstate, *phase_full, *norm_phase, *swing_remain;
-    int32_t *allow, *early, *swing_mask;
+    int32_t *allow, *early, *swing_mask, *stance_mask;
 };
 __global__ void qr_gait_update_kernel(int batch, float contact_threshold, int advanced_trot, const QrGaitRows R) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1358,7 +1358,9 @@ __global__ void qr_gait_update_kernel(int batch, float contact_threshold, int ad
         if (R.allow) R.allow[r4 + l] = al[l];
         if (R.early) R.early[r4 + l] = ls == 2;
         // the legs the swing controller moves (qr_swing_leg_controller.cpp:218-228)
-        if (R.swing_mask) R.swing_mask[r4 + l] = !((ls == 1 && al[l]) || ls == 2);
+        const int swing = !((ls == 1 && al[l]) || ls == 2);
+        if (R.swing_mask) R.swing_mask[r4 + l] = swing;
+        if (R.stance_mask) R.stance_mask[r4 + l] = !swing;
     }
 }
 
@@ -1439,7 +1441,8 @@ extern "C" int qr_gpu_swing_targets_batch(const qr_leg_geometry* geom, int batch
 extern "C" int qr_gpu_gait_update_batch(int batch, const float* time, const float* cfg, float contact_threshold,
                                         const int32_t* contacts, const int32_t* stop, int advanced_trot, int32_t* istate_io,
                                         float* fstate_io, float* phase_full_io, float* norm_phase_io, float* swing_remain_io,
-                                        int32_t* allow_out, int32_t* early_out, int32_t* swing_mask_out, void* cuda_stream) {
+                                        int32_t* allow_out, int32_t* early_out, int32_t* swing_mask_out, int32_t* stance_mask_out,
+                                        void* cuda_stream) {
     std::lock_guard<std::mutex> lk(g_mu);
     Ctx* cx = current_ctx();
     if (!cx) return QR_ECUDA;
@@ -1448,7 +1451,7 @@ extern "C" int qr_gpu_gait_update_batch(int batch, const float* time, const floa
     if (!time || !cfg || !contacts || !istate_io || !fstate_io || !phase_full_io || !norm_phase_io || !swing_remain_io)
         return fail(QR_EINVAL, "null pointer");
     QrGaitRows R{time, cfg, contacts, stop, istate_io, fstate_io, phase_full_io, norm_phase_io, swing_remain_io,
-                 allow_out, early_out, swing_mask_out};
+                 allow_out, early_out, swing_mask_out, stance_mask_out};
     qr_gait_update_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(batch, contact_threshold, advanced_trot, R);
     return launch_check("launch qr_gait_update_kernel");
 }

@@ -68,12 +68,11 @@ def test_full_tick_chain_against_reference_builds(gpu, oracle, pkg, monkeypatch)
     # ---------------- GPU tick
     d_i, d_f = dev(istate), dev(fstate)
     d_pf, d_np, d_sr = dev(phases[:, :4]), dev(phases[:, 4:8]), dev(phases[:, 8:])
-    d_allow, d_early, d_mask = (torch.empty((B, 4), dtype=torch.int32, device="cuda") for _ in range(3))
+    d_allow, d_early, d_mask, contact_state = (torch.empty((B, 4), dtype=torch.int32, device="cuda") for _ in range(4))
     gpu.gait_update_batch_device(dev(t_now), dev(cfg), 0.1, dev(contacts), None, False, d_i, d_f, d_pf, d_np, d_sr, st,
-                                 allow=d_allow, early=d_early, swing_mask=d_mask)
+                                 allow=d_allow, early=d_early, swing_mask=d_mask, stance_mask=contact_state)
     d_duty = dev(np.full((B, 4), duty, F32))
     gait = torch.empty((B, 4 * h), device="cuda"); traj = torch.empty((B, 12 * h), device="cuda")
-    contact_state = (1 - d_mask).to(torch.int32).contiguous()   # the legs the controllers treat as contacts this tick
     gpu.mpc_inputs_batch_device(h, nhl, dt, d_pf, d_duty, d_early, contact_state, dev(init), dev(pos[:, :2]), gait, traj, st)
     foot_base = torch.empty((B, 12), device="cuda")
     gpu.leg_kinematics_batch_device(G, dev(q), None, foot_base, None, None, st)
