@@ -193,7 +193,6 @@ QR_DEV void qr_gait_update(float current_time, const float* cfg, float contact_t
     int32_t* first = istate + 16;
     float time_since_reset = current_time;
     // ---- Schedule(currentTime), :211-247
-    bool scheduled_out = false;
     if (QR_A(fstate[0], cfg[1]) < time_since_reset) fstate[0] = time_since_reset;   // fullCyclePeriod[0] = cfg[5*0 + 1]
     time_since_reset = QR_S(time_since_reset, fstate[0]);
     for (int l = 0; l < 4; ++l) allow[l] = 1;
@@ -206,7 +205,6 @@ QR_DEV void qr_gait_update(float current_time, const float* cfg, float contact_t
             fstate[2] = QR_A(fstate[2], dt_);
             if (fstate[2] > fstate[3]) {
                 for (int l = 0; l < 4; ++l) allow[l] = 1;
-                scheduled_out = true;
             } else {
                 fstate[0] = QR_A(fstate[0], dt_);
             }
@@ -214,7 +212,6 @@ QR_DEV void qr_gait_update(float current_time, const float* cfg, float contact_t
             fstate[2] = 0.f;
         }
     }
-    (void)scheduled_out;
     // ---- Update, :131-207
     const int all_allowed = allow[0] + allow[1] + allow[2] + allow[3] == 4;
     for (int l = 0; l < 4; ++l) {

@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(qr_fused_nt(CAP), qr_fused_min_ctas(CAP)) qr_m
                  HSG ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(CAP) : nullptr,
                  KG ? A.k_global + (size_t)blockIdx.x * 9 * qr_ntri(CAP) : nullptr);
     S.Hc = A.hc_global ? A.hc_global + (size_t)blockIdx.x * 9 * qr_ntri(CAP) : nullptr;
+    S.Hc2 = (S.Hc && qr_coarse2_cap(CAP) > 0) ? S.Hc + 9 * qr_ntri(qr_coarse_cap(CAP)) : nullptr;   // ntri(3c/4) + ntri(9c/16) < ntri(c)
     qr_mpc_init_tables<NT>(S, CAP);
     // A.next == null (small batches): one launch, instances strided over the grid, no work lists.
     const int total = A.count ? *A.count : A.batch;
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(QR_LAT_NT, 1) qr_mpc_fused_latency_kernel(cons
                  A.hs_global ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr,
                  A.k_global ? A.k_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr);
     S.Hc = A.hc_global ? A.hc_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr;
+    S.Hc2 = (S.Hc && qr_coarse2_cap(A.nfcap) > 0) ? S.Hc + 9 * qr_ntri(qr_coarse_cap(A.nfcap)) : nullptr;
     qr_mpc_init_tables<NT>(S, A.nfcap);
     for (int prob = blockIdx.x; prob < A.batch; prob += gridDim.x) qr_mpc_solve_problem<NT>(A, prob, S);
 }
@@ -134,8 +136,12 @@ constexpr int QR_HSG_FROM_CAP = QR_HSG_FROM;
 QrFusedKernel fused_kernel_for(int cap) {
     switch (cap) {
 #define QR_CASE(C) case C: return qr_mpc_fused_kernel<C, (C >= QR_HSG_FROM), (C >= QR_KG_FROM_CAP)>;
+#ifdef QR_EXP_ONLY_CAP   // experiment builds (tools/exp_bench.py): one size class, seconds to compile
+        QR_CASE(QR_EXP_ONLY_CAP)
+#else
         QR_CASE(8) QR_CASE(16) QR_CASE(24) QR_CASE(32) QR_CASE(40) QR_CASE(48) QR_CASE(56) QR_CASE(64) QR_CASE(72)
         QR_CASE(96) QR_CASE(128)
+#endif
 #undef QR_CASE
         default: return nullptr;
     }
@@ -158,6 +164,7 @@ __global__ void __launch_bounds__(QR_NT) qr_qp_solve_kernel(const QrMpcArgs A) {
                  A.hs_global ? A.hs_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr,
                  A.k_global ? A.k_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr);
     S.Hc = A.hc_global ? A.hc_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr;
+    S.Hc2 = (S.Hc && qr_coarse2_cap(A.nfcap) > 0) ? S.Hc + 9 * qr_ntri(qr_coarse_cap(A.nfcap)) : nullptr;
     qr_mpc_init_tables<NT>(S, A.nfcap);
     for (int prob = blockIdx.x; prob < A.batch; prob += gridDim.x)
         qr_qp_solve_problem<NT>(A, prob, S);
@@ -590,6 +597,9 @@ int mpc_enqueue(Ctx& cx, const qr_mpc_params* P, const qr_qp_options* opt, int b
     size_t scratch_need = 0;
     for (int c = 0; c < nclass; ++c) {
         const int cap = class_cap(c, h);
+#ifdef QR_EXP_ONLY_CAP
+        if (cap != QR_EXP_ONLY_CAP) continue;
+#endif
         rc = launch_geometry(cx, fused_kernel_for(cap), cap, h, batch, &plan[c], class_hsg(cap), class_kg(cap), qr_fused_nt(cap));
         if (rc) return rc;
         if (plan[c].hsg != class_hsg(cap) || plan[c].kg != class_kg(cap))
@@ -614,6 +624,9 @@ int mpc_enqueue(Ctx& cx, const qr_mpc_params* P, const qr_qp_options* opt, int b
     // after the other on the stream.
     for (int c = nclass - 1; c >= 0 && e == cudaSuccess; --c) {
         A.nfcap = class_cap(c, h);
+#ifdef QR_EXP_ONLY_CAP
+        if (A.nfcap != QR_EXP_ONLY_CAP) continue;
+#endif
         bind_scratch(A, plan[c], A.nfcap, *lane);
         A.list = lists + (size_t)c * batch;
         A.count = counts + c;
@@ -916,7 +929,13 @@ extern "C" int qr_gpu_debug_profile(unsigned long long* out64) {
 
 namespace {
 
-constexpr int QR_WBC_NT = 32;   // one warp per robot
+// Threads per robot.  Shared memory (36.8 KB per robot) fixes six robots in flight per SM whatever the team size, so the
+// team size sets the number of warps that hide each other's latency: measured on B200 (Lite3, 65536 robots, outputs
+// bit-identical) 32 / 64 / 96 / 128 threads -> 4.63 / 5.90 / 5.23 / 5.06 M robots/s (batch 1024: 4.47 / 5.63 / 6.29 / 6.01).
+#ifndef QR_WBC_NT_DEF
+#define QR_WBC_NT_DEF 64
+#endif
+constexpr int QR_WBC_NT = QR_WBC_NT_DEF;
 
 __global__ void __launch_bounds__(QR_WBC_NT) qr_wbc_kernel(const QrWbcArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];

@@ -48,6 +48,12 @@ QR_HD size_t qr_fallback_doubles(int nfcap) { return (size_t)46 * nfcap + 8; }
 // The coarse problem pairs consecutive foot-steps of a leg; it is only used when that removes at least a quarter
 // of the foot-steps.
 QR_HD int qr_coarse_cap(int nfcap) { return (3 * nfcap + 3) / 4; }
+// A second level (pairs of pairs) in front of it pays only for long horizons, where a factorisation of the first
+// level is itself expensive: workspaces above QR_COARSE2_MIN_CAP foot-steps carry its vectors.
+#ifndef QR_COARSE2_MIN_CAP
+#define QR_COARSE2_MIN_CAP 48
+#endif
+QR_HD int qr_coarse2_cap(int nfcap) { return nfcap >= QR_COARSE2_MIN_CAP ? (3 * qr_coarse_cap(nfcap) + 3) / 4 : 0; }
 QR_HD size_t qr_kbytes(int nfcap) {
     size_t kb = (size_t)9 * qr_ntri(nfcap) * sizeof(double);
     return kb > sizeof(QrCondenseTables) ? kb : ((sizeof(QrCondenseTables) + 15) & ~(size_t)15);
@@ -60,6 +66,8 @@ QR_HD size_t qr_mpc_smem_bytes(int nfcap, int horizon, bool hs_in_smem = true, b
                        : ((sizeof(QrCondenseTables) + 15) & ~(size_t)15);   // the tables alone
     bytes += (size_t)(9 + 9 + 6 * 3 + 1) * nfcap * sizeof(double) + 8 * sizeof(double);
     bytes += (size_t)(3 + 1) * qr_coarse_cap(nfcap) * sizeof(double);   // coarse problem: g, ub
+    bytes += (size_t)(3 + 1) * qr_coarse2_cap(nfcap) * sizeof(double);  // second coarse level (long horizons only): g, ub
+    bytes += (size_t)(3 + 1 + 2) * qr_coarse_cap(nfcap) * sizeof(int);  // .. descriptors of the first level, grp2, gmem2
     bytes += (size_t)(16 * horizon + 32) * sizeof(float);          // staged traj + gait + state rows
     bytes += (size_t)(3 * nfcap + (nfcap + 1) + 3 * nfcap + 2 * 4 * horizon + 8 + 24 + nfcap + 3 * nfcap) * sizeof(int);   // .. + grp, gmem
     bytes += (size_t)((qr_ntri(nfcap) + 1) / 2) * sizeof(int);         // tri (unsigned short, padded to ints)
@@ -82,6 +90,13 @@ struct QrMpcSmem {
     double* ubc;   // [coarse cap]
     int* grp;      // [nfcap] coarse foot-step of every stance foot-step
     int* gmem;     // [2*nfcap] members of every coarse foot-step (second = -1 for a single)
+    // second coarse level (pairs of first-level foot-steps), only when qr_coarse2_cap(nfcap) > 0
+    double* Hc2;   // global, behind Hc
+    double* gc2;   // [3*coarse2 cap]
+    double* ubc2;  // [coarse2 cap]
+    int* cdesc;    // [3*coarse cap] leg, first step, last step of every first-level foot-step
+    int* grp2;     // [coarse cap]
+    int* gmem2;    // [2*coarse cap]
 };
 
 QR_DEV void qr_mpc_carve(QrMpcSmem& S, unsigned char* base, int nfcap, int horizon, double* fallback,
@@ -106,7 +121,10 @@ QR_DEV void qr_mpc_carve(QrMpcSmem& S, unsigned char* base, int nfcap, int horiz
     W.ubz = d; d += nfcap;
     S.gc = d; d += 3 * qr_coarse_cap(nfcap);
     S.ubc = d; d += qr_coarse_cap(nfcap);
+    S.gc2 = d; d += 3 * qr_coarse2_cap(nfcap);
+    S.ubc2 = d; d += qr_coarse2_cap(nfcap);
     S.Hc = nullptr;
+    S.Hc2 = nullptr;
     S.scal = d; d += 8;
     // fixed-size integer tables first, the horizon-dependent rows last: with a compile-time capacity every
     // pointer of the solver is then a constant offset from the shared-memory base
@@ -120,6 +138,9 @@ QR_DEV void qr_mpc_carve(QrMpcSmem& S, unsigned char* base, int nfcap, int horiz
     W.hist = ip; ip += 24 + nfcap;
     S.grp = ip; ip += nfcap;
     S.gmem = ip; ip += 2 * nfcap;
+    S.cdesc = ip; ip += 3 * qr_coarse_cap(nfcap);
+    S.grp2 = ip; ip += qr_coarse_cap(nfcap);
+    S.gmem2 = ip; ip += 2 * qr_coarse_cap(nfcap);
     W.tri = reinterpret_cast<unsigned short*>(ip);
     ip += (qr_ntri(nfcap) + 1) / 2;
     float* f = reinterpret_cast<float*>(ip);
@@ -235,14 +256,50 @@ QR_DEV void qr_mpc_condense_to_work(const QrMpcArgs& A, QrMpcSmem& S) {
 // full-size iteration from its pair's active rows (qr_qp_solve, stage 0).  The full-size iteration then needs 4-5
 // rounds instead of 7-8, all of them on the small final systems, and still ends only on verified KKT conditions --
 // the prediction changes the starting guess, never the result.  This routine builds the coarse problem.
+// H_c = T'HT by 3x3 blocks (block-packed like W.Hs, diagonal blocks in full), g_c = T'g, ub_c for the ng tied foot-steps
+// whose members gmem lists.  The four loads of an entry are issued together (a missing second member reads the first
+// one's entry with weight 0): the fine Hessian lives in L2, so the latency of a dependent or branchy load sequence
+// would dominate this phase.
 template <int NT>
-QR_DEV QrCoarse qr_mpc_build_coarse(QrMpcSmem& S, const qr_qp_options& opt, int max_rounds) {
+QR_DEV void qr_coarse_reduce(const unsigned short* tri, const double* __restrict__ Hs, const double* g, const double* ubz,
+                             int ng, const int* gmem, double* __restrict__ Hc, double* gc, double* ubc) {
+    QR_FOR(idx, 9 * qr_ntri(ng)) {
+        const int b = idx / 9, e = idx - 9 * b;
+        const int code = tri[b];
+        const int Ac = code >> 8, Bc = code & 255;
+        const int r = e / 3, c = e - 3 * r;
+        const int f0 = gmem[2 * Ac], f1r = gmem[2 * Ac + 1], g0 = gmem[2 * Bc], g1r = gmem[2 * Bc + 1];
+        const int f1 = f1r < 0 ? f0 : f1r, g1 = g1r < 0 ? g0 : g1r;
+        const double wf = f1r < 0 ? 0.0 : 1.0, wg = g1r < 0 ? 0.0 : 1.0;
+        const int erc = 3 * r + c, ecr = 3 * c + r;
+        const double v00 = f0 >= g0 ? Hs[qr_blk(f0, g0) + erc] : Hs[qr_blk(g0, f0) + ecr];
+        const double v01 = f0 >= g1 ? Hs[qr_blk(f0, g1) + erc] : Hs[qr_blk(g1, f0) + ecr];
+        const double v10 = f1 >= g0 ? Hs[qr_blk(f1, g0) + erc] : Hs[qr_blk(g0, f1) + ecr];
+        const double v11 = f1 >= g1 ? Hs[qr_blk(f1, g1) + erc] : Hs[qr_blk(g1, f1) + ecr];
+        Hc[idx] = (v00 + wg * v01) + wf * (v10 + wg * v11);
+    }
+    QR_FOR(i, 3 * ng) {
+        const int gidx = i / 3, a = i - 3 * gidx;
+        const int f = gmem[2 * gidx], f2 = gmem[2 * gidx + 1];
+        gc[i] = g[3 * f + a] + (f2 >= 0 ? g[3 * f2 + a] : 0.0);
+        if (a == 0) ubc[gidx] = ubz[f];
+    }
+    QR_SYNC();
+}
+
+template <int NT>
+QR_DEV void qr_mpc_build_coarse(QrMpcSmem& S, const qr_qp_options& opt, int max_rounds, QrCoarse* C) {
     QrQpWork& W = S.W;
     const int nf = W.nf;
-    QrCoarse C;
-    C.ng = 0; C.Hs = S.Hc; C.g = S.gc; C.ubz = S.ubc; C.grp = S.grp;
-    C.max_rounds = max_rounds > 0 ? max_rounds : QR_COARSE_MAX_ROUNDS;
-    if (!S.Hc || nf < 8 || (opt.flags & QR_QP_NO_PREDICTION)) return C;
+    C[0].ng = 0; C[0].Hs = S.Hc; C[0].g = S.gc; C[0].ubz = S.ubc; C[0].grp = S.grp;
+    C[0].max_rounds = max_rounds > 0 ? max_rounds : QR_COARSE_MAX_ROUNDS;
+    C[1].ng = 0; C[1].Hs = S.Hc2; C[1].g = S.gc2; C[1].ubz = S.ubc2; C[1].grp = S.grp2;
+    C[1].max_rounds = C[0].max_rounds;
+    if (!S.Hc || nf < 8 || (opt.flags & QR_QP_NO_PREDICTION)) return;
+    const bool want2 = S.Hc2 != nullptr && nf >= QR_COARSE2_MIN_CAP - 7;
+    // Pairing: consecutive foot-steps of one leg with the same force cap are tied to one force; a foot-step that finds
+    // no partner stays single.  The second level pairs the first level's foot-steps by the same rule (a first-level
+    // foot-step covers the steps first..last of its leg).
     QR_THREADS(t) {
         if (t == 0) {
             int open[4] = {-1, -1, -1, -1}, last[4] = {-9, -9, -9, -9};
@@ -252,53 +309,51 @@ QR_DEV QrCoarse qr_mpc_build_coarse(QrMpcSmem& S, const qr_qp_options& opt, int 
                 if (open[leg] >= 0 && last[leg] == step - 1 && W.ubz[S.gmem[2 * open[leg]]] == W.ubz[s]) {
                     S.grp[s] = open[leg];
                     S.gmem[2 * open[leg] + 1] = s;
+                    if (want2) S.cdesc[3 * open[leg] + 2] = step;
                     open[leg] = -1;
                 } else {
                     S.grp[s] = ng;
                     S.gmem[2 * ng] = s;
                     S.gmem[2 * ng + 1] = -1;
+                    if (want2) { S.cdesc[3 * ng] = leg; S.cdesc[3 * ng + 1] = step; S.cdesc[3 * ng + 2] = step; }
                     open[leg] = ng;
                     ++ng;
                 }
                 last[leg] = step;
             }
             S.misc[2] = ng;
+            int ng2 = 0;
+            if (want2 && 4 * ng <= 3 * nf) {
+                for (int l = 0; l < 4; ++l) { open[l] = -1; last[l] = -9; }
+                for (int s = 0; s < ng; ++s) {
+                    const int leg = S.cdesc[3 * s], first = S.cdesc[3 * s + 1], lst = S.cdesc[3 * s + 2];
+                    const double ub = W.ubz[S.gmem[2 * s]];
+                    if (open[leg] >= 0 && last[leg] == first - 1 && W.ubz[S.gmem[2 * S.gmem2[2 * open[leg]]]] == ub) {
+                        S.grp2[s] = open[leg];
+                        S.gmem2[2 * open[leg] + 1] = s;
+                        open[leg] = -1;
+                    } else {
+                        S.grp2[s] = ng2;
+                        S.gmem2[2 * ng2] = s;
+                        S.gmem2[2 * ng2 + 1] = -1;
+                        open[leg] = ng2;
+                        ++ng2;
+                    }
+                    last[leg] = lst;
+                }
+            }
+            S.misc[3] = ng2;
         }
     }
     QR_SYNC();
-    const int ng = S.misc[2];
-    if (4 * ng > 3 * nf) return C;   // hardly anything to pair
-    // H_c = T'HT by 3x3 blocks (block-packed like W.Hs, diagonal blocks in full), g_c = T'g.  The four loads of an
-    // entry are issued together (a missing second member reads the first one's entry with weight 0): W.Hs lives in
-    // L2, so the latency of a dependent or branchy load sequence would dominate this phase.
-    {
-        const double* __restrict__ Hs = W.Hs;
-        double* __restrict__ Hc = S.Hc;
-        QR_FOR(idx, 9 * qr_ntri(ng)) {
-            const int b = idx / 9, e = idx - 9 * b;
-            const int code = W.tri[b];
-            const int Ac = code >> 8, Bc = code & 255;
-            const int r = e / 3, c = e - 3 * r;
-            const int f0 = S.gmem[2 * Ac], f1r = S.gmem[2 * Ac + 1], g0 = S.gmem[2 * Bc], g1r = S.gmem[2 * Bc + 1];
-            const int f1 = f1r < 0 ? f0 : f1r, g1 = g1r < 0 ? g0 : g1r;
-            const double wf = f1r < 0 ? 0.0 : 1.0, wg = g1r < 0 ? 0.0 : 1.0;
-            const int erc = 3 * r + c, ecr = 3 * c + r;
-            const double v00 = f0 >= g0 ? Hs[qr_blk(f0, g0) + erc] : Hs[qr_blk(g0, f0) + ecr];
-            const double v01 = f0 >= g1 ? Hs[qr_blk(f0, g1) + erc] : Hs[qr_blk(g1, f0) + ecr];
-            const double v10 = f1 >= g0 ? Hs[qr_blk(f1, g0) + erc] : Hs[qr_blk(g0, f1) + ecr];
-            const double v11 = f1 >= g1 ? Hs[qr_blk(f1, g1) + erc] : Hs[qr_blk(g1, f1) + ecr];
-            Hc[idx] = (v00 + wg * v01) + wf * (v10 + wg * v11);
-        }
+    const int ng = S.misc[2], ng2 = S.misc[3];
+    if (4 * ng > 3 * nf) return;   // hardly anything to pair
+    qr_coarse_reduce<NT>(W.tri, W.Hs, W.g, W.ubz, ng, S.gmem, S.Hc, S.gc, S.ubc);
+    C[0].ng = ng;
+    if (ng2 > 0 && 4 * ng2 <= 3 * ng) {
+        qr_coarse_reduce<NT>(W.tri, S.Hc, S.gc, S.ubc, ng2, S.gmem2, S.Hc2, S.gc2, S.ubc2);
+        C[1].ng = ng2;
     }
-    QR_FOR(i, 3 * ng) {
-        const int gidx = i / 3, a = i - 3 * gidx;
-        const int f = S.gmem[2 * gidx], f2 = S.gmem[2 * gidx + 1];
-        S.gc[i] = W.g[3 * f + a] + (f2 >= 0 ? W.g[3 * f2 + a] : 0.0);
-        if (a == 0) S.ubc[gidx] = W.ubz[f];
-    }
-    QR_SYNC();
-    C.ng = ng;
-    return C;
 }
 
 // Scatter the stance solution into the 12h force vector (swing foot-steps are exactly zero).
@@ -364,9 +419,10 @@ QR_DEV void qr_mpc_solve_problem(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
     if (status == 0) {
         qr_mpc_condense_to_work<NT>(A, S);
         QR_PROF(21);
-        const QrCoarse C = qr_mpc_build_coarse<NT>(S, A.opt, A.coarse_rounds);
+        QrCoarse C[2];
+        qr_mpc_build_coarse<NT>(S, A.opt, A.coarse_rounds, C);
         QR_PROF(23);
-        status = qr_qp_solve<NT>(S.W, A.opt, &it, &rounds, &x, &C QR_PROF_PASS);
+        status = qr_qp_solve<NT>(S.W, A.opt, &it, &rounds, &x, C QR_PROF_PASS);
         status = qr_result_status<NT>(S, x, status);
     }
     qr_mpc_scatter<NT>(A, prob, S, x, status, it, rounds);
@@ -438,8 +494,9 @@ QR_DEV void qr_qp_solve_problem(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
         QR_FOR(i, 3 * nf) S.W.g[i] = (double)g[3 * S.fs[i / 3] + i % 3];
         QR_SYNC();
         QR_PROF_DECL;
-        const QrCoarse C = qr_mpc_build_coarse<NT>(S, A.opt, A.coarse_rounds);
-        status = qr_qp_solve<NT>(S.W, A.opt, &it, &rounds, &x, &C QR_PROF_PASS);
+        QrCoarse C[2];
+        qr_mpc_build_coarse<NT>(S, A.opt, A.coarse_rounds, C);
+        status = qr_qp_solve<NT>(S.W, A.opt, &it, &rounds, &x, C QR_PROF_PASS);
         status = qr_result_status<NT>(S, x, status);
     }
     qr_mpc_scatter<NT>(A, prob, S, x, status, it, rounds);

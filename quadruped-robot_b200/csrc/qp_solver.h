@@ -181,6 +181,19 @@ QR_DEV void qr_inv3_sym(double a, double b, double c, double d, double e, double
 // Dinv_{K+1}; that block is never written back.  The right-hand side is treated as one more block
 // row: y_J -= W_JK (Dinv_K y_K).  On exit: off-diagonal tiles hold W = L D (unscaled columns),
 // W.Dinv the pivot inverses, and W.wv = L^{-1} rhs.
+// Device: teams of at least this many threads factorise with one lane per tile ROW instead of one per tile (see
+// qr_ldl_factor).  Measured on B200 (A1 trot, 65536 instances): the row form issues 1.6x the instructions of the
+// tile form in the factorisation (21 loads per 18 DFMA instead of 33 per 54), which costs the 96-thread throughput
+// kernels 10 % (4.12 -> 3.70 M QP/s: at six CTAs per SM they are bound by issued instructions, not by the latency of a
+// step), while the kernels that run ONE 256-thread CTA per SM -- the latency kernel and the long-horizon size
+// classes -- are bound by the latency of a step and gain from it.
+#ifndef QR_LDL_ROWSPLIT_MIN_NT
+#define QR_LDL_ROWSPLIT_MIN_NT 256
+#endif
+#ifndef QR_LDL_ROWSPLIT_MAX_NB
+#define QR_LDL_ROWSPLIT_MAX_NB 24   // larger systems (long horizons): back to the tile form (h = 30: 165 k QP/s against 138 k with rows)
+#endif
+
 template <int NT>
 QR_DEV void qr_ldl_factor(QrQpWork& W, int nb, int with_rhs QR_PROF_ARG) {
     double* K = W.K;
@@ -192,6 +205,64 @@ QR_DEV void qr_ldl_factor(QrQpWork& W, int nb, int with_rhs QR_PROF_ARG) {
         }
     }
     QR_SYNC();
+#if defined(QR_ON_DEVICE)
+    if (NT >= QR_LDL_ROWSPLIT_MIN_NT && nb <= QR_LDL_ROWSPLIT_MAX_NB) {
+    // Device: one lane per tile ROW.  With the coarse prediction in front, most factorisations have 9..17 block columns
+    // and most of their steps fewer tiles than the team has lanes, so a step costs the latency of one item, not its
+    // flops: a row (18 DFMA, 21 loads) is a third of a tile (54 DFMA, 33 loads), three times as many lanes take part,
+    // and the warp instructions of a step cover three times fewer tiles' worth of work each.  The three rows of the
+    // next pivot block sit on lanes 0..2 of warp 0; lane 0 gathers them by shuffle and inverts the block one step ahead
+    // as before.  Every entry is the same expression as in the tile form below (host emulation), evaluated once.
+    for (int Kc = 0; Kc < nb; ++Kc) {
+        const int nrem = nb - Kc - 1;
+        const int ntile = (nrem * (nrem + 1)) / 2;
+        const int kc0 = qr_kcol(nb, Kc), kc1 = qr_kcol(nb, Kc + 1);
+        const double* Di = W.Dinv + 9 * Kc;
+        const int nitem = 3 * ntile + (with_rhs ? 3 * nrem : 0);
+        const double d0 = Di[0], d1 = Di[1], d2 = Di[2], d4 = Di[4], d5 = Di[5], d8 = Di[8];
+        for (int base = 0; base < nitem; base += NT) {
+            const int item = base + (int)threadIdx.x;
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+            double* dst = nullptr;
+            if (item < 3 * ntile) {
+                const int tile = item / 3, q = item - 3 * tile;
+                const int code = W.tri[ntile - 1 - tile];
+                const int I = nb - 1 - (code & 255), J = nb - 1 - (code >> 8);
+                const double* wi = K + 9 * (kc0 + (I - Kc)) + 3 * q;
+                const double* wj = K + 9 * (kc0 + (J - Kc));
+                double* a = K + 9 * (kc1 + tile) + 3 * q;
+                const double w0 = wi[0], w1 = wi[1], w2 = wi[2];
+                const double t0 = w0 * d0 + w1 * d1 + w2 * d2;
+                const double t1 = w0 * d1 + w1 * d4 + w2 * d5;
+                const double t2 = w0 * d2 + w1 * d5 + w2 * d8;
+                r0 = a[0] - (t0 * wj[0] + t1 * wj[1] + t2 * wj[2]);
+                r1 = a[1] - (t0 * wj[3] + t1 * wj[4] + t2 * wj[5]);
+                r2 = a[2] - (t0 * wj[6] + t1 * wj[7] + t2 * wj[8]);
+                if (tile != 0) dst = a;   // tile 0 = the next pivot block (Kc+1, Kc+1): consumed below, never written back
+            } else if (item < nitem) {
+                const int j = item - 3 * ntile, Jb = j / 3, q = j - 3 * Jb;
+                const int J = Kc + 1 + Jb;
+                const double y0 = y[3 * Kc], y1 = y[3 * Kc + 1], y2 = y[3 * Kc + 2];
+                const double t0 = d0 * y0 + d1 * y1 + d2 * y2;
+                const double t1 = d1 * y0 + d4 * y1 + d5 * y2;
+                const double t2 = d2 * y0 + d5 * y1 + d8 * y2;
+                const double* wj = K + 9 * (kc0 + (J - Kc)) + 3 * q;
+                y[3 * J + q] -= wj[0] * t0 + wj[1] * t1 + wj[2] * t2;
+            }
+            if (base == 0 && threadIdx.x < 32 && ntile > 0) {   // warp 0, first pass: lanes 0..2 hold the pivot rows
+                const double p10 = __shfl_sync(0xffffffffu, r0, 1), p11 = __shfl_sync(0xffffffffu, r1, 1);
+                const double p20 = __shfl_sync(0xffffffffu, r0, 2), p21 = __shfl_sync(0xffffffffu, r1, 2);
+                const double p22 = __shfl_sync(0xffffffffu, r2, 2);
+                if (threadIdx.x == 0) qr_inv3_sym(r0, p10, p20, p11, p21, p22, W.Dinv + 9 * (Kc + 1));
+            }
+            if (dst) { dst[0] = r0; dst[1] = r1; dst[2] = r2; }
+        }
+        QR_SYNC();
+        QR_PROF(11);
+    }
+    return;
+    }
+#endif
     for (int Kc = 0; Kc < nb; ++Kc) {
         const int nrem = nb - Kc - 1;
         const int ntile = (nrem * (nrem + 1)) / 2;
@@ -938,7 +1009,7 @@ struct QrCoarse {
 // Full solve on a prepared workspace (Hs, g, ubz, mu_ set).  Result in W.xn (verified) or W.x.
 // Returns the per-instance status code of qr_gpu.h.
 //
-// Stages: [0: the iteration on the coarse problem, whose active rows every foot-step inherits] -> 1: the iteration on
+// Stages: [-1, 0: the iteration on the coarse problems, whose active rows every foot-step of the next level inherits] -> 1: the iteration on
 // the full-size problem (cold, or from the inherited guess) -> on failure 2: interior point to identify the active
 // set (tightening the tolerance once if the verification still does not settle) and 3: the same verification from
 // its guess.  Written as one loop around a single qr_active_set call site so that the (force-inlined) iteration is
@@ -954,22 +1025,30 @@ QR_DEV int qr_qp_solve(QrQpWork& W, const qr_qp_options& opt, int* ipm_iters, in
     double* const hs_full = W.Hs;
     double* const g_full = W.g;
     double* const ubz_full = W.ubz;
-    int stage = (C && C->ng > 0) ? 0 : 1;
+    // stages -1 / 0: the coarse levels C[1] (coarsest, optional) and C[0]; every level starts from the active rows
+    // inherited from the level before it
+    int stage = 1;
+    if (C && C[0].ng > 0) stage = (C[1].ng > 0) ? -1 : 0;
     int mode = 1, attempt = 0;
     double tol = opt.ipm_tol;
     for (;;) {
         int maxr = opt.max_as_rounds;
-        if (stage == 0) { W.nf = C->ng; W.Hs = C->Hs; W.g = C->g; W.ubz = C->ubz; maxr = C->max_rounds; }
-        else if (stage == 3) { mode = 0; maxr = opt.max_polish_rounds; }
+        if (stage <= 0) {
+            const QrCoarse& L = C[-stage];
+            W.nf = L.ng; W.Hs = L.Hs; W.g = L.g; W.ubz = L.ubz; maxr = L.max_rounds;
+        } else if (stage == 3) { mode = 0; maxr = opt.max_polish_rounds; }
         const int rounds = qr_active_set<NT>(W, opt, &ok, mode, maxr QR_PROF_PASS);
-        if (stage == 0) {
-            // every foot-step inherits its tied foot-step's active rows (through W.flag: rewritten in place)
+        if (stage <= 0) {
+            // every foot-step of the next finer level inherits its tied foot-step's active rows (through W.flag:
+            // rewritten in place)
+            const int* grp = C[-stage].grp;
+            const int n_fine = (stage == -1) ? C[0].ng : nf_full;
             W.nf = nf_full; W.Hs = hs_full; W.g = g_full; W.ubz = ubz_full;
-            QR_FOR(f, nf_full) W.flag[f] = W.act[C->grp[f]];
+            QR_FOR(f, n_fine) W.flag[f] = W.act[grp[f]];
             QR_SYNC();
-            QR_FOR(f, nf_full) W.act[f] = W.flag[f];
+            QR_FOR(f, n_fine) W.act[f] = W.flag[f];
             QR_SYNC();
-            stage = 1; mode = 2;
+            ++stage; mode = 2;
             continue;
         }
         *as_rounds += rounds;

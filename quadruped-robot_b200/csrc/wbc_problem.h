@@ -147,7 +147,7 @@ template <int NT> QR_DEV void tm_copy(double* D, const double* S, int n) { QR_FO
 // inverted by Gauss-Jordan and the bound sigma_min^2 >= 1 / ||(J J')^-1||_F certifies the rank decision with a
 // 10x margin.  Anything closer to the threshold (or singular, or non-finite) takes the Jacobi SVD below, so the
 // thresholding semantics of the reference are kept exactly where they matter.  The SVD was 63 % of the kernel.
-template <int NT> QR_DEV void tm_inverse_spd(QrWbcWork& W, double* A, int n);
+template <int NT> QR_DEV void tm_inverse_spd(QrWbcWork& W, const double* src0, double* A, double* tmp, int n);
 template <int NT>
 QR_DEV void tm_pinv(QrWbcWork& W, double* out, const double* J, int m, int n, double thr, int sym_psd = 0) {
     double* B = W.svdB;   // n x m
@@ -170,7 +170,7 @@ QR_DEV void tm_pinv(QrWbcWork& W, double* out, const double* J, int m, int n, do
             }
         }
         QR_SYNC();
-        tm_inverse_spd<NT>(W, Gi, m);
+        tm_inverse_spd<NT>(W, Gi, Gi, B, m);   // svdB is free until the Jacobi fallback below
         int bad = 0;
         double fro = 0.0;
         QR_THREADS(t) {
@@ -243,31 +243,40 @@ QR_DEV void tm_pinv(QrWbcWork& W, double* out, const double* J, int m, int n, do
 // In-place inverse of a symmetric positive definite n x n matrix by Gauss-Jordan without pivoting
 // (GetModelRes: Ainv = A.inverse(), qr_wholebody_impulse_ctrl.cpp:50-58).
 template <int NT>
-QR_DEV void tm_inverse_spd(QrWbcWork& W, double* A, int n) {
+QR_DEV void tm_inverse_spd(QrWbcWork& W, const double* src0, double* A, double* tmp, int n) {
     if (n == 3) {   // task-sized blocks: adjugate, one phase
         double o[9];
         QR_THREADS(t) {
             if (t == 0) {
-                qr_inv3_sym(A[0], A[3], A[6], A[4], A[7], A[8], o);
+                qr_inv3_sym(src0[0], src0[3], src0[6], src0[4], src0[7], src0[8], o);
                 for (int e = 0; e < 9; ++e) A[e] = o[e];
             }
         }
         QR_SYNC();
         return;
     }
+    // Gauss-Jordan without pivoting (symmetric positive definite input), ONE barrier per pivot: step k reads the matrix
+    // of step k-1 from one buffer and writes its own into the other, so the pivot row and column need no staging
+    // phase of their own (the in-place form needed two barriers per pivot; the 18 + 6..12 + 6 pivots of a tick were
+    // 19 % of the kernel).  Every entry is the same expression as before: results are bit-identical.
+    const double* s = src0;
+    double* d = (n & 1) ? A : tmp;   // after n steps the result sits in A ...
+    if (s == d) d = tmp;              // ... unless an in-place call with odd n starts on A: copied back below
     for (int k = 0; k < n; ++k) {
-        QR_FOR(c, n) {
-            const double akk = A[k * n + k];
-            const double piv = akk > 1e-300 ? qr_rcp_pos(akk) : 1.0 / akk;   // positive pivots: Newton reciprocal
-            W.rowbuf[c] = (c == k ? 1.0 : A[k * n + c]) * piv;
-            W.colbuf[c] = A[c * n + k];
-        }
-        QR_SYNC();
+        const double akk = s[k * n + k];
+        const double piv = akk > 1e-300 ? qr_rcp_pos(akk) : 1.0 / akk;   // positive pivots: Newton reciprocal (once per thread and step)
         QR_FOR(idx, n * n) {
             const int i = idx / n, c = idx - i * n;
-            if (i == k) A[idx] = W.rowbuf[c];
-            else A[idx] = (c == k ? 0.0 : A[idx]) - W.colbuf[i] * W.rowbuf[c];
+            const double rowc = (c == k ? 1.0 : s[k * n + c]) * piv;
+            if (i == k) d[idx] = rowc;
+            else d[idx] = (c == k ? 0.0 : s[idx]) - s[i * n + k] * rowc;
         }
+        QR_SYNC();
+        s = d;
+        d = (d == A) ? tmp : A;
+    }
+    if (s != A) {
+        QR_FOR(idx, n * n) A[idx] = s[idx];
         QR_SYNC();
     }
 }
@@ -723,7 +732,7 @@ QR_DEV int qr_wbc_qp_and_torque(const QrWbcModelDev& M, const qr_qp_options& opt
     }
     QR_FOR(e, 36) W.A6[e] = W.H[18 * (e / 6) + e % 6];
     QR_SYNC();
-    tm_inverse_spd<NT>(W, W.A6, 6);
+    tm_inverse_spd<NT>(W, W.A6, W.A6, W.rowbuf, 6);
     // da = P df - a0 with P = A6^-1 (JC')_{0:6} (6 x m), a0 = A6^-1 tot_{0:6}
     QR_FOR(idx, 6 * m) { const int i = idx / m, c = idx - i * m; double s = 0.0; for (int l = 0; l < 6; ++l) s += W.A6[6 * i + l] * W.JC[18 * c + l]; W.P6[idx] = s; }
     QR_FOR(i, 6) { double s = 0.0; for (int l = 0; l < 6; ++l) s += W.A6[6 * i + l] * W.tot[l]; W.a0[i] = s; }
@@ -795,8 +804,7 @@ QR_DEV void qr_wbc_problem(const QrWbcArgs& A, int prob, QrWbcWork& W) {
     QR_FOR(i, 66) W.cmd[i] = (double)A.cmd[(size_t)prob * 66 + i];
     QR_SYNC();
     qr_wbc_dynamics<NT>(M, W);
-    tm_copy<NT>(W.Ainv, W.H, 324);
-    tm_inverse_spd<NT>(W, W.Ainv, 18);
+    tm_inverse_spd<NT>(W, W.H, W.Ainv, W.M1, 18);   // the dynamics temporaries are dead: M1 of the overlay is free
     qr_wbc_tasks<NT>(M, W, A.contact + (size_t)prob * 4);
     qr_wbc_kin<NT>(W);
     qr_wbc_wbic_stack<NT>(W);

@@ -30,6 +30,7 @@ struct EmulTeam {
                                        coarse(9 * qr_ntri(nfcap)) {
         qr_mpc_carve(S, smem.data(), nfcap, horizon, fallback.data());
         S.Hc = coarse.data();
+        S.Hc2 = qr_coarse2_cap(nfcap) > 0 ? S.Hc + 9 * qr_ntri(qr_coarse_cap(nfcap)) : nullptr;
         qr_mpc_init_tables<128>(S, nfcap);
     }
 };

@@ -42,4 +42,6 @@ for i in range(600):
     a = time.perf_counter(); capi.mpc_solve_batch_host(P, one); ts.append(time.perf_counter() - a)
 ts = np.asarray(ts[100:]) * 1e6
 print(f"{name}: latency p50 {np.percentile(ts, 50):.1f} us p99 {np.percentile(ts, 99):.1f} us")
+g = out['grf'].double()
+print(f"{name}: checksum grf sum {float(g.sum()):.6f} abs-sum {float(g.abs().sum()):.6f} rounds {float(out['iters'][:,1].float().mean()):.4f}")
 print(f"{name}: {nb / ms * 1e3 / 1e6:.3f} M QP/s  ({ms:.2f} ms/step) occupancy {capi.occupancy(h, 24)} bad {int((out['status'] != 0).sum())}")

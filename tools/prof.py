@@ -15,9 +15,10 @@ capi.init(0)
 lib = capi.lib()
 NAMES = {20: "stage", 21: "condense", 1: "bases", 3: "pack + H p", 4: "reduced matrix+rhs", 11: "LDL' + fwd solve", 13: "backward solve",
          5: "x = Z y + p", 6: "H x + g", 7: "verify", 22: "scatter", 23: "coarse problem build", 12: "fwd (fallback)"}
-for nb in (148, 4096):
-    batch = pkg.synth.make_mpc_batch("a1", 10, 0.03, nb, seed=5, gait="trot")
-    P = capi.params_of(batch["robot"], 10, 0.03)
+H = int(os.environ.get("QR_PROF_H", "10"))
+for nb in ((148, 4096) if H <= 16 else (148, 1184)):
+    batch = pkg.synth.make_mpc_batch("a1", H, 0.03, nb, seed=5, gait="trot")
+    P = capi.params_of(batch["robot"], H, 0.03)
     capi.mpc_solve_batch_host(P, batch)
     tab = (C.c_ulonglong * 64)()
     lib.qr_gpu_debug_profile(tab)
