@@ -324,7 +324,7 @@ def bench_wbc_and_full_step(pkg, capi, torch, stream, with_cpu=False, fp64_peak=
     d_cfg, d_i, d_f = dev(cfg.reshape(B, 20)), dev(istate), dev(fstate)
     d_pf, d_np, d_sr = (torch.zeros((B, 4), device="cuda") for _ in range(3))
     d_allow, d_early, d_mask, d_stance = (torch.empty((B, 4), dtype=torch.int32, device="cuda") for _ in range(4))
-    d_contacts = torch.ones((B, 4), dtype=torch.int32, device="cuda")
+    d_stance.fill_(0)   # measured contacts of a tick = the planned stance legs of the tick before (no early touch-downs)
     d_duty, d_init, d_xy = dev(np.full((B, 4), duty, F32)), dev(traj_init), dev(mb["p"][:, :2])
     o = dict(grf=torch.empty((B, 12), device="cuda"), status=torch.empty(B, dtype=torch.int32, device="cuda"),
              iters=torch.empty((B, 2), dtype=torch.int32, device="cuda"))
@@ -343,7 +343,7 @@ def bench_wbc_and_full_step(pkg, capi, torch, stream, with_cpu=False, fp64_peak=
     TICK_KERNELS = 9 + (4 * h + 7) // 8   # gait, table/trajectory, FK, lever arms, classify + fused classes, foothold, swing targets, WBC
 
     def tick():
-        capi.gait_update_batch_device(d_time, d_cfg, 0.1, d_contacts, None, False, d_i, d_f, d_pf, d_np, d_sr, stream,
+        capi.gait_update_batch_device(d_time, d_cfg, 0.1, d_stance, None, False, d_i, d_f, d_pf, d_np, d_sr, stream,
                                       allow=d_allow, early=d_early, swing_mask=d_mask, stance_mask=d_stance)
         capi.mpc_inputs_batch_device(h, nhl, dt, d_pf, d_duty, d_early, d_stance, d_init, d_xy, d["gait"], d["traj"], stream)
         capi.leg_kinematics_batch_device(G, q, None, foot_base, None, None, stream)

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(qr_fused_nt(CAP), qr_fused_min_ctas(CAP)) qr_m
         __syncthreads();
         if (k >= total) break;
         strided += gridDim.x;
-        qr_mpc_solve_problem<NT>(A, A.list ? A.list[k] : k, S);
+        qr_mpc_solve_problem<NT, (CAP >= QR_COARSE2_MIN_CAP)>(A, A.list ? A.list[k] : k, S);
     }
 }
 
@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(qr_fused_nt(CAP), qr_fused_min_ctas(CAP)) qr_m
 #ifndef QR_LAT_NT
 #define QR_LAT_NT 256   // a wider team shortens the phases with plenty of parallel work (condensing, early LDL' steps)
 #endif
+template <bool L2>
 __global__ void __launch_bounds__(QR_LAT_NT, 1) qr_mpc_fused_latency_kernel(const QrMpcArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NT = QR_LAT_NT;
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(QR_LAT_NT, 1) qr_mpc_fused_latency_kernel(cons
     S.Hc = A.hc_global ? A.hc_global + (size_t)blockIdx.x * 9 * qr_ntri(A.nfcap) : nullptr;
     S.Hc2 = (S.Hc && qr_coarse2_cap(A.nfcap) > 0) ? S.Hc + 9 * qr_ntri(qr_coarse_cap(A.nfcap)) : nullptr;
     qr_mpc_init_tables<NT>(S, A.nfcap);
-    for (int prob = blockIdx.x; prob < A.batch; prob += gridDim.x) qr_mpc_solve_problem<NT>(A, prob, S);
+    for (int prob = blockIdx.x; prob < A.batch; prob += gridDim.x) qr_mpc_solve_problem<NT, L2>(A, prob, S);
 }
 
 typedef void (*QrFusedKernel)(const QrMpcArgs);
@@ -577,7 +578,9 @@ int mpc_enqueue(Ctx& cx, const qr_mpc_params* P, const qr_qp_options* opt, int b
         // largest size class once (its workspace holds any instance of this horizon).
         const int cap = class_cap(nclass - 1, h);
         Plan pl;
-        rc = launch_geometry(cx, qr_mpc_fused_latency_kernel, cap, h, batch, &pl, false, false, QR_LAT_NT);
+        const bool two_levels = qr_coarse2_cap(cap) > 0;
+        rc = two_levels ? launch_geometry(cx, qr_mpc_fused_latency_kernel<true>, cap, h, batch, &pl, false, false, QR_LAT_NT)
+                        : launch_geometry(cx, qr_mpc_fused_latency_kernel<false>, cap, h, batch, &pl, false, false, QR_LAT_NT);
         if (rc) return rc;
         rc = acquire_lane(cx, st, &lane);
         if (rc) return rc;
@@ -586,7 +589,8 @@ int mpc_enqueue(Ctx& cx, const qr_mpc_params* P, const qr_qp_options* opt, int b
         A.nfcap = cap;
         A.coarse_rounds = QR_COARSE_MAX_ROUNDS_LAT;
         bind_scratch(A, pl, cap, *lane);
-        qr_mpc_fused_latency_kernel<<<pl.grid, QR_LAT_NT, pl.smem, st>>>(A);
+        if (two_levels) qr_mpc_fused_latency_kernel<true><<<pl.grid, QR_LAT_NT, pl.smem, st>>>(A);
+        else qr_mpc_fused_latency_kernel<false><<<pl.grid, QR_LAT_NT, pl.smem, st>>>(A);
         cudaError_t e1 = cudaGetLastError();
         release_lane(*lane, st);
         if (e1 != cudaSuccess) return fail(QR_ECUDA, "launch qr_mpc_fused_latency_kernel", e1);

@@ -67,7 +67,7 @@ QR_HD size_t qr_mpc_smem_bytes(int nfcap, int horizon, bool hs_in_smem = true, b
     bytes += (size_t)(9 + 9 + 6 * 3 + 1) * nfcap * sizeof(double) + 8 * sizeof(double);
     bytes += (size_t)(3 + 1) * qr_coarse_cap(nfcap) * sizeof(double);   // coarse problem: g, ub
     bytes += (size_t)(3 + 1) * qr_coarse2_cap(nfcap) * sizeof(double);  // second coarse level (long horizons only): g, ub
-    bytes += (size_t)(3 + 1 + 2) * qr_coarse_cap(nfcap) * sizeof(int);  // .. descriptors of the first level, grp2, gmem2
+    if (qr_coarse2_cap(nfcap) > 0) bytes += (size_t)(3 + 1 + 2) * qr_coarse_cap(nfcap) * sizeof(int);  // .. descriptors of the first level, grp2, gmem2
     bytes += (size_t)(16 * horizon + 32) * sizeof(float);          // staged traj + gait + state rows
     bytes += (size_t)(3 * nfcap + (nfcap + 1) + 3 * nfcap + 2 * 4 * horizon + 8 + 24 + nfcap + 3 * nfcap) * sizeof(int);   // .. + grp, gmem
     bytes += (size_t)((qr_ntri(nfcap) + 1) / 2) * sizeof(int);         // tri (unsigned short, padded to ints)
@@ -138,9 +138,12 @@ QR_DEV void qr_mpc_carve(QrMpcSmem& S, unsigned char* base, int nfcap, int horiz
     W.hist = ip; ip += 24 + nfcap;
     S.grp = ip; ip += nfcap;
     S.gmem = ip; ip += 2 * nfcap;
-    S.cdesc = ip; ip += 3 * qr_coarse_cap(nfcap);
-    S.grp2 = ip; ip += qr_coarse_cap(nfcap);
-    S.gmem2 = ip; ip += 2 * qr_coarse_cap(nfcap);
+    S.cdesc = S.grp2 = S.gmem2 = nullptr;
+    if (qr_coarse2_cap(nfcap) > 0) {
+        S.cdesc = ip; ip += 3 * qr_coarse_cap(nfcap);
+        S.grp2 = ip; ip += qr_coarse_cap(nfcap);
+        S.gmem2 = ip; ip += 2 * qr_coarse_cap(nfcap);
+    }
     W.tri = reinterpret_cast<unsigned short*>(ip);
     ip += (qr_ntri(nfcap) + 1) / 2;
     float* f = reinterpret_cast<float*>(ip);
@@ -287,16 +290,18 @@ QR_DEV void qr_coarse_reduce(const unsigned short* tri, const double* __restrict
     QR_SYNC();
 }
 
-template <int NT>
+template <int NT, bool L2>
 QR_DEV void qr_mpc_build_coarse(QrMpcSmem& S, const qr_qp_options& opt, int max_rounds, QrCoarse* C) {
     QrQpWork& W = S.W;
     const int nf = W.nf;
     C[0].ng = 0; C[0].Hs = S.Hc; C[0].g = S.gc; C[0].ubz = S.ubc; C[0].grp = S.grp;
     C[0].max_rounds = max_rounds > 0 ? max_rounds : QR_COARSE_MAX_ROUNDS;
-    C[1].ng = 0; C[1].Hs = S.Hc2; C[1].g = S.gc2; C[1].ubz = S.ubc2; C[1].grp = S.grp2;
-    C[1].max_rounds = C[0].max_rounds;
+    if (L2) {
+        C[1].ng = 0; C[1].Hs = S.Hc2; C[1].g = S.gc2; C[1].ubz = S.ubc2; C[1].grp = S.grp2;
+        C[1].max_rounds = C[0].max_rounds;
+    }
     if (!S.Hc || nf < 8 || (opt.flags & QR_QP_NO_PREDICTION)) return;
-    const bool want2 = S.Hc2 != nullptr && nf >= QR_COARSE2_MIN_CAP - 7;
+    const bool want2 = L2 && S.Hc2 != nullptr && nf >= QR_COARSE2_MIN_CAP - 7;
     // Pairing: consecutive foot-steps of one leg with the same force cap are tied to one force; a foot-step that finds
     // no partner stays single.  The second level pairs the first level's foot-steps by the same rule (a first-level
     // foot-step covers the steps first..last of its leg).
@@ -350,7 +355,7 @@ QR_DEV void qr_mpc_build_coarse(QrMpcSmem& S, const qr_qp_options& opt, int max_
     if (4 * ng > 3 * nf) return;   // hardly anything to pair
     qr_coarse_reduce<NT>(W.tri, W.Hs, W.g, W.ubz, ng, S.gmem, S.Hc, S.gc, S.ubc);
     C[0].ng = ng;
-    if (ng2 > 0 && 4 * ng2 <= 3 * ng) {
+    if (L2 && ng2 > 0 && 4 * ng2 <= 3 * ng) {
         qr_coarse_reduce<NT>(W.tri, S.Hc, S.gc, S.ubc, ng2, S.gmem2, S.Hc2, S.gc2, S.ubc2);
         C[1].ng = ng2;
     }
@@ -408,7 +413,7 @@ QR_DEV int qr_result_status(QrMpcSmem& S, const double* x, int status) {
 }
 
 // The fused path: SolveMPCKernel + GetMPCSolution for one instance.
-template <int NT>
+template <int NT, bool L2>
 QR_DEV void qr_mpc_solve_problem(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
     QR_PROF_DECL;
     qr_mpc_stage<NT>(A, prob, S);
@@ -419,10 +424,10 @@ QR_DEV void qr_mpc_solve_problem(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
     if (status == 0) {
         qr_mpc_condense_to_work<NT>(A, S);
         QR_PROF(21);
-        QrCoarse C[2];
-        qr_mpc_build_coarse<NT>(S, A.opt, A.coarse_rounds, C);
+        QrCoarse C[L2 ? 2 : 1];
+        qr_mpc_build_coarse<NT, L2>(S, A.opt, A.coarse_rounds, C);
         QR_PROF(23);
-        status = qr_qp_solve<NT>(S.W, A.opt, &it, &rounds, &x, C QR_PROF_PASS);
+        status = qr_qp_solve<NT, L2>(S.W, A.opt, &it, &rounds, &x, C QR_PROF_PASS);
         status = qr_result_status<NT>(S, x, status);
     }
     qr_mpc_scatter<NT>(A, prob, S, x, status, it, rounds);
@@ -495,8 +500,8 @@ QR_DEV void qr_qp_solve_problem(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
         QR_SYNC();
         QR_PROF_DECL;
         QrCoarse C[2];
-        qr_mpc_build_coarse<NT>(S, A.opt, A.coarse_rounds, C);
-        status = qr_qp_solve<NT>(S.W, A.opt, &it, &rounds, &x, C QR_PROF_PASS);
+        qr_mpc_build_coarse<NT, true>(S, A.opt, A.coarse_rounds, C);
+        status = qr_qp_solve<NT, true>(S.W, A.opt, &it, &rounds, &x, C QR_PROF_PASS);
         status = qr_result_status<NT>(S, x, status);
     }
     qr_mpc_scatter<NT>(A, prob, S, x, status, it, rounds);

@@ -1014,7 +1014,10 @@ struct QrCoarse {
 // set (tightening the tolerance once if the verification still does not settle) and 3: the same verification from
 // its guess.  Written as one loop around a single qr_active_set call site so that the (force-inlined) iteration is
 // instantiated once.
-template <int NT>
+// L2 (compile time): the workspace class carries a second coarse level (C points at two levels, else at one).  Kept out
+// of the instantiations that never use it: two levels make C an indexed array, which lives on the thread's stack, and
+// the h = 10 classes lost 4 % to that alone (B200, A1 trot 65536: 4.12 -> 3.96 M QP/s).
+template <int NT, bool L2>
 QR_DEV int qr_qp_solve(QrQpWork& W, const qr_qp_options& opt, int* ipm_iters, int* as_rounds,
                        const double** result, const QrCoarse* C QR_PROF_ARG) {
     int conv = 0, ok = 0;
@@ -1028,21 +1031,21 @@ QR_DEV int qr_qp_solve(QrQpWork& W, const qr_qp_options& opt, int* ipm_iters, in
     // stages -1 / 0: the coarse levels C[1] (coarsest, optional) and C[0]; every level starts from the active rows
     // inherited from the level before it
     int stage = 1;
-    if (C && C[0].ng > 0) stage = (C[1].ng > 0) ? -1 : 0;
+    if (C && C[0].ng > 0) stage = (L2 && C[1].ng > 0) ? -1 : 0;
     int mode = 1, attempt = 0;
     double tol = opt.ipm_tol;
     for (;;) {
         int maxr = opt.max_as_rounds;
         if (stage <= 0) {
-            const QrCoarse& L = C[-stage];
+            const QrCoarse& L = C[L2 ? -stage : 0];
             W.nf = L.ng; W.Hs = L.Hs; W.g = L.g; W.ubz = L.ubz; maxr = L.max_rounds;
         } else if (stage == 3) { mode = 0; maxr = opt.max_polish_rounds; }
         const int rounds = qr_active_set<NT>(W, opt, &ok, mode, maxr QR_PROF_PASS);
         if (stage <= 0) {
             // every foot-step of the next finer level inherits its tied foot-step's active rows (through W.flag:
             // rewritten in place)
-            const int* grp = C[-stage].grp;
-            const int n_fine = (stage == -1) ? C[0].ng : nf_full;
+            const int* grp = C[L2 ? -stage : 0].grp;
+            const int n_fine = (L2 && stage == -1) ? C[0].ng : nf_full;
             W.nf = nf_full; W.Hs = hs_full; W.g = g_full; W.ubz = ubz_full;
             QR_FOR(f, n_fine) W.flag[f] = W.act[grp[f]];
             QR_SYNC();

@@ -763,7 +763,7 @@ QR_DEV int qr_wbc_qp_and_torque(const QrWbcModelDev& M, const qr_qp_options& opt
         int it = 0, rounds = 0;
         const double* x = Q.xn;
         QR_PROF_DECL;
-        status = qr_qp_solve<NT>(Q, opt, &it, &rounds, &x, nullptr QR_PROF_PASS);
+        status = qr_qp_solve<NT, false>(Q, opt, &it, &rounds, &x, nullptr QR_PROF_PASS);
         f = x;
     }
     // qdd[0:6] += da ; tau = (A qdd + C + G - JC' f)[6:18]

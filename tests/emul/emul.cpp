@@ -59,7 +59,7 @@ extern "C" int qr_emul_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_optio
         // same size classification as qr_mpc_classify_kernel
         A.nfcap = class_cap_of(gait + (size_t)i * 4 * P->horizon, fmax_i ? fmax_i[i] : P->f_max, P->horizon);
         EmulTeam team(A.nfcap, P->horizon);
-        qr_mpc_solve_problem<128>(A, i, team.S);
+        qr_mpc_solve_problem<128, true>(A, i, team.S);
     }
     return 0;
 }
@@ -247,7 +247,7 @@ extern "C" int qr_emul_mpc_solve_batch_ex(const qr_mpc_params* P, int batch, con
     for (int i = 0; i < batch; ++i) {
         A.nfcap = class_cap_of(gait + (size_t)i * 4 * P->horizon, P->f_max, P->horizon);
         EmulTeam team(A.nfcap, P->horizon);
-        qr_mpc_solve_problem<128>(A, i, team.S);
+        qr_mpc_solve_problem<128, true>(A, i, team.S);
     }
     return 0;
 }
