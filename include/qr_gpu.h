@@ -144,8 +144,9 @@ int qr_gpu_mpc_solve_batch_ex(const qr_mpc_params* P, const qr_qp_options* opt, 
  * qr_mpc_stance_leg_controller.cpp:385-410).  The batch is cut into contiguous shards [g*B/G, (g+1)*B/G), one per
  * entry of devices[]; one host thread per device uploads its shard, runs the fused kernel and downloads the
  * results straight into the caller's arrays (that device->host copy is the "final gather").  There is no
- * collective on the path.  Contexts of devices not yet initialised are created on the fly; the calling thread's
- * current device is restored before returning.  Returns the first failing shard's code. */
+ * collective on the path.  Contexts of devices not yet initialised are created on the fly; the per-device host threads
+ * are persistent (created on first use, joined by qr_gpu_shutdown) and the calling thread's current device is not
+ * touched.  One multi-device call runs at a time (further callers wait).  Returns the first failing shard's code. */
 int qr_gpu_mpc_solve_batch_host_multi(int n_devices, const int* devices, const qr_mpc_params* P,
                                       const qr_qp_options* opt, int batch, const float* p, const float* v,
                                       const float* quat, const float* w, const float* r_feet, const float* rpy,

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <condition_variable>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -514,7 +515,9 @@ extern "C" int qr_gpu_init(int device) {
     return QR_OK;
 }
 
+namespace { void workers_stop(); }
 extern "C" void qr_gpu_shutdown(void) {
+    workers_stop();
     std::lock_guard<std::mutex> lk(g_mu);
     int prev = -1;
     cudaGetDevice(&prev);
@@ -871,6 +874,66 @@ extern "C" int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_o
 // single SolveDenseMPC call of qr_mpc_stance_leg_controller.cpp:385-410): contiguous shards [g*B/G, (g+1)*B/G), one
 // host thread per device running the host entry point above on its shard, results written straight into the
 // caller's arrays (the "final gather" is each shard's own device->host copy).  No collective.
+// The per-device host threads are persistent (created on first use, bound to their device once): at 8192 instances
+// per GPU a solve takes 2 ms, and creating and binding eight threads per call was a tenth of that.
+namespace {
+struct Worker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has_job = false, done = false, quit = false;
+};
+Worker* g_workers[QR_MAX_DEVICES] = {};
+std::mutex g_multi_mu;   // one multi-device call at a time (the workers are shared)
+
+void worker_main(Worker* w, int device) {
+    cudaSetDevice(device);
+    std::unique_lock<std::mutex> lk(w->m);
+    for (;;) {
+        w->cv.wait(lk, [&] { return w->has_job || w->quit; });
+        if (w->quit) return;
+        std::function<void()> job = std::move(w->job);
+        w->has_job = false;
+        lk.unlock();
+        job();
+        lk.lock();
+        w->done = true;
+        w->cv.notify_all();
+    }
+}
+void worker_submit(int device, std::function<void()> job) {
+    Worker*& w = g_workers[device];
+    if (!w) {
+        w = new Worker();
+        w->th = std::thread(worker_main, w, device);
+    }
+    std::lock_guard<std::mutex> lk(w->m);
+    w->job = std::move(job);
+    w->has_job = true;
+    w->done = false;
+    w->cv.notify_all();
+}
+void worker_wait(int device) {
+    Worker* w = g_workers[device];
+    std::unique_lock<std::mutex> lk(w->m);
+    w->cv.wait(lk, [&] { return w->done; });
+}
+void workers_stop() {
+    for (Worker*& w : g_workers) {
+        if (!w) continue;
+        {
+            std::lock_guard<std::mutex> lk(w->m);
+            w->quit = true;
+            w->cv.notify_all();
+        }
+        w->th.join();
+        delete w;
+        w = nullptr;
+    }
+}
+}  // namespace
+
 extern "C" int qr_gpu_mpc_solve_batch_host_multi(int n_devices, const int* devices, const qr_mpc_params* P,
                                                  const qr_qp_options* opt, int batch, const float* p, const float* v,
                                                  const float* quat, const float* w, const float* r_feet,
@@ -880,19 +943,19 @@ extern "C" int qr_gpu_mpc_solve_batch_host_multi(int n_devices, const int* devic
     if (n_devices < 1 || n_devices > QR_MAX_DEVICES || !devices) return fail(QR_EINVAL, "bad device list");
     int rc = check_params(P, batch);
     if (rc) return rc;
-    for (int g = 0; g < n_devices; ++g)
+    for (int g = 0; g < n_devices; ++g) {
+        if (devices[g] < 0 || devices[g] >= QR_MAX_DEVICES) return fail(QR_EINVAL, "device index out of range");
         for (int k = 0; k < g; ++k)
             if (devices[k] == devices[g]) return fail(QR_EINVAL, "device listed twice");
+    }
     if (batch == 0) return QR_OK;
     const int h = P->horizon;
-    int prev = -1;
-    cudaGetDevice(&prev);
     int codes[QR_MAX_DEVICES];
     char errs[QR_MAX_DEVICES][320];
     auto shard = [&](int g) {
         errs[g][0] = 0;
         const size_t b0 = (size_t)batch * g / n_devices, b1 = (size_t)batch * (g + 1) / n_devices, nb = b1 - b0;
-        int r = qr_gpu_init(devices[g]);   // binds this thread to the device; creates its context on first use
+        int r = qr_gpu_init(devices[g]);   // (re)binds the worker to its device; creates the context on first use
         if (r == QR_OK && nb > 0) {
             auto at = [&](const float* a, size_t k) -> const float* { return a ? a + b0 * k : nullptr; };
             r = qr_gpu_mpc_solve_batch_host(P, opt, (int)nb, at(p, 3), at(v, 3), at(quat, 4), at(w, 3), at(r_feet, 12),
@@ -904,12 +967,10 @@ extern "C" int qr_gpu_mpc_solve_batch_host_multi(int n_devices, const int* devic
         if (r != QR_OK) snprintf(errs[g], sizeof(errs[g]), "device %d: %s", devices[g], t_err);
     };
     {
-        std::vector<std::thread> workers;
-        for (int g = 1; g < n_devices; ++g) workers.emplace_back(shard, g);
-        shard(0);
-        for (std::thread& t : workers) t.join();
+        std::lock_guard<std::mutex> lk(g_multi_mu);
+        for (int g = 0; g < n_devices; ++g) worker_submit(devices[g], [&shard, g] { shard(g); });
+        for (int g = 0; g < n_devices; ++g) worker_wait(devices[g]);
     }
-    if (prev >= 0) cudaSetDevice(prev);
     for (int g = 0; g < n_devices; ++g)
         if (codes[g] != QR_OK) { snprintf(t_err, sizeof(t_err), "%s", errs[g]); return codes[g]; }
     return QR_OK;

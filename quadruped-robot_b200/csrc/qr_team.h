@@ -30,6 +30,11 @@ __device__ __forceinline__ void qr_team_sync() {
     if (NT <= 32) __syncwarp(); else __syncthreads();
 }
 #define QR_FOR(i, n) for (int i = threadIdx.x; i < (n); i += NT)
+// strided loop over the entries (i, j) of an m x n row-major array: the row / column of an entry follow from the previous
+// one by additions (one integer division per loop instead of one per entry)
+#define QR_FOR_2D(idx, i, j, m, n)                                                                                    \
+    for (int idx = threadIdx.x, _qn = (n), _qdi = NT / _qn, _qdj = NT - _qdi * _qn, i = idx / _qn, j = idx - i * _qn; \
+         idx < (m) * _qn; idx += NT, i += _qdi, j += _qdj, i += (j >= _qn), j -= (j >= _qn) ? _qn : 0)
 #define QR_THREADS(t) for (int t = threadIdx.x, _qr_once = 1; _qr_once; _qr_once = 0)
 #define QR_SYNC() qr_team_sync<NT>()
 // barrier + "does any thread of the team hold a non-zero flag"
@@ -50,6 +55,8 @@ __device__ __forceinline__ int qr_team_any(int v) {
 #else
 // ---- host emulation (tests only) ---------------------------------------------------------
 #define QR_FOR(i, n) for (int i = 0; i < (n); ++i)
+#define QR_FOR_2D(idx, i, j, m, n) \
+    for (int idx = 0, _qn = (n), i = 0, j = 0; idx < (m) * _qn; ++idx, ++j, i += (j >= _qn), j -= (j >= _qn) ? _qn : 0)
 #define QR_THREADS(t) for (int t = 0; t < NT; ++t)
 #define QR_SYNC() ((void)0)
 #define QR_ANY(v) (v)

@@ -123,19 +123,28 @@ QR_DEV void qr_wbc_carve(QrWbcWork& W, unsigned char* base) {
 
 // ---- small team-parallel dense kernels (row-major, contiguous).  Every helper ends with a barrier. ----
 template <int NT> QR_DEV void tm_mul(double* C, const double* A, const double* B, int m, int k, int n) {
-    QR_FOR(idx, m * n) { const int i = idx / n, j = idx - i * n; double s = 0.0; for (int l = 0; l < k; ++l) s += A[i * k + l] * B[l * n + j]; C[idx] = s; }
+    QR_FOR_2D(idx, i, j, m, n) { double s = 0.0; for (int l = 0; l < k; ++l) s += A[i * k + l] * B[l * n + j]; C[idx] = s; }
     QR_SYNC();
 }
 template <int NT> QR_DEV void tm_mul_nt(double* C, const double* A, const double* B, int m, int k, int n) {   // C = A B', B is n x k
-    QR_FOR(idx, m * n) { const int i = idx / n, j = idx - i * n; double s = 0.0; for (int l = 0; l < k; ++l) s += A[i * k + l] * B[j * k + l]; C[idx] = s; }
+    QR_FOR_2D(idx, i, j, m, n) { double s = 0.0; for (int l = 0; l < k; ++l) s += A[i * k + l] * B[j * k + l]; C[idx] = s; }
     QR_SYNC();
 }
 // C = I - A B  (A: m x k, B: k x m)
 template <int NT> QR_DEV void tm_eye_minus_mul(double* C, const double* A, const double* B, int m, int k) {
-    QR_FOR(idx, m * m) { const int i = idx / m, j = idx - i * m; double s = (i == j) ? 1.0 : 0.0; for (int l = 0; l < k; ++l) s -= A[i * k + l] * B[l * m + j]; C[idx] = s; }
+    QR_FOR_2D(idx, i, j, m, m) { double s = (i == j) ? 1.0 : 0.0; for (int l = 0; l < k; ++l) s -= A[i * k + l] * B[l * m + j]; C[idx] = s; }
     QR_SYNC();
 }
 template <int NT> QR_DEV void tm_copy(double* D, const double* S, int n) { QR_FOR(i, n) D[i] = S[i]; QR_SYNC(); }
+// N <- N (I - Jbar Jpre) for an 18 x 18 projector and a three-row task (Jbar 18 x 3, Jpre 3 x 18), evaluated as the
+// rank-3 update N - (N Jbar) Jpre: 1.9 k multiply-adds and two phases instead of the 6.8 k and three of forming
+// I - Jbar Jpre and multiplying by it (the same matrix up to float64 rounding).  T: 54 doubles of scratch.
+template <int NT> QR_DEV void tm_project_out(double* N, const double* Jbar, const double* Jpre, double* T) {
+    QR_FOR_2D(idx, i, c, 18, 3) { double s = 0.0; for (int l = 0; l < 18; ++l) s += N[18 * i + l] * Jbar[3 * l + c]; T[idx] = s; }
+    QR_SYNC();
+    QR_FOR_2D(idx, i, j, 18, 18) N[idx] -= T[3 * i] * Jpre[j] + T[3 * i + 1] * Jpre[18 + j] + T[3 * i + 2] * Jpre[36 + j];
+    QR_SYNC();
+}
 
 // Pseudo-inverse of J (m x n, m <= 12, n <= 18) with singular values <= thr dropped
 // (pseudoInverse, include/quadruped/utils/qr_algebra.h:119-140).  One-sided Jacobi on the columns of
@@ -162,8 +171,7 @@ QR_DEV void tm_pinv(QrWbcWork& W, double* out, const double* J, int m, int n, do
         if (sym_psd) {
             QR_FOR(idx, m * m) Gi[idx] = J[idx];
         } else {
-            QR_FOR(idx, m * m) {
-                const int i = idx / m, j = idx - i * m;
+            QR_FOR_2D(idx, i, j, m, m) {
                 double a = 0.0;
                 for (int l = 0; l < n; ++l) a += J[i * n + l] * J[j * n + l];
                 Gi[idx] = a;
@@ -185,8 +193,7 @@ QR_DEV void tm_pinv(QrWbcWork& W, double* out, const double* J, int m, int n, do
             if (sym_psd) {
                 QR_FOR(idx, m * m) out[idx] = Gi[idx];
             } else {
-                QR_FOR(idx, n * m) {
-                    const int i = idx / m, l = idx - i * m;
+                QR_FOR_2D(idx, i, l, n, m) {
                     double a = 0.0;
                     for (int j = 0; j < m; ++j) a += J[j * n + i] * Gi[j * m + l];
                     out[idx] = a;
@@ -265,8 +272,7 @@ QR_DEV void tm_inverse_spd(QrWbcWork& W, const double* src0, double* A, double* 
     for (int k = 0; k < n; ++k) {
         const double akk = s[k * n + k];
         const double piv = akk > 1e-300 ? qr_rcp_pos(akk) : 1.0 / akk;   // positive pivots: Newton reciprocal (once per thread and step)
-        QR_FOR(idx, n * n) {
-            const int i = idx / n, c = idx - i * n;
+        QR_FOR_2D(idx, i, c, n, n) {
             const double rowc = (c == k ? 1.0 : s[k * n + c]) * piv;
             if (i == k) d[idx] = rowc;
             else d[idx] = (c == k ? 0.0 : s[idx]) - s[i * n + k] * rowc;
@@ -677,11 +683,7 @@ QR_DEV void qr_wbc_kin(QrWbcWork& W) {
             W.qdot[i] += W.Jbar[3 * i] * W.vec[3] + W.Jbar[3 * i + 1] * W.vec[4] + W.Jbar[3 * i + 2] * W.vec[5];
         }
         QR_SYNC();
-        if (k < nt - 1) {
-            tm_eye_minus_mul<NT>(W.M1, W.Jbar, W.Jpre, 18, 3);    // I - pinv(JtPre) JtPre
-            tm_mul<NT>(W.N2, W.N, W.M1, 18, 18, 18);
-            tm_copy<NT>(W.N, W.N2, 324);
-        }
+        if (k < nt - 1) tm_project_out<NT>(W.N, W.Jbar, W.Jpre, W.M1);   // N <- N (I - pinv(JtPre) JtPre)
     }
 }
 
@@ -710,11 +712,7 @@ QR_DEV void qr_wbc_wbic_stack(QrWbcWork& W) {
         QR_SYNC();
         QR_FOR(i, 18) W.qdd[i] += W.Jbar[3 * i] * W.vec[0] + W.Jbar[3 * i + 1] * W.vec[1] + W.Jbar[3 * i + 2] * W.vec[2];
         QR_SYNC();
-        if (k < nt - 1) {
-            tm_eye_minus_mul<NT>(W.M1, W.Jbar, W.Jpre, 18, 3);
-            tm_mul<NT>(W.N2, W.N, W.M1, 18, 18, 18);
-            tm_copy<NT>(W.N, W.N2, 324);
-        }
+        if (k < nt - 1) tm_project_out<NT>(W.N, W.Jbar, W.Jpre, W.M1);   // N <- N (I - pinv(JtPre) JtPre)
     }
 }
 

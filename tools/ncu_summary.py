@@ -2,7 +2,10 @@
 import csv, subprocess, sys, io
 rep, out = sys.argv[1], sys.argv[2]
 kfilter = sys.argv[3] if len(sys.argv) > 3 else ""
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".csv"):   # a raw page exported on the GPU box (tools/ncu_r02.sh)
+    raw = open(rep).read()
+else:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 WANT = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
