@@ -18,7 +18,11 @@
 // (SURVEY.md section 0 fact 2), so every float32 operation below is issued in the order the
 // reference's dense products visit their NON-ZERO terms (k ascending, multiply then add, no FMA
 // contraction: QR_FMUL / QR_FADD); terms that are structurally zero are skipped, which changes
-// nothing because x + 0 == x.  tests/ check (H, g, ub) against the oracle for equality.
+// nothing because x + 0 == x.  tests/ check (H, g, ub) against the oracle for equality, and against the
+// reference's own qr_mpc_interface.cpp compiled from /root/reference (oracle/_ref/libqr_mpc_ref.so) for equality
+// when that build evaluates exp() of the nilpotent matrix by its finite series (the test hook
+// MINI_EIGEN_EXP_NILPOTENT3); against the scaling-and-squaring Pade evaluation of Eigen's MatrixFunctions the
+// entries agree to 3e-7 relative (float32 rounding of the Pade steps), not bitwise.
 #pragma once
 
 #include "qr_team.h"

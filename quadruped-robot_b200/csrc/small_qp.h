@@ -5,8 +5,10 @@
 // Replaces quadprogpp::solve_quadprog as the force-balance controller calls it
 // (/root/reference/quadruped/src/controllers/balance_controller/qr_qp_torque_optimizer.cpp:273-276, 380-383;
 // solver: extern/QuadProgpp/src/QuadProg++.cc:453-...), i.e. no equality rows.  Same method -- the dual
-// active-set iteration of Goldfarb & Idnani (Math. Programming 27, 1983) -- written from the published
-// algorithm: G = LL', J = L^-T, the active normals are kept as N = J[:, :q] R with R upper triangular, and
+// active-set iteration of Goldfarb & Idnani (Math. Programming 27, 1983) -- and the same FORMULATION as
+// QuadProg++ (its variable names np, z, r, d, u, R_norm, psi, t1, t2 are the paper's; its termination constant
+// m * eps * c1 * c2 * 100 is kept so that both stop on the same instances), but not its code: no gotos, bitmask
+// active sets, a restart on dependent rows, fixed row-major arrays.  G = LL', J = L^-T, the active normals are kept as N = J[:, :q] R with R upper triangular, and
 // constraints enter / leave through Givens rotations of J and R.  The most violated constraint is processed
 // first, and -- like the reference's solver -- an infeasible constraint ends the iteration with the CURRENT
 // iterate in x (the force-balance QP of a leg in swing asks for n.f >= 1e-7 and -n.f >= 1e-7 at once; the

@@ -163,3 +163,24 @@ def test_interleaved_hessian_pair_is_bit_identical(emul, oracle, pkg):
         b = pkg.synth.make_mpc_batch(robot, h, 0.03, 6, seed=seed, gait=gait)
         P = oracle.params_of(b["robot"], h, 0.03)
         assert emul.condense_pair_mismatches(P, b) == 0
+
+
+def test_all_apex_instance(emul, oracle, pkg):
+    """A reference trajectory that asks for a downward acceleration above g: every stance foot-step ends pinned to the apex
+    f = 0 of its pyramid, the reduced system of that round is EMPTY (no factorisation, x = p), and the verification
+    accepts it."""
+    h, dt = 10, 0.03
+    b = pkg.synth.make_mpc_batch("a1", h, dt, 3, seed=23, gait="trot")
+    b["traj"] = b["traj"].copy()
+    b["traj"].reshape(3, h, 12)[:, :, 5] = b["p"][:, 2:3] - 10.0     # desired height 10 m below the robot
+    P = oracle.params_of(b["robot"], h, dt)
+    e = emul.solve(P, b)
+    assert (e["status"] == 0).all() and (e["iters"][:, 0] == 0).all()
+    A = oracle.constraint_rows(h, P.mu)
+    for i in range(3):
+        H, g, ub = oracle.mpc_build(P, b, i)
+        assert np.abs(e["u64"][i]).max() == 0.0                        # the optimum is f = 0 everywhere ...
+        # ... a degenerate vertex (all five rows of every foot-step meet there; the reference's qpOASES call does not
+        # survive it -- it returns forces of thousands of newtons with an error code): certified by NNLS multipliers
+        stat, feas = oracle.kkt_certificate(H, g, A, np.zeros(20 * h), ub.astype(float), e["u64"][i])
+        assert stat < 1e-9 and feas == 0.0

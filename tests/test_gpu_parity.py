@@ -206,6 +206,12 @@ def test_edge_cases(gpu, pkg):
     assert r["status"][1] == 2 and (r["u"][1] == 0).all()
     assert r["status"][2] == 0 and (r["u"][2] == 0).all()
     assert r["status"][3] == 0
+    # every stance foot-step pinned to the apex f = 0 (the reduced system of that round is empty)
+    a = pkg.synth.make_mpc_batch("a1", 10, 0.03, 300, seed=34, gait="trot")
+    a["traj"] = a["traj"].copy()
+    a["traj"].reshape(300, 10, 12)[:, :, 5] = a["p"][:, 2:3] - 10.0
+    ra = gpu_solve(gpu, gpu.params_of(a["robot"], 10, 0.03), a)
+    assert (ra["status"] == 0).all() and (ra["u"] == 0).all() and (ra["iters"][:, 0] == 0).all()
     # empty batch and single instance
     e = {k: (v[:0] if isinstance(v, np.ndarray) else v) for k, v in b.items()}
     assert gpu.mpc_solve_batch_host(P, e)["grf"].shape == (0, 12)
