@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(QR_NT) qr_qp_solve_kernel(const QrMpcArgs A) {
 //  * the *_host entry points take a private staging slot (device staging buffer, pinned mirror, two streams) for
 //    the whole call, so two host threads never share a buffer; error paths drain the slot's streams before it is
 //    released, so no copy from caller memory is left pending;
-//  * g_mu serialises only the bookkeeping and the launch calls themselves, never device execution.
+//  * a per-device mutex serialises only the bookkeeping and the launch calls themselves, never device execution.
 constexpr int QR_MAX_DEVICES = 16;
 constexpr int QR_MAX_LANES = 8;
 constexpr int QR_MAX_SLOTS = 4;
@@ -247,8 +247,10 @@ struct Ctx {
     int wbc_occ = 0;                  // resident CTAs per SM of the WBC kernel (0: not queried yet)
 };
 Ctx g_dev[QR_MAX_DEVICES];
-std::mutex g_mu;
-std::condition_variable g_slot_cv;
+std::mutex g_mu;                                   // init / shutdown (the table of contexts)
+std::mutex g_ctx_mu[QR_MAX_DEVICES];               // one per context: its lanes, plans, slots, WBC models -- calls on
+std::condition_variable g_slot_cv[QR_MAX_DEVICES]; // different devices never contend (the multi-GPU call's threads)
+std::mutex& ctx_mu(const Ctx& cx) { return g_ctx_mu[cx.device]; }
 thread_local char t_err[256] = {0};
 
 int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
@@ -323,7 +325,7 @@ int launch_geometry(Ctx& cx, Kern kern, int nfcap, int horizon, int batch, Plan*
     return QR_OK;
 }
 
-// Workspace for a launch sequence on stream `st` (g_mu held).  See the contract at the top of this section.
+// Workspace for a launch sequence on stream `st` (the context mutex held).  See the contract at the top of this section.
 int acquire_lane(Ctx& cx, cudaStream_t st, Lane** out) {
     Lane* pick = nullptr;
     for (int i = 0; i < cx.nlanes && !pick; ++i)
@@ -414,17 +416,17 @@ struct SlotHold {
         cudaStreamSynchronize(s->stream[0]);
         cudaStreamSynchronize(s->stream[1]);
         {
-            std::lock_guard<std::mutex> lk(g_mu);
+            std::lock_guard<std::mutex> lk(ctx_mu(*cx));
             s->busy = false;
         }
-        g_slot_cv.notify_one();
+        g_slot_cv[cx->device].notify_one();
     }
 };
 
 // Take a free staging slot of the device (waits when all QR_MAX_SLOTS are in use) with at least `bytes` of device
 // staging and, when pinned_bytes > 0, a pinned mirror of that size.
 int acquire_slot(Ctx& cx, size_t bytes, size_t pinned_bytes, SlotHold& hold) {
-    std::unique_lock<std::mutex> lk(g_mu);
+    std::unique_lock<std::mutex> lk(ctx_mu(cx));
     HostSlot* s = nullptr;
     for (;;) {
         for (int i = 0; i < QR_MAX_SLOTS && !s; ++i)
@@ -432,7 +434,7 @@ int acquire_slot(Ctx& cx, size_t bytes, size_t pinned_bytes, SlotHold& hold) {
         for (int i = 0; i < QR_MAX_SLOTS && !s; ++i)
             if (!cx.slots[i].created) s = &cx.slots[i];
         if (s) break;
-        g_slot_cv.wait(lk);
+        g_slot_cv[cx.device].wait(lk);
     }
     if (!s->created) {
         for (int k = 0; k < 2; ++k) {
@@ -534,9 +536,9 @@ bool class_kg(int cap) { return cap >= QR_KG_FROM_CAP; }
 
 extern "C" int qr_gpu_mpc_occupancy(int horizon, int stance_footsteps, int* sm_count, int* ctas_per_sm,
                                     int* threads_per_cta, int* smem_bytes) {
-    std::lock_guard<std::mutex> lk(g_mu);
     Ctx* cx = current_ctx();
     if (!cx) return QR_ECUDA;
+    std::lock_guard<std::mutex> lk(ctx_mu(*cx));
     if (horizon < 1 || horizon > QR_MAX_HORIZON) return fail(QR_EINVAL, "horizon out of range");
     if (stance_footsteps < 0 || stance_footsteps > 4 * horizon) return fail(QR_EINVAL, "stance count out of range");
     const int cap = class_cap(qr_class_of(stance_footsteps), horizon);
@@ -551,7 +553,7 @@ extern "C" int qr_gpu_mpc_occupancy(int horizon, int stance_footsteps, int* sm_c
 }
 
 namespace {
-// Enqueue the fused MPC solve of one batch on `st` (g_mu held by the caller).
+// Enqueue the fused MPC solve of one batch on `st` (the context mutex held by the caller).
 int mpc_enqueue(Ctx& cx, const qr_mpc_params* P, const qr_qp_options* opt, int batch, const float* p, const float* v,
                 const float* quat, const float* w, const float* r_feet, const float* rpy, const float* traj,
                 const float* gait, const float* mu_i, const float* fmax_i, float* grf_out, float* u_out,
@@ -653,9 +655,9 @@ extern "C" int qr_gpu_mpc_solve_batch(const qr_mpc_params* P, const qr_qp_option
                                       const float* traj, const float* gait, const float* mu_i,
                                       const float* fmax_i, float* grf_out, float* u_out,
                                       int32_t* status_out, int32_t* iters_out, void* cuda_stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
     Ctx* cx = current_ctx();
     if (!cx) return QR_ECUDA;
+    std::lock_guard<std::mutex> lk(ctx_mu(*cx));
     return mpc_enqueue(*cx, P, opt, batch, p, v, quat, w, r_feet, rpy, traj, gait, mu_i, fmax_i, grf_out, u_out,
                        status_out, iters_out, (cudaStream_t)cuda_stream);
 }
@@ -667,9 +669,9 @@ extern "C" int qr_gpu_mpc_solve_batch_ex(const qr_mpc_params* P, const qr_qp_opt
                                          const float* fmax_i, float* grf_out, float* u_out,
                                          int32_t* status_out, int32_t* iters_out, const qr_mpc_epilogue* epilogue,
                                          void* cuda_stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
     Ctx* cx = current_ctx();
     if (!cx) return QR_ECUDA;
+    std::lock_guard<std::mutex> lk(ctx_mu(*cx));
     return mpc_enqueue(*cx, P, opt, batch, p, v, quat, w, r_feet, rpy, traj, gait, mu_i, fmax_i, grf_out, u_out,
                        status_out, iters_out, (cudaStream_t)cuda_stream, epilogue);
 }
@@ -679,9 +681,9 @@ extern "C" int qr_gpu_mpc_condense_batch(const qr_mpc_params* P, int batch, cons
                                          const float* r_feet, const float* rpy, const float* traj,
                                          const float* gait, const float* fmax_i, float* H_out,
                                          float* g_out, float* ub_out, void* cuda_stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
     Ctx* cx = current_ctx();
     if (!cx) return QR_ECUDA;
+    std::lock_guard<std::mutex> lk(ctx_mu(*cx));
     int rc = check_params(P, batch);
     if (rc) return rc;
     if (batch == 0) return QR_OK;
@@ -711,9 +713,9 @@ extern "C" int qr_gpu_qp_solve_batch(int horizon, float mu, const qr_qp_options*
                                      const float* H, const float* g, const float* ub,
                                      const float* mu_i, float* x_out, double* x_out_f64,
                                      int32_t* status_out, int32_t* iters_out, void* cuda_stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
     Ctx* cx = current_ctx();
     if (!cx) return QR_ECUDA;
+    std::lock_guard<std::mutex> lk(ctx_mu(*cx));
     qr_mpc_params P;
     memset(&P, 0, sizeof(P));
     P.horizon = horizon; P.mu = mu; P.dt = 1.f; P.mass = 1.f;
@@ -753,11 +755,9 @@ extern "C" int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_o
                                            const float* traj, const float* gait, const float* mu_i,
                                            const float* fmax_i, float* grf_out, float* u_out,
                                            int32_t* status_out, int32_t* iters_out) {
-    Ctx* cx = nullptr;
+    Ctx* cx = current_ctx();
+    if (!cx) return QR_ECUDA;
     {
-        std::lock_guard<std::mutex> lk(g_mu);
-        cx = current_ctx();
-        if (!cx) return QR_ECUDA;
         int rc = check_params(P, batch);
         if (rc) return rc;
     }
@@ -805,7 +805,7 @@ extern "C" int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_o
             if (e != cudaSuccess) return fail(QR_ECUDA, "cudaMemcpyAsync H2D", e);
             auto at = [&](const Row& r) -> const float* { return r.src ? r.dev + b0 * r.k : nullptr; };
             {
-                std::lock_guard<std::mutex> lk(g_mu);
+                std::lock_guard<std::mutex> lk(ctx_mu(*cx));
                 rc = mpc_enqueue(*cx, P, opt, (int)nb, at(rows[0]), at(rows[1]), at(rows[2]), at(rows[3]), at(rows[4]),
                                  at(rows[5]), at(rows[6]), at(rows[7]), at(rows[8]), at(rows[9]), dgrf + b0 * 12,
                                  du ? du + b0 * 12 * h : nullptr, dstat + b0, dit + 2 * b0, cs);
@@ -853,7 +853,7 @@ extern "C" int qr_gpu_mpc_solve_batch_host(const qr_mpc_params* P, const qr_qp_o
     int32_t* dstat = reinterpret_cast<int32_t*>(d);
     int32_t* dit = dstat + B;
     {
-        std::lock_guard<std::mutex> lk(g_mu);
+        std::lock_guard<std::mutex> lk(ctx_mu(*cx));
         rc = mpc_enqueue(*cx, P, opt, batch, dp, dv, dq, dw, dr, drpy, dtraj, dgait, dmu, dfm, dgrf, du, dstat, dit, st);
     }
     if (rc) return rc;
@@ -1021,7 +1021,7 @@ __global__ void qr_swing_parabola_kernel(int batch, const float* start, const fl
     if (valid) valid[i] = ok;
 }
 
-// Device copy of the robot constants for `model` on this context (g_mu held).  Every distinct model keeps its own
+// Device copy of the robot constants for `model` on this context (the context mutex held).  Every distinct model keeps its own
 // buffer (a few robots per process at most), so a batch in flight never sees its constants overwritten; when the
 // table is full the least recently used entry is recycled after the device has drained.
 int wbc_model_on_device(Ctx& cx, const qr_wbc_model* model, const QrWbcModelDev** out) {
@@ -1056,7 +1056,7 @@ int wbc_model_on_device(Ctx& cx, const qr_wbc_model* model, const QrWbcModelDev*
     return QR_OK;
 }
 
-// g_mu held by the caller.
+// The context mutex is held by the caller.
 int wbc_launch(Ctx& cx, const qr_wbc_model* model, int batch, const float* state, const float* cmd, const int32_t* contact,
                QrWbcArgs& A, void* cuda_stream) {
     if (!model || batch < 0) return fail(QR_EINVAL, "null model or negative batch");
@@ -1092,9 +1092,9 @@ int wbc_launch(Ctx& cx, const qr_wbc_model* model, int batch, const float* state
 extern "C" int qr_gpu_wbc_solve_batch(const qr_wbc_model* model, int batch, const float* state, const float* cmd,
                                       const int32_t* contact, float* tau_out, float* fr_out, float* qdes_out,
                                       float* qddes_out, int32_t* status_out, void* cuda_stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
     Ctx* cx = current_ctx();
     if (!cx) return QR_ECUDA;
+    std::lock_guard<std::mutex> lk(ctx_mu(*cx));
     if (batch > 0 && !tau_out) return fail(QR_EINVAL, "null output pointer");
     QrWbcArgs A;
     memset(&A, 0, sizeof(A));
@@ -1105,12 +1105,8 @@ extern "C" int qr_gpu_wbc_solve_batch(const qr_wbc_model* model, int batch, cons
 extern "C" int qr_gpu_wbc_solve_batch_host(const qr_wbc_model* model, int batch, const float* state, const float* cmd,
                                            const int32_t* contact, float* tau_out, float* fr_out, float* qdes_out,
                                            float* qddes_out, int32_t* status_out) {
-    Ctx* cx = nullptr;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        cx = current_ctx();
-        if (!cx) return QR_ECUDA;
-    }
+    Ctx* cx = current_ctx();
+    if (!cx) return QR_ECUDA;
     if (!model || batch < 0) return fail(QR_EINVAL, "null model or negative batch");
     if (batch == 0) return QR_OK;
     if (!state || !cmd || !contact || !tau_out) return fail(QR_EINVAL, "null pointer");
@@ -1149,9 +1145,9 @@ extern "C" int qr_gpu_wbc_solve_batch_host(const qr_wbc_model* model, int batch,
 extern "C" int qr_gpu_wbc_solve_batch_f64(const qr_wbc_model* model, int batch, const float* state, const float* cmd,
                                           const int32_t* contact, double* tau_out, double* fr_out, double* qdes_out,
                                           double* qddes_out, double* dbg_out, int32_t* status_out, void* cuda_stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
     Ctx* cx = current_ctx();
     if (!cx) return QR_ECUDA;
+    std::lock_guard<std::mutex> lk(ctx_mu(*cx));
     if (batch > 0 && !tau_out) return fail(QR_EINVAL, "null output pointer");
     QrWbcArgs A;
     memset(&A, 0, sizeof(A));
@@ -1162,9 +1158,9 @@ extern "C" int qr_gpu_wbc_solve_batch_f64(const qr_wbc_model* model, int batch, 
 extern "C" int qr_gpu_swing_parabola_batch(int batch, const float* start, const float* end, const float* height,
                                            const float* phase, int phase_module, float* pos_out, int32_t* valid_out,
                                            void* cuda_stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
     Ctx* cx = current_ctx();
     if (!cx) return QR_ECUDA;
+    std::lock_guard<std::mutex> lk(ctx_mu(*cx));
     if (batch < 0) return fail(QR_EINVAL, "negative batch");
     if (batch == 0) return QR_OK;
     if (!start || !end || !height || !phase || !pos_out) return fail(QR_EINVAL, "null pointer");
@@ -1209,9 +1205,9 @@ extern "C" int qr_gpu_mpc_inputs_batch(int horizon, int num_horizon_l, float dt_
                                        const float* duty, const int32_t* early_contact, const int32_t* contacts,
                                        const float* traj_init, const float* pos_xy, float* gait_out, float* traj_out,
                                        void* cuda_stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
     Ctx* cx = current_ctx();
     if (!cx) return QR_ECUDA;
+    std::lock_guard<std::mutex> lk(ctx_mu(*cx));
     if (horizon < 1 || horizon > QR_MAX_HORIZON || num_horizon_l < 1 || batch < 0) return fail(QR_EINVAL, "bad size argument");
     if (batch == 0) return QR_OK;
     if (gait_out && (!progress || !duty)) return fail(QR_EINVAL, "contact table needs progress and duty");
@@ -1226,9 +1222,9 @@ extern "C" int qr_gpu_mpc_inputs_batch(int horizon, int num_horizon_l, float dt_
 extern "C" int qr_gpu_mpc_leg_torque_batch(float hip_len, float upper_len, float lower_len, int batch, const float* quat,
                                            const float* q, const float* grf, float* f_ff_out, float* tau_out,
                                            void* cuda_stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
     Ctx* cx = current_ctx();
     if (!cx) return QR_ECUDA;
+    std::lock_guard<std::mutex> lk(ctx_mu(*cx));
     if (batch < 0) return fail(QR_EINVAL, "negative batch");
     if (batch == 0) return QR_OK;
     if (!quat || !q || !grf || !tau_out) return fail(QR_EINVAL, "null pointer");
@@ -1255,9 +1251,9 @@ extern "C" int qr_gpu_force_balance_batch(const qr_fb_params* P, int batch, cons
                                           const float* acc, const int32_t* contact, const float* gravity,
                                           const float* frame, float* force_out, int32_t* status_out, int32_t* iters_out,
                                           void* cuda_stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
     Ctx* cx = current_ctx();
     if (!cx) return QR_ECUDA;
+    std::lock_guard<std::mutex> lk(ctx_mu(*cx));
     if (!P || batch < 0) return fail(QR_EINVAL, "null params or negative batch");
     if (!(P->mass > 0.f) || !(P->mu > 0.f)) return fail(QR_EINVAL, "mass and mu must be positive");
     if (batch == 0) return QR_OK;
@@ -1311,9 +1307,9 @@ __global__ void qr_foothold_kernel(const QrFootholdParams P, int batch, const Qr
 extern "C" int qr_gpu_swing_bspline_batch(int batch, const float* initial_pos, const float* target_pos, const float* height,
                                           const float* duration, const float* initial_time, const float* time,
                                           float* pos_out, float* vel_out, int32_t* valid_out, void* cuda_stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
     Ctx* cx = current_ctx();
     if (!cx) return QR_ECUDA;
+    std::lock_guard<std::mutex> lk(ctx_mu(*cx));
     if (batch < 0) return fail(QR_EINVAL, "negative batch");
     if (batch == 0) return QR_OK;
     if (!initial_pos || !target_pos || !height || !duration || !initial_time || !time || !pos_out || !vel_out)
@@ -1330,9 +1326,9 @@ extern "C" int qr_gpu_foothold_heuristic_batch(const qr_foothold_params* P, int 
                                                const float* des_speed, const float* des_twist, const float* des_height,
                                                const float* swing_remain, const float* norm_phase, const int32_t* allow_switch,
                                                const int32_t* swing_mask, float* foothold_io, float* phase_io, void* cuda_stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
     Ctx* cx = current_ctx();
     if (!cx) return QR_ECUDA;
+    std::lock_guard<std::mutex> lk(ctx_mu(*cx));
     if (!P || batch < 0) return fail(QR_EINVAL, "null params or negative batch");
     if (batch == 0) return QR_OK;
     if (!com_vel || !rpy_rate || !dR || !base_R || !rpy || !foot_base || !des_speed || !des_twist || !des_height ||
@@ -1465,9 +1461,9 @@ int launch_check(const char* what) {
 
 extern "C" int qr_gpu_mpc_lever_arms_batch(int batch, const float* quat, const float* foot_base, const float* com_offset,
                                            float* r_feet_out, void* cuda_stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
     Ctx* cx = current_ctx();
     if (!cx) return QR_ECUDA;
+    std::lock_guard<std::mutex> lk(ctx_mu(*cx));
     if (batch < 0) return fail(QR_EINVAL, "negative batch");
     if (batch == 0) return QR_OK;
     if (!quat || !foot_base || !com_offset || !r_feet_out) return fail(QR_EINVAL, "null pointer");
@@ -1478,9 +1474,9 @@ extern "C" int qr_gpu_mpc_lever_arms_batch(int batch, const float* quat, const f
 
 extern "C" int qr_gpu_leg_kinematics_batch(const qr_leg_geometry* geom, int batch, const float* q, const float* qd,
                                            float* foot_base_out, float* jac_out, float* foot_vel_out, void* cuda_stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
     Ctx* cx = current_ctx();
     if (!cx) return QR_ECUDA;
+    std::lock_guard<std::mutex> lk(ctx_mu(*cx));
     if (!geom || batch < 0) return fail(QR_EINVAL, "null geometry or negative batch");
     if (batch == 0) return QR_OK;
     if (!q || (foot_vel_out && !qd)) return fail(QR_EINVAL, "null pointer");
@@ -1491,9 +1487,9 @@ extern "C" int qr_gpu_leg_kinematics_batch(const qr_leg_geometry* geom, int batc
 
 extern "C" int qr_gpu_leg_ik_batch(const qr_leg_geometry* geom, int batch, const float* foot_base, const float* foot_vel,
                                    const int32_t* leg_mask, float* q_out, float* qd_out, void* cuda_stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
     Ctx* cx = current_ctx();
     if (!cx) return QR_ECUDA;
+    std::lock_guard<std::mutex> lk(ctx_mu(*cx));
     if (!geom || batch < 0) return fail(QR_EINVAL, "null geometry or negative batch");
     if (batch == 0) return QR_OK;
     if (!foot_base || !q_out || (qd_out && !foot_vel)) return fail(QR_EINVAL, "null pointer");
@@ -1507,9 +1503,9 @@ extern "C" int qr_gpu_swing_targets_batch(const qr_leg_geometry* geom, int batch
                                           const float* switch_pos, const float* swing_duration, const int32_t* swing_mask,
                                           int horizontal_terrain, float* wbc_cmd_io, float* foot_base_des_out, float* q_des_out,
                                           float* qd_des_out, int32_t* valid_out, void* cuda_stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
     Ctx* cx = current_ctx();
     if (!cx) return QR_ECUDA;
+    std::lock_guard<std::mutex> lk(ctx_mu(*cx));
     if (!geom || batch < 0) return fail(QR_EINVAL, "null geometry or negative batch");
     if (batch == 0) return QR_OK;
     if (!base_pos || !quat || !v_world || !foothold || !planner_phase || !switch_pos || !swing_duration || !swing_mask || !wbc_cmd_io)
@@ -1527,9 +1523,9 @@ extern "C" int qr_gpu_gait_update_batch(int batch, const float* time, const floa
                                         float* fstate_io, float* phase_full_io, float* norm_phase_io, float* swing_remain_io,
                                         int32_t* allow_out, int32_t* early_out, int32_t* swing_mask_out, int32_t* stance_mask_out,
                                         void* cuda_stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
     Ctx* cx = current_ctx();
     if (!cx) return QR_ECUDA;
+    std::lock_guard<std::mutex> lk(ctx_mu(*cx));
     if (batch < 0) return fail(QR_EINVAL, "negative batch");
     if (batch == 0) return QR_OK;
     if (!time || !cfg || !contacts || !istate_io || !fstate_io || !phase_full_io || !norm_phase_io || !swing_remain_io)
