@@ -638,3 +638,17 @@ def ref_contact_force_world(params: dict, quat, foot_base, acc, contact, n=(0, 0
                                           _fp(_f32(t2)), _fp(_f32(params["acc_weight"])), _fp(_f32(params["fmin_ratio"])),
                                           _fp(_f32(params["fmax_ratio"])), C.c_float(params["reg_weight"]), C.c_float(params["mu"]), _fp(out))
     return out
+
+
+def ref_contact_force_control(params: dict, quat, foot_base, acc, contact, terrain_type=0, control_rpy=(0, 0, 0), aligned=None):
+    """Quadruped::ComputeContactForce, control-frame overload (qr_qp_torque_optimizer.cpp:190-301) compiled from the reference.
+    Returns (F[12] = (X Rcb)^T column-major, dict(Rcb[3,3], inertia[9], foot[12] rows of the 4x3 footPosition, gravity[3], normal[3]))."""
+    out, der = np.zeros(12, np.float32), np.zeros(36, np.float32)
+    aligned = np.eye(3, dtype=np.float32) if aligned is None else _f32(aligned)
+    _ref_ctl().qr_ref_contact_force_control(C.c_float(params["mass"]), _fp(_f32(np.asarray(params["inertia"]).reshape(9))), _fp(_f32(quat)),
+                                            _fp(_f32(foot_base)), _fp(_f32(acc)), _ip(_i32(contact)), int(terrain_type), _fp(_f32(control_rpy)),
+                                            _fp(_f32(np.asarray(aligned).reshape(9))), _fp(_f32(params["acc_weight"])),
+                                            C.c_float(params["fmin_ratio"][0]), C.c_float(params["fmax_ratio"][0]),
+                                            C.c_float(params["reg_weight"]), C.c_float(params["mu"]), _fp(out), _fp(der))
+    return out, dict(Rcb=der[:9].reshape(3, 3).copy(), inertia=der[9:18].copy(), foot=der[18:30].copy(), gravity=der[30:33].copy(),
+                     normal=der[33:36].copy())

@@ -536,4 +536,60 @@ int qr_ref_contact_force_world(float mass, const float* inertia9, const float* q
     return 0;
 }
 
+// Quadruped::ComputeContactForce, control-frame overload (qr_qp_torque_optimizer.cpp:190-301), through the reference's
+// own helpers + QuadProg++.  terrain_type: TerrainType (PLANE 0 ... SLOPE 3); control_rpy [3], aligned [9] row-major =
+// groundEstimator->GetControlFrameRPY() / GetAlignedDirections().
+//   out [12] = the returned 3x4 matrix (X * Rcb)^T, column-major (leg columns)
+//   derived [9 + 9 + 12 + 3 + 3] (optional): Rcb, Rcb I Rcb^T, (Rcb footPos)^T (4x3 row-major), g.head(3), surfaceNormal --
+//   the quantities the reference derives at :203-225 before it calls its helpers, recomputed here with the same
+//   expressions so that a test can hand them to the restatement / the kernel, whose inputs they are
+int qr_ref_contact_force_control(float mass, const float* inertia9, const float* quat, const float* foot_base,
+                                 const float* desired_acc, const int* contacts, int terrain_type, const float* control_rpy,
+                                 const float* aligned9, const float* acc_weight, float fmin_ratio, float fmax_ratio,
+                                 float reg_weight, float mu, float* out, float* derived) {
+    qrRobot robot;
+    qrGroundSurfaceEstimator ge;
+    robot.totalMass = mass;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            robot.totalInertia(a, b) = inertia9[3 * a + b];
+            ge.alignedDirections(a, b) = aligned9[3 * a + b];
+        }
+    for (int a = 0; a < 3; ++a) ge.controlFrameRPY[a] = control_rpy[a];
+    ge.terrain.terrainType = (TerrainType)terrain_type;
+    for (int a = 0; a < 4; ++a) robot.baseOrientation[a] = quat[a];
+    for (int l = 0; l < 4; ++l)
+        for (int a = 0; a < 3; ++a) robot.stateDataFlow.footPositionsInBaseFrame(a, l) = foot_base[3 * l + a];
+    Eigen::Matrix<float, 6, 1> acc, w;
+    for (int i = 0; i < 6; ++i) {
+        acc[i] = desired_acc[i];
+        w[i] = acc_weight[i];
+    }
+    Eigen::Matrix<bool, 4, 1> c;
+    for (int l = 0; l < 4; ++l) c[l] = contacts[l] != 0;
+    Eigen::Matrix<float, 3, 4> F = ComputeContactForce(&robot, &ge, acc, c, w, reg_weight, mu, fmin_ratio, fmax_ratio);
+    for (int l = 0; l < 4; ++l)
+        for (int a = 0; a < 3; ++a) out[3 * l + a] = F(a, l);
+    if (derived) {
+        Mat3<float> Rcb;
+        Vec3<float> g3(0.f, 0.f, 9.8f), normal(0.f, 0.f, 1.f);
+        if (terrain_type == TerrainType::PLANE || terrain_type == TerrainType::PLUM_PILES) {
+            Rcb = Mat3<float>::Identity();
+        } else {   // :217-219
+            Rcb = ge.alignedDirections.transpose() * robotics::math::quaternionToRotationMatrix(robot.baseOrientation).transpose();
+            g3 = ge.alignedDirections.transpose() * g3;
+            normal << -std::sin(control_rpy[1]), 0.f, std::cos(control_rpy[1]);
+        }
+        Mat3<float> inertia = Rcb * robot.totalInertia * Rcb.transpose();                                             // :224
+        Eigen::Matrix<float, 4, 3> footPosition = (Rcb * robot.GetFootPositionsInBaseFrame()).transpose();           // :225
+        float* o = derived;
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) *o++ = Rcb(a, b);
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) *o++ = inertia(a, b);
+        for (int l = 0; l < 4; ++l) for (int a = 0; a < 3; ++a) *o++ = footPosition(l, a);
+        for (int a = 0; a < 3; ++a) *o++ = g3[a];
+        for (int a = 0; a < 3; ++a) *o++ = normal[a];
+    }
+    return 0;
+}
+
 }   // extern "C"

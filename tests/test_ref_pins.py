@@ -141,3 +141,29 @@ def test_force_balance_restatement_is_the_reference(ref, pkg):
         assert np.array_equal(r, o["force"]), i
         seen_swing += int(fb["contact"][i].sum() < 4)
     assert seen_swing > 50
+
+
+def test_force_balance_control_frame_overload(ref, pkg):
+    """Control-frame overload of ComputeContactForce (qr_qp_torque_optimizer.cpp:190-301) compiled from the reference, fed
+    through a ground-estimator stand-in: on flat ground (Rcb = I) the restatement's forces equal it bit for bit; on a slope
+    the QP data (Rcb I Rcb', rotated feet, rotated gravity, tilted normal -- derived by the same expressions, :203-225)
+    give the same X, compared after the reference's final X * Rcb in float32."""
+    fb = pkg.synth.make_fb_batch("a1", 96, seed=4, world_frame=False)
+    P = ref.fb_params_of(fb["params"])
+    rng = np.random.default_rng(5)
+    for i in range(96):
+        F, d = ref.ref_contact_force_control(fb["params"], [1, 0, 0, 0], fb["foot"][i], fb["acc"][i], fb["contact"][i], terrain_type=0)
+        o = ref.force_balance(P, d["foot"], fb["acc"][i], fb["contact"][i], inertia=d["inertia"], gravity=d["gravity"])
+        assert np.array_equal(F.reshape(4, 3), o["force"].reshape(4, 3)), i
+        pitch, roll = rng.uniform(-0.3, 0.3), rng.uniform(-0.1, 0.1)
+        quat = pkg.synth._quat_from_rpy(np.array([[roll, pitch, 0.0]]))[0].astype(F32)
+        cp = F32(pitch + rng.uniform(-0.05, 0.05))
+        Rg = pkg.synth._rot_zyx(np.array([[0.0, float(cp), 0.0]]))[0].astype(F32)
+        F, d = ref.ref_contact_force_control(fb["params"], quat, fb["foot"][i], fb["acc"][i], fb["contact"][i], terrain_type=3,
+                                             control_rpy=(0, cp, 0), aligned=Rg)
+        n, t2 = d["normal"], np.array([0, 1, 0], F32)
+        t1 = np.cross(t2, n).astype(F32)          # :95-96
+        o = ref.force_balance(P, d["foot"], fb["acc"][i], fb["contact"][i], inertia=d["inertia"], gravity=d["gravity"],
+                              frame=np.concatenate([n, t1, t2]).astype(F32))
+        want = (o["force"].reshape(4, 3).astype(F32) @ d["Rcb"]).astype(F32)
+        assert np.abs(F.reshape(4, 3) - want).max() <= 2e-5 * max(1.0, np.abs(want).max()), i
