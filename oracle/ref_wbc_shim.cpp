@@ -7,10 +7,9 @@
 //   src/controllers/wbc/task_set/qr_task_*.cpp          body orientation / body position / link position
 //   src/controllers/wbc/qr_multitask_projection.cpp     qrMultitaskProjection<float>
 //   src/controllers/wbc/qr_wholebody_impulse_ctrl.cpp   qrWholeBodyImpulseCtrl<float> (+ QuadProg++)
-// What cannot be compiled here is the glue around them -- qrWbcLocomotionController and
-// qrRobot*::BuildDynamicModel need the robot / estimator / ROS / yaml classes -- so this file plays
-// that part: it feeds the model constants of src/robots/qr_robot_a1_sim.cpp:176-345 (Lite3 file
-// identical) to FloatingBaseModel's builder API and then issues the call sequence of
+// What cannot be compiled here is the glue around them -- qrWbcLocomotionController needs the robot /
+// estimator / ROS classes -- so this file plays that part: it runs the reference's own BuildDynamicModel
+// (cut out of src/robots/qr_robot_a1_sim.cpp:176-345, see below) and then issues the call sequence of
 // qr_wbc_locomotion_controller.cpp:29-73 (construction, gains), :138-168 (UpdateModel),
 // :172-201 (ContactTaskUpdate), :122-124 (FindConfiguration, MakeTorque).
 // Same C signature as qro_wbc_step_f32 (qr_oracle.h) so tests can hold the two side by side.
@@ -30,77 +29,41 @@
 using robotics::math::coordinateRotation;
 using robotics::math::CoordinateAxis;
 
+// qrRobotA1Sim::BuildDynamicModel (src/robots/qr_robot_a1_sim.cpp:176-345; qr_robot_lite3_sim.cpp:176-345 is the same
+// text) compiled from the reference: the Makefile cuts its body (lines 178-344, up to the dormant self-test) into
+// _ref/gen/build_model.inc, and qrRobot::WithLegSigns (qr_robot.cpp:89-104) into _ref/gen/robot_signs.inc; the class
+// below only supplies the members the body reads (the yaml node is a three-number stand-in).
+namespace Quadruped {
+struct CfgNode {
+    std::vector<float> body_size;
+    CfgNode operator[](const char*) const { return *this; }
+    template <class T> T as() const { return body_size; }
+};
+class qrRobot {
+public:
+    CfgNode robotConfig;
+    float hipLength = 0, upperLegLength = 0, lowerLegLength = 0;
+    FloatingBaseModel<float> model;
+    Vec3<float> WithLegSigns(const Vec3<float>& v, int leg_id);
+    bool BuildDynamicModel();
+};
+#include "gen/robot_signs.inc"
+bool qrRobot::BuildDynamicModel() {
+#include "gen/build_model.inc"
+    return true;
+}
+}   // namespace Quadruped
+
 namespace {
-
-typedef SpatialInertia<float> SI;
-
-Vec3<float> signed_for_leg(const Vec3<float>& v, int leg) {   // qrRobot::WithLegSigns, qr_robot.cpp:89-104
-    const float sx = leg < 2 ? 1.f : -1.f, sy = (leg % 2 == 0) ? -1.f : 1.f;
-    return Vec3<float>(sx * v[0], sy * v[1], v[2]);
-}
-
-Mat3<float> micro(std::initializer_list<double> v) {   // `M << ...; M = M * 1e-6`
-    Mat3<float> m;
-    int i = 0;
-    for (double x : v) {
-        m(i / 3, i % 3) = x;
-        ++i;
-    }
-    return m * 1e-6;
-}
-
 void build_model(FloatingBaseModel<float>& model, const qro_wbc_model* cfg) {
-    const float hipLength = cfg->hip_len, upperLegLength = cfg->upper_len, lowerLegLength = cfg->lower_len;
-    Vec3<float> bodyDims(cfg->body_size[0], cfg->body_size[1], cfg->body_size[2]);
-
-    Mat3<float> rotorZ;
-    rotorZ.setIdentity();
-    float scale_ = 1e-2;
-    rotorZ = scale_ * 1e-6 * rotorZ;
-    Mat3<float> RY = coordinateRotation<float>(CoordinateAxis::Y, M_PI / 2);
-    Mat3<float> RX = coordinateRotation<float>(CoordinateAxis::X, M_PI / 2);
-    Mat3<float> rotorX = RY * rotorZ * RY.transpose();
-    Mat3<float> rotorY = RX * rotorZ * RX.transpose();
-
-    SI abad(0.696, Vec3<float>(-0.0033, 0, 0),
-            micro({469.2, -9.4, -0.342, -9.4, 807.5, -0.466, -0.342, -0.466, 552.9}));
-    SI hip(1.013, Vec3<float>(-0.003237, -0.022327, -0.027326),
-           micro({5529, 4.825, 343.9, 4.825, 5139.3, 22.4, 343.9, 22.4, 1367.8}));
-    SI knee(0.166, Vec3<float>(0.006435, 0, -0.107), micro({2998, 0, -141.2, 0, 3014, 0, -141.2, 0, 32.4}));
-    SI body(6, Vec3<float>(0, 0, 0), micro({15853, 0, 0, 0, 37799, 0, 0, 0, 45654}));
-    Vec3<float> origin(0, 0, 0);
-    float rotorMass = 1e-8;
-    SI rotX(rotorMass, origin, rotorX), rotY(rotorMass, origin, rotorY);
-
-    model.addBase(body);
-    model.addGroundContactBoxPoints(5, bodyDims);
-
-    const Mat3<float> I3 = Mat3<float>::Identity();
-    const Vec3<float> abadLoc(0.1805f, 0.047f, 0.f), abadRotorLoc(0.14f, 0.047f, 0.f), hipLoc(0, hipLength, 0),
-        hipRotorLoc(0, 0.04, 0), kneeLoc(0, 0, -upperLegLength);
-    const float kneeLinkY_offset = 0.004;
-    int id = 5;
-    for (int leg = 0; leg < 4; ++leg) {
-        const bool right = (leg % 2 == 0);   // sideSign < 0 in the reference loop
-        auto side = [&](SI s) { return right ? s.flipAlongAxis(CoordinateAxis::Y) : s; };
-        const int abadId = ++id;
-        model.addBody(side(abad), side(rotX), 1.f, 5, JointType::Revolute, CoordinateAxis::X,
-                      createSXform(I3, signed_for_leg(abadLoc, leg)), createSXform(I3, signed_for_leg(abadRotorLoc, leg)));
-        const int hipId = ++id;
-        model.addBody(side(hip), side(rotY), 1.f, abadId, JointType::Revolute, CoordinateAxis::Y,
-                      createSXform(I3, signed_for_leg(hipLoc, leg)),
-                      createSXform(coordinateRotation(CoordinateAxis::Z, float(M_PI)), signed_for_leg(hipRotorLoc, leg)));
-        model.addGroundContactPoint(hipId, Vec3<float>(0, 0, -upperLegLength));
-        const int kneeId = ++id;
-        model.addBody(knee, side(rotY), 1.f, hipId, JointType::Revolute, CoordinateAxis::Y, createSXform(I3, kneeLoc),
-                      createSXform(I3, origin));
-        model.addGroundContactPoint(kneeId, Vec3<float>(0, right ? kneeLinkY_offset : -kneeLinkY_offset, -lowerLegLength),
-                                    true);
-    }
-    Vec3<float> g(0, 0, -9.81);
-    model.setGravity(g);
+    Quadruped::qrRobot r;
+    r.robotConfig.body_size = {cfg->body_size[0], cfg->body_size[1], cfg->body_size[2]};
+    r.hipLength = cfg->hip_len;
+    r.upperLegLength = cfg->upper_len;
+    r.lowerLegLength = cfg->lower_len;
+    r.BuildDynamicModel();
+    model = r.model;
 }
-
 }   // namespace
 
 namespace {
