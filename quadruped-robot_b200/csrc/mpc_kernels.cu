@@ -33,7 +33,10 @@ __host__ __device__ inline int qr_class_of(int nf) {
     if (nf <= 72) { const int c = (nf + QR_CLASS_STEP - 1) / QR_CLASS_STEP - 1; return c < 0 ? 0 : c; }
     return nf <= 96 ? 9 : 10;
 }
-constexpr int QR_KG_FROM_CAP = 96;   // smallest capacity whose matrix under factorisation lives in the global scratch
+#ifndef QR_KG_FROM
+#define QR_KG_FROM 96
+#endif
+constexpr int QR_KG_FROM_CAP = QR_KG_FROM;   // smallest capacity whose matrix under factorisation lives in the global scratch
 
 // Size classification: one thread per instance counts its stance foot-steps (gait * f_max > 0, the
 // rows SolveMPC would give a non-zero upper bound, qr_mpc_interface.cpp:387) and appends the instance
@@ -74,6 +77,9 @@ __global__ void qr_mpc_classify_kernel(const QrMpcArgs A, int nclass, int* count
 #ifndef QR_NT_LARGE
 #define QR_NT_LARGE 256
 #endif
+#ifndef QR_CTAS_LARGE
+#define QR_CTAS_LARGE 1   // resident CTAs per SM asked of the compiler for the 56..72 foot-step classes
+#endif
 #ifndef QR_HSG_FROM
 #define QR_HSG_FROM 8     // smallest capacity that keeps the Hessian in the global scratch (8: every class)
 #endif
@@ -81,7 +87,7 @@ __host__ __device__ constexpr int qr_fused_nt(int cap) {
     return cap <= 24 ? QR_NT_SMALL : (cap >= 56 && cap <= 72 ? QR_NT_LARGE : QR_NT);
 }
 __host__ __device__ constexpr int qr_fused_min_ctas(int cap) {
-    return cap <= 24 ? QR_CTAS_SMALL : (cap == 32 ? 4 : (cap == 40 ? 3 : (cap == 48 ? 2 : (cap <= 72 ? 1 : 5))));
+    return cap <= 24 ? QR_CTAS_SMALL : (cap == 32 ? 4 : (cap == 40 ? 3 : (cap == 48 ? 2 : (cap <= 72 ? QR_CTAS_LARGE : 5))));
 }
 template <int CAP, bool HSG, bool KG>
 __global__ void __launch_bounds__(qr_fused_nt(CAP), qr_fused_min_ctas(CAP)) qr_mpc_fused_kernel(const QrMpcArgs A) {
