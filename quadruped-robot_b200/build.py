@@ -10,7 +10,7 @@ LIB = os.path.join(_HERE, "libqr_gpu.so")
 PEAKS_LIB = os.path.join(_HERE, "libqr_peaks.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SOURCES = ["mpc_kernels.cu"]
-HEADERS = ["qr_team.h", "mpc_condense.h", "qp_solver.h", "mpc_problem.h", "wbc_model.h", "wbc_problem.h", "mpc_io.h", "small_qp.h", "fb_problem.h", "swing_extra.h"]
+HEADERS = ["qr_team.h", "mpc_condense.h", "qp_solver.h", "mpc_problem.h", "wbc_model.h", "wbc_problem.h", "mpc_io.h", "small_qp.h", "fb_problem.h", "swing_extra.h", "chol8.h", "ctl_extra.h"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-shared"]
 

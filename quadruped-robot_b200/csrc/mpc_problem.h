@@ -56,6 +56,7 @@ QR_HD int qr_coarse_cap(int nfcap) { return (3 * nfcap + 3) / 4; }
 QR_HD int qr_coarse2_cap(int nfcap) { return nfcap >= QR_COARSE2_MIN_CAP ? (3 * qr_coarse_cap(nfcap) + 3) / 4 : 0; }
 QR_HD size_t qr_kbytes(int nfcap) {
     size_t kb = (size_t)9 * qr_ntri(nfcap) * sizeof(double);
+    if (qr_k8_bytes(nfcap) > kb) kb = qr_k8_bytes(nfcap);   // long-horizon classes: room for the 8x8-tile layout of chol8.h
     return kb > sizeof(QrCondenseTables) ? kb : ((sizeof(QrCondenseTables) + 15) & ~(size_t)15);
 }
 
@@ -106,6 +107,7 @@ QR_DEV void qr_mpc_carve(QrMpcSmem& S, unsigned char* base, int nfcap, int horiz
     const int n = 3 * nfcap, m = 5 * nfcap;
     if (hs_global) W.Hs = hs_global;
     else { W.Hs = d; d += 9 * qr_ntri(nfcap); }
+    W.k8 = (!k_global && qr_k8_bytes(nfcap) > 0) ? 1 : 0;
     if (k_global) {
         W.K = k_global;
         S.T = reinterpret_cast<QrCondenseTables*>(d);

@@ -46,6 +46,7 @@
 
 struct QrQpWork {
     int nf;             // stance foot-steps
+    int k8;             // device: K is in shared memory with room for the 8x8-tile layout of chol8.h (set by the carve)
     double mu_;         // 1/mu as the reference rounds it (float32 value)
     double* Hs;         // [9*ntri(cap)] shared: symmetric block-packed Hessian
     double* K;          // [9*ntri(cap)] shared: matrix under factorisation
@@ -168,6 +169,8 @@ QR_DEV void qr_inv3_sym(double a, double b, double c, double d, double e, double
     o[3] = o[1];    o[4] = c11 * r; o[5] = c12 * r;
     o[6] = o[2];    o[7] = o[5];    o[8] = c22 * r;
 }
+
+#include "chol8.h"   // blocked Cholesky on the FP64 tensor cores for the large reduced systems (device only)
 
 // Block LDL' factorisation K = L D L' of the leading nb x nb blocks (3x3 pivot blocks, no pivoting:
 // K is symmetric positive definite), fused with the forward substitution of the right-hand side
@@ -516,6 +519,14 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
         const int nred = W.foff[nf];
         const int nbr = (nred + 2) / 3;
         QR_TRACE_ROUND(round, nred, W);
+#if defined(QR_ON_DEVICE)
+        // large systems of the long-horizon classes: 8x8 tiles, blocked Cholesky on the FP64 tensor cores (chol8.h)
+        const bool big = NT >= 128 && W.k8 && nbr >= QR_CHOL8_MIN_NB;
+        const int nt8 = qr_k8_nt(nred);
+#else
+        const bool big = false;
+        const int nt8 = 0;
+#endif
         // ---- reduced matrix Z'HZ (column-packed, see qr_kblk), padded to a multiple of 3 with identity.
         // One thread per PAIR of foot-steps: the 3x3 block H_{f1 f2} is loaded once and contributes its d1 x d2
         // entries Z_f1' (H_{f1 f2} Z_f2) -- the same products in the same order as an entry-wise evaluation, with a
@@ -544,6 +555,13 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
                         if (r2 <= r1) {
                             const double* y = W.zv + 3 * r1;
                             const double val = y[0] * t0 + y[1] * t1 + y[2] * t2;
+#if defined(QR_ON_DEVICE)
+                            if (big) {
+                                W.K[qr_k8_idx(nt8, r1, r2)] = val;
+                                if ((r1 >> 3) == (r2 >> 3)) W.K[qr_k8_idx(nt8, r2, r1)] = val;
+                                continue;
+                            }
+#endif
                             const int I = r1 / 3, ri = r1 - 3 * I;
                             double* blk = W.K + qr_kblk(nbr, I, J);
                             blk[3 * ri + rj] = val;
@@ -553,6 +571,22 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
                 }
             }
         }
+#if defined(QR_ON_DEVICE)
+        if (big) {   // identity padding rows nred .. 8*nt8-1, right-hand side padded with zeros
+            QR_FOR(idx, (8 * nt8 - nred) * 8 * nt8) {
+                const int r = nred + idx / (8 * nt8), c = idx - (r - nred) * (8 * nt8);
+                if (c <= r) {
+                    W.K[qr_k8_idx(nt8, r, c)] = (r == c) ? 1.0 : 0.0;
+                    if ((c >> 3) == (r >> 3)) W.K[qr_k8_idx(nt8, c, r)] = (r == c) ? 1.0 : 0.0;
+                }
+            }
+            QR_FOR(r, 8 * nt8) {
+                const int f = r < nred ? W.rfoot[r] : -1;
+                W.wv[r] = f < 0 ? 0.0
+                                : -(W.zv[3 * r] * W.q[3 * f] + W.zv[3 * r + 1] * W.q[3 * f + 1] + W.zv[3 * r + 2] * W.q[3 * f + 2]);
+            }
+        } else {
+#endif
         QR_FOR(idx, (3 * nbr - nred) * 3 * nbr) {   // identity padding rows nred .. 3*nbr-1
             const int r = nred + idx / (3 * nbr), c = idx - (r - nred) * (3 * nbr);
             if (c <= r) {
@@ -566,8 +600,21 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
             W.wv[r] = f < 0 ? 0.0
                             : -(W.zv[3 * r] * W.q[3 * f] + W.zv[3 * r + 1] * W.q[3 * f + 1] + W.zv[3 * r + 2] * W.q[3 * f + 2]);
         }
+#if defined(QR_ON_DEVICE)
+        }
+#endif
         QR_SYNC();
         QR_PROF(4);
+#if defined(QR_ON_DEVICE)
+        if (big) {
+            if constexpr (NT >= 128) {
+                qr_chol8_factor<NT>(W.K, W.wv, W.tri, nt8, 1);
+                QR_PROF(11);
+                qr_chol8_backward<NT>(W.K, W.wv, W.Dinv, nt8, W.dx, nred);   // Dinv is free on this path: 8 doubles of scratch
+                QR_PROF(13);
+            }
+        } else
+#endif
         if (nbr > 0) {   // nbr == 0: every foot-step is pinned to the apex, x = p and only the verification is left
             qr_ldl_factor<NT>(W, nbr, 1 QR_PROF_PASS);
             qr_ldl_backward<NT>(W, nbr, W.dx QR_PROF_PASS);

@@ -99,6 +99,7 @@ QR_DEV void qr_wbc_carve(QrWbcWork& W, unsigned char* base) {
     W.svdB = take(216); W.svdV = take(144); W.svdS = take(12);
     W.qdd = take(18); W.dq = take(18); W.qdot = take(18); W.vec = take(18); W.tot = take(18); W.P6 = take(72); W.a0 = take(6); W.A6 = take(36);
     QrQpWork& Q = W.Q;
+    Q.k8 = 0;
     Q.Hs = take(90); Q.K = take(90); Q.Dinv = take(36); Q.zv = take(36);
     Q.ps = take(12); Q.g = take(12); Q.xn = take(12); Q.q = take(12); Q.wv = take(12); Q.dx = take(12);
     Q.ubz = take(4);

@@ -27,7 +27,7 @@ def run(tag, robot, h, nb, gait, seed, reps):
     for i in range(reps): capi.mpc_solve_batch_device(P, d, out, st)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    print(f"{name} {tag}: {nb / ms * 1e3 / 1e3:.1f} k QP/s ({ms:.2f} ms) bad {int((out['status'] != 0).sum())} rounds {float(out['iters'][:,1].float().mean()):.2f} max {int(out['iters'][:,1].max())} ipm_inst {int((out['iters'][:,0]>0).sum())} ipm_max {int(out['iters'][:,0].max())}", flush=True)
+    print(f"{name} {tag}: {nb / ms * 1e3 / 1e3:.1f} k QP/s ({ms:.2f} ms) bad {int((out['status'] != 0).sum())} rounds {float(out['iters'][:,1].float().mean()):.2f} max {int(out['iters'][:,1].max())} ipm_inst {int((out['iters'][:,0]>0).sum())} ipm_max {int(out['iters'][:,0].max())} grf abs-sum {float(out['grf'].double().abs().sum()):.6f}", flush=True)
 if "h30" in which: run("h30", "a1", 30, 4096, "trot", 14, 3)
 if "mixed" in which: run("mixed", "aliengo", 10, 16384, "mixed", 13, 5)
 if "trot" in which: run("trot", "a1", 10, 65536, "trot", 0, 5)
