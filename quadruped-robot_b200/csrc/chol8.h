@@ -23,13 +23,13 @@
 #pragma once
 
 #ifndef QR_CHOL8_MIN_NB
-#define QR_CHOL8_MIN_NB 20   // reduced systems of at least this many 3x3 block columns take this path (when the class supports it)
+#define QR_CHOL8_MIN_NB 16   // reduced systems of at least this many 3x3 block columns take this path (when the class supports it)
 #endif
 #ifndef QR_CHOL8_MIN_CAP
 #define QR_CHOL8_MIN_CAP 56  // workspace classes (stance foot-steps) whose K region is sized for the 8x8 layout
 #endif
 #ifndef QR_CHOL8_BIAS
-#define QR_CHOL8_BIAS 8      // trailing tiles each other warp takes before warp 0 (busy with the next diagonal factor) joins in
+#define QR_CHOL8_BIAS 14     // trailing tiles each other warp takes before warp 0 (busy with the next diagonal factor) joins in
 #endif
 
 #ifndef QR_C8P
@@ -60,17 +60,35 @@ __device__ __forceinline__ void qr_dmma(double& c0, double& c1, double a, double
 
 // Cholesky factor of one 8x8 diagonal tile, returned as its inverse R = L^-1 (lower triangular) written over the tile
 // with zeros above the diagonal.  Called by a whole warp: every lane runs the same register-resident recurrence (no
-// shuffles on the dependent chain) and stores every entry (same value, same address: uniform control flow -- a per-lane
-// split of the 64 stores compiles to a 32-way divergent tail that cost more than the factorisation itself, 7.5 k cycles
-// against 1.7 k).  R is eliminated alongside L (Gauss-Jordan on [A | I]): row k of R is E_k / l_kk and E_i -= l_ik R_k
-// for i > k, so the inverse adds independent work to the pivot chain (rsqrt -> scale -> update) instead of a second
-// chain behind it.  Measured alternatives (tools/chol8_test.cu, cycles per tile for a lone warp): inverse after the
-// factor 1.73 k; this form 1.68 k; square-root-free with the products formed under the reciprocal 2.45 k (more FP64
-// instructions -- a lone warp issues one every ~3.5 cycles, so the instruction count, not the chain, sets the time);
-// [A | I] spread over the lanes with shuffles 1.61 k alone but slower inside the factorisation (56 k against 51 k cycles
-// at 135 variables).
+// shuffle or shared-memory round trip on the dependent chain) and stores every entry (same value, same address: uniform
+// control flow -- a per-lane split of the 64 stores compiled to a 32-way divergent tail that cost more than the
+// factorisation itself, 7.5 k cycles against 1.6 k).  R is eliminated alongside L (Gauss-Jordan on [A | I]): row k of R
+// is E_k / l_kk and E_i -= l_ik R_k for i > k.
+// The routine is bound by its pivot chain (rsqrt -> scale -> update, ~190 cycles per pivot), not by its instruction
+// count: measured with tools/chol8_test.cu (cycles per tile, lone warp) this form takes 1.55 k; the inverse split over
+// the lanes (lane j solves L r = e_j, 45 instructions instead of 120) 1.56 k; [A | I] spread over the lanes with shuffles
+// 1.61 k; square-root-free elimination with the products formed under the reciprocal 2.45 k; a float-seeded Newton rsqrt
+// instead of the library's 2.5 k (the conversions are slow).  QR_C8_DIAG / QR_C8_RSQRT keep two of them buildable.
 // A non-positive pivot is clamped; the caller's verification and finiteness checks catch a breakdown, as in qr_inv3_sym.
+__device__ __forceinline__ double qr_rsqrt_pos(double p) {
+    if (p > 1e-30 && p < 1e30) {   // float seed (23 bits) + two Newton steps: shorter than the library's chain
+        double r = (double)rsqrtf((float)p);
+        const double hp = 0.5 * p;
+        double e = fma(-hp * r, r, 0.5);
+        r = fma(r, e, r);
+        e = fma(-hp * r, r, 0.5);
+        return fma(r, e, r);
+    }
+    return rsqrt(p);
+}
+#ifndef QR_C8_DIAG
+#define QR_C8_DIAG 0
+#endif
+#ifndef QR_C8_RSQRT
+#define QR_C8_RSQRT(p) rsqrt(p)
+#endif
 __device__ __noinline__ void qr_chol8_diag(double* T) {
+#if QR_C8_DIAG == 0
     double a[36], E[36];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -84,7 +102,7 @@ __device__ __noinline__ void qr_chol8_diag(double* T) {
     for (int k = 0; k < 8; ++k) {
         double p = a[k * (k + 1) / 2 + k];
         if (!(p > 1e-300)) p = 1e-300;
-        const double r = rsqrt(p);
+        const double r = QR_C8_RSQRT(p);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {   // row k of R (zeros above the diagonal)
             const double v = j < k ? E[k * (k + 1) / 2 + j] * r : (j == k ? r : 0.0);
@@ -101,6 +119,42 @@ __device__ __noinline__ void qr_chol8_diag(double* T) {
             for (int j = 0; j <= k; ++j) E[i * (i + 1) / 2 + j] -= a[i * (i + 1) / 2 + k] * E[k * (k + 1) / 2 + j];
         }
     }
+#else
+    double a[36], d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) a[i * (i + 1) / 2 + j] = T[qr_k8_swz(i, j)];
+    __syncwarp();   // every lane has read the tile before any lane overwrites it
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        double p = a[k * (k + 1) / 2 + k];
+        if (!(p > 1e-300)) p = 1e-300;
+        const double r = QR_C8_RSQRT(p);
+        d[k] = r;
+#pragma unroll
+        for (int i = k + 1; i < 8; ++i) a[i * (i + 1) / 2 + k] *= r;
+#pragma unroll
+        for (int i = k + 1; i < 8; ++i)
+#pragma unroll
+            for (int j = k + 1; j <= i; ++j) a[i * (i + 1) / 2 + j] -= a[i * (i + 1) / 2 + k] * a[j * (j + 1) / 2 + k];
+    }
+    const int j = threadIdx.x & 7;
+    double col[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int m = 0; m + 1 < i; m += 2) {
+            s0 += a[i * (i + 1) / 2 + m] * col[m];
+            s1 += a[i * (i + 1) / 2 + m + 1] * col[m + 1];
+        }
+        if (i & 1) s0 += a[i * (i + 1) / 2 + i - 1] * col[i - 1];
+        col[i] = d[i] * ((i == j ? 1.0 : 0.0) - (s0 + s1));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) T[qr_k8_swz(i, j)] = col[i];
+#endif
 }
 
 // K = L L' in place (tiles below the diagonal: L_Ip; diagonal tiles: R_p = L_pp^-1), fused with the forward
@@ -228,7 +282,9 @@ __device__ __forceinline__ void qr_chol8_factor(double* K, double* y, const unsi
 
 // x = L'^-1 z after qr_chol8_factor (z in y): x_p = R_p' (z_p - sum_{I > p} L_Ip' x_I), evaluated right-looking -- once
 // x_p is known every z_J, J < p, loses L_pJ' x_p (one thread per entry, tile row p).  The first nout entries of x go to
-// out.  xs: 8 doubles of scratch.  All NT threads call it; ends with a CTA barrier.
+// out.  xs: 8 doubles of scratch.  All NT threads call it; ends with a CTA barrier.  (One barrier per step -- the eight
+// threads that finish z_{p-1} exchanging it by shuffle and forming x_{p-1} on the spot -- was measured slower: 18.4 k
+// against 14.5 k cycles at 27 tile rows; the shuffles and the divergent branch cost more than the barrier.)
 template <int NT>
 __device__ __forceinline__ void qr_chol8_backward(const double* K, double* y, double* xs, int nt, double* out, int nout) {
     for (int p = nt - 1; p >= 0; --p) {

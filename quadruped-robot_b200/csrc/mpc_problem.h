@@ -53,6 +53,13 @@ QR_HD int qr_coarse_cap(int nfcap) { return (3 * nfcap + 3) / 4; }
 #ifndef QR_COARSE2_MIN_CAP
 #define QR_COARSE2_MIN_CAP 48
 #endif
+// round caps of the two levels of those classes (pairs / pairs of pairs)
+#ifndef QR_COARSE_MAX_ROUNDS_2L_PAIR
+#define QR_COARSE_MAX_ROUNDS_2L_PAIR 2
+#endif
+#ifndef QR_COARSE_MAX_ROUNDS_2L_QUAD
+#define QR_COARSE_MAX_ROUNDS_2L_QUAD 2
+#endif
 QR_HD int qr_coarse2_cap(int nfcap) { return nfcap >= QR_COARSE2_MIN_CAP ? (3 * qr_coarse_cap(nfcap) + 3) / 4 : 0; }
 QR_HD size_t qr_kbytes(int nfcap) {
     size_t kb = (size_t)9 * qr_ntri(nfcap) * sizeof(double);
@@ -297,10 +304,10 @@ QR_DEV void qr_mpc_build_coarse(QrMpcSmem& S, const qr_qp_options& opt, int max_
     QrQpWork& W = S.W;
     const int nf = W.nf;
     C[0].ng = 0; C[0].Hs = S.Hc; C[0].g = S.gc; C[0].ubz = S.ubc; C[0].grp = S.grp;
-    C[0].max_rounds = max_rounds > 0 ? max_rounds : QR_COARSE_MAX_ROUNDS;
+    C[0].max_rounds = max_rounds > 0 ? max_rounds : (L2 ? QR_COARSE_MAX_ROUNDS_2L_PAIR : QR_COARSE_MAX_ROUNDS);
     if (L2) {
         C[1].ng = 0; C[1].Hs = S.Hc2; C[1].g = S.gc2; C[1].ubz = S.ubc2; C[1].grp = S.grp2;
-        C[1].max_rounds = C[0].max_rounds;
+        C[1].max_rounds = max_rounds > 0 ? max_rounds : QR_COARSE_MAX_ROUNDS_2L_QUAD;
     }
     if (!S.Hc || nf < 8 || (opt.flags & QR_QP_NO_PREDICTION)) return;
     const bool want2 = L2 && S.Hc2 != nullptr && nf >= QR_COARSE2_MIN_CAP - 7;

@@ -120,6 +120,44 @@ QR_DEV double qr_sym_matvec_row(const double* Hs, const double* v, int nf, int i
     return (a0 + a1) + a2;
 }
 
+#if defined(QR_ON_DEVICE)
+// q = Hs v + g on the rows of the foot-steps with act != 0 (all rows when act is null), four lanes per row: lane `part`
+// of a quad takes the blocks T = part (mod 4) and the partial sums meet by shuffle.  For the long-horizon classes, whose
+// Hessian streams from L2: with one thread per row a row is a serial chain of up to 72 dependent-latency L2 loads on the
+// 40 % of the threads whose foot-step has active rows (17 k cycles per round at h = 30).  Different summation order than
+// qr_sym_matvec_row (1e-16 relative), which is why the h <= 16 classes do not use it.
+template <int NT>
+__device__ __forceinline__ void qr_sym_matvec_quad(const double* Hs, const double* v, const double* g, const int* act,
+                                                   int nf, double* q) {
+    const int n = 3 * nf;
+    for (int item = threadIdx.x; item < 4 * n; item += NT) {   // NT and 4n are multiples of 4: a quad stays together
+        const int i = item >> 2, part = item & 3;
+        const int S = i / 3, a = i - 3 * S;
+        if (act && !act[S]) continue;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        const double* row = Hs + qr_blk(S, part) + 3 * a;
+#pragma unroll 4
+        for (int T = part; T <= S; T += 4, row += 36) {
+            a0 += row[0] * v[3 * T];
+            a1 += row[1] * v[3 * T + 1];
+            a2 += row[2] * v[3 * T + 2];
+        }
+#pragma unroll 4
+        for (int T = S + 1 + ((part - (S + 1)) & 3); T < nf; T += 4) {
+            const double* col = Hs + qr_blk(T, S) + a;
+            a0 += col[0] * v[3 * T];
+            a1 += col[3] * v[3 * T + 1];
+            a2 += col[6] * v[3 * T + 2];
+        }
+        double s = (a0 + a1) + a2;
+        const unsigned m = 0xFu << (threadIdx.x & 28);
+        s += __shfl_xor_sync(m, s, 1);
+        s += __shfl_xor_sync(m, s, 2);
+        if (part == 0) q[i] = s + g[i];
+    }
+}
+#endif
+
 // Row i of (Hs * p) where p is non-zero only on foot-steps whose cap row is active (act bit 4).
 QR_DEV double qr_sym_matvec_row_capped(const double* Hs, const double* p, const int* act, int nf, int i) {
     const int S = i / 3, a = i - 3 * S;
@@ -531,6 +569,53 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
         // One thread per PAIR of foot-steps: the 3x3 block H_{f1 f2} is loaded once and contributes its d1 x d2
         // entries Z_f1' (H_{f1 f2} Z_f2) -- the same products in the same order as an entry-wise evaluation, with a
         // ninth of its loads and a quarter of its instructions (this phase was 17 % of the kernel's instructions).
+#if defined(QR_ON_DEVICE)
+        if (big) {
+            // the same entries written to the 8x8-tile layout.  These classes run without a register cap, so the two
+            // loops are unrolled under predicates (nine independent entries in flight instead of one) and the tile
+            // address of a column is formed once.
+            QR_FOR(pidx, (nf * (nf + 1)) / 2) {
+                const int code = W.tri[pidx];
+                const int f1 = code >> 8, f2 = code & 255;   // f1 >= f2
+                const int d1 = W.flag[f1], d2 = W.flag[f2];
+                if (d1 != 0 && d2 != 0) {
+                    const double* Hb = W.Hs + qr_blk(f1, f2);
+                    double hb[9];
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) hb[e] = Hb[e];
+                    const int o1 = W.foff[f1], o2 = W.foff[f2];
+                    double y[9];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const double* yp = W.zv + 3 * (o1 + (a < d1 ? a : 0));
+                        y[3 * a] = yp[0]; y[3 * a + 1] = yp[1]; y[3 * a + 2] = yp[2];
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        if (c < d2) {
+                            const double* z2 = W.zv + 3 * (o2 + c);
+                            const double z0 = z2[0], z1 = z2[1], zz = z2[2];
+                            const double t0 = hb[0] * z0 + hb[1] * z1 + hb[2] * zz;
+                            const double t1 = hb[3] * z0 + hb[4] * z1 + hb[5] * zz;
+                            const double t2 = hb[6] * z0 + hb[7] * z1 + hb[8] * zz;
+                            const int r2 = o2 + c, Jt = r2 >> 3, cj = r2 & 7;
+                            double* colp = W.K + 64 * (Jt * nt8 - ((Jt * (Jt - 1)) >> 1) - Jt);
+#pragma unroll
+                            for (int a = 0; a < 3; ++a) {
+                                const int r1 = o1 + a;
+                                if (a < d1 && r2 <= r1) {
+                                    const double val = y[3 * a] * t0 + y[3 * a + 1] * t1 + y[3 * a + 2] * t2;
+                                    const int It = r1 >> 3, ri = r1 & 7;
+                                    colp[64 * It + qr_k8_swz(ri, cj)] = val;
+                                    if (It == Jt) colp[64 * It + qr_k8_swz(cj, ri)] = val;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        } else
+#endif
         QR_FOR(pidx, (nf * (nf + 1)) / 2) {
             const int code = W.tri[pidx];
             const int f1 = code >> 8, f2 = code & 255;   // f1 >= f2
@@ -555,13 +640,6 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
                         if (r2 <= r1) {
                             const double* y = W.zv + 3 * r1;
                             const double val = y[0] * t0 + y[1] * t1 + y[2] * t2;
-#if defined(QR_ON_DEVICE)
-                            if (big) {
-                                W.K[qr_k8_idx(nt8, r1, r2)] = val;
-                                if ((r1 >> 3) == (r2 >> 3)) W.K[qr_k8_idx(nt8, r2, r1)] = val;
-                                continue;
-                            }
-#endif
                             const int I = r1 / 3, ri = r1 - 3 * I;
                             double* blk = W.K + qr_kblk(nbr, I, J);
                             blk[3 * ri + rj] = val;
@@ -610,7 +688,7 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
             if constexpr (NT >= 128) {
                 qr_chol8_factor<NT>(W.K, W.wv, W.tri, nt8, 1);
                 QR_PROF(11);
-                qr_chol8_backward<NT>(W.K, W.wv, W.Dinv, nt8, W.dx, nred);   // Dinv is free on this path: 8 doubles of scratch
+                qr_chol8_backward<NT>(W.K, W.wv, W.Dinv, nt8, W.dx, nred);   // Dinv is free on this path: 16 doubles of scratch
                 QR_PROF(13);
             }
         } else
@@ -634,6 +712,11 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
         QR_PROF(5);
         // gradient rows of the foot-steps with active rows only: the verification reads nothing else (a free foot-step's
         // gradient is zero by construction), and with the Hessian in L2 this phase is bound by its L2 -> SM traffic
+#if defined(QR_ON_DEVICE)
+        if (NT >= 128 && W.k8) {
+            if constexpr (NT >= 128) qr_sym_matvec_quad<NT>(W.Hs, W.xn, W.g, W.act, nf, W.q);
+        } else
+#endif
         QR_FOR(i, n) {
             if (W.act[i / 3]) W.q[i] = qr_sym_matvec_row(W.Hs, W.xn, nf, i) + W.g[i];
         }

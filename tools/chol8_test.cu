@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(NT, 1) k_test(const double* Kd, const double* 
     double* out = y + 8 * nt + 8;
     double* Dinv = out + 8 * nt + 8;
     double* xs = Dinv + 9 * nb;
-    unsigned short* tri = reinterpret_cast<unsigned short*>(xs + 8);
+    unsigned short* tri = reinterpret_cast<unsigned short*>(xs + 16);
     for (int idx = threadIdx.x; idx < ntri3; idx += NT) {
         int I, J;
         qr_tri_decode(idx, I, J);
@@ -116,7 +116,7 @@ int main(int argc, char** argv) {
         cudaMemcpy(db, b.data(), nred * 8, cudaMemcpyHostToDevice);
         const int nt = (nred + 7) / 8, nbb = (nred + 2) / 3;
         size_t kd = std::max((size_t)9 * nbb * (nbb + 1) / 2, (size_t)64 * nt * (nt + 1) / 2);
-        size_t smem = (kd + 2 * (8 * nt + 8) + 9 * nbb + 8) * 8 + (size_t)nbb * (nbb + 1) / 2 * 2 + 64;
+        size_t smem = (kd + 2 * (8 * nt + 8) + 9 * nbb + 16) * 8 + (size_t)nbb * (nbb + 1) / 2 * 2 + 64;
         cudaFuncSetAttribute(k_test, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         for (int mode = 0; mode < 2; ++mode) {
             k_test<<<148, NT, smem>>>(dK, db, nred, reps, dx, dc, mode);
