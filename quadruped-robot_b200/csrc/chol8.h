@@ -28,6 +28,9 @@
 #ifndef QR_CHOL8_MIN_CAP
 #define QR_CHOL8_MIN_CAP 56  // workspace classes (stance foot-steps) whose K region is sized for the 8x8 layout
 #endif
+#ifndef QR_CHOL8_MIN_NT
+#define QR_CHOL8_MIN_NT 256  // team size from which the path is compiled in (one CTA per SM: the classes bound by step latency)
+#endif
 #ifndef QR_CHOL8_BIAS
 #define QR_CHOL8_BIAS 14     // trailing tiles each other warp takes before warp 0 (busy with the next diagonal factor) joins in
 #endif

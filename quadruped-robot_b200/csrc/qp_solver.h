@@ -559,7 +559,7 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
         QR_TRACE_ROUND(round, nred, W);
 #if defined(QR_ON_DEVICE)
         // large systems of the long-horizon classes: 8x8 tiles, blocked Cholesky on the FP64 tensor cores (chol8.h)
-        const bool big = NT >= 128 && W.k8 && nbr >= QR_CHOL8_MIN_NB;
+        const bool big = NT >= QR_CHOL8_MIN_NT && W.k8 && nbr >= QR_CHOL8_MIN_NB;
         const int nt8 = qr_k8_nt(nred);
 #else
         const bool big = false;
@@ -685,7 +685,7 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
         QR_PROF(4);
 #if defined(QR_ON_DEVICE)
         if (big) {
-            if constexpr (NT >= 128) {
+            if constexpr (NT >= QR_CHOL8_MIN_NT) {
                 qr_chol8_factor<NT>(W.K, W.wv, W.tri, nt8, 1);
                 QR_PROF(11);
                 qr_chol8_backward<NT>(W.K, W.wv, W.Dinv, nt8, W.dx, nred);   // Dinv is free on this path: 16 doubles of scratch
@@ -713,8 +713,8 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
         // gradient rows of the foot-steps with active rows only: the verification reads nothing else (a free foot-step's
         // gradient is zero by construction), and with the Hessian in L2 this phase is bound by its L2 -> SM traffic
 #if defined(QR_ON_DEVICE)
-        if (NT >= 128 && W.k8) {
-            if constexpr (NT >= 128) qr_sym_matvec_quad<NT>(W.Hs, W.xn, W.g, W.act, nf, W.q);
+        if (NT >= QR_CHOL8_MIN_NT && W.k8) {
+            if constexpr (NT >= QR_CHOL8_MIN_NT) qr_sym_matvec_quad<NT>(W.Hs, W.xn, W.g, W.act, nf, W.q);
         } else
 #endif
         QR_FOR(i, n) {
