@@ -397,7 +397,9 @@ def bench_wbc_and_full_step(pkg, capi, torch, stream, with_cpu=False, fp64_peak=
                                     "(BASELINE configs[4]); beyond the reference's own K_MAX_GAIT_SEGMENTS = 16",
                         "value": B / ms * 1e3, "unit": "QP/s", "ms_per_step": ms,
                         "not_converged": int((o30["status"] != 0).sum()),
-                        "rounds_mean": float(o30["iters"][:, 1].float().mean())}
+                        "rounds_mean": float(o30["iters"][:, 1].float().mean()),
+                        "factorisation": "reduced systems of >= 16 block columns: blocked Cholesky on 8x8 tiles with "
+                                         "mma.sync.m8n8k4.f64 (csrc/chol8.h); smaller ones: scalar 3x3-block LDL'"}
     tf30 = out["horizon30"]["value"] * F_ALG_FLOP_H30 / 1e12
     out["horizon30"]["roofline"] = {"bound": "fp64_fma", "achieved": tf30, "peak": fp64_peak, "unit": "TFLOP/s",
                                     "frac": (tf30 / fp64_peak) if fp64_peak else None, "algorithmic_flop_per_qp": F_ALG_FLOP_H30}
