@@ -47,6 +47,8 @@ typedef struct {
 } qr_mpc_params;
 
 #define QR_QP_NO_PREDICTION 1
+#define QR_QP_SCALAR_FACTOR 2   /* long-horizon size classes: factorise every reduced system with the scalar 3x3-block
+                                   LDL' instead of the tensor-core blocked Cholesky (csrc/chol8.h); diagnostics / tests */
 
 /* Solver knobs; pass NULL for the defaults written next to each field. */
 typedef struct {
@@ -54,6 +56,7 @@ typedef struct {
     int32_t max_ipm_iter;     /* 40    interior-point iteration cap (fallback path)               */
     int32_t max_polish_rounds;/* 12    active-set verification / correction rounds after it       */
     int32_t flags;            /* 0     QR_QP_NO_PREDICTION: skip the coarse active-set prediction (diagnostics / tests);
+                                       QR_QP_SCALAR_FACTOR: see above;
                                        occupies what used to be alignment padding: the layout is unchanged */
     double ipm_tol;           /* 1e-7  fallback: scaled stationarity and complementarity-gap tolerance */
     double act_kappa;         /* 1e3   constraint i is guessed active when s_i < kappa*lambda_i   */

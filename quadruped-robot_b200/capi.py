@@ -30,6 +30,7 @@ class QpOptions(C.Structure):
 
 
 QP_NO_PREDICTION = 1
+QP_SCALAR_FACTOR = 2
 
 
 def default_options() -> QpOptions:

@@ -36,7 +36,7 @@
 #endif
 
 #ifndef QR_C8P
-#define QR_C8P(tag) ((void)0)   // cycle marks of tools/chol8_test.cu
+#define QR_C8P(tag) ((void)0)   // cycle marks of tests/cpp/chol8_test.cu
 #endif
 
 QR_HD int qr_k8_nt(int nred) { return (nred + 7) >> 3; }
@@ -68,7 +68,7 @@ __device__ __forceinline__ void qr_dmma(double& c0, double& c1, double a, double
 // factorisation itself, 7.5 k cycles against 1.6 k).  R is eliminated alongside L (Gauss-Jordan on [A | I]): row k of R
 // is E_k / l_kk and E_i -= l_ik R_k for i > k.
 // The routine is bound by its pivot chain (rsqrt -> scale -> update, ~190 cycles per pivot), not by its instruction
-// count: measured with tools/chol8_test.cu (cycles per tile, lone warp) this form takes 1.55 k; the inverse split over
+// count: measured with tests/cpp/chol8_test.cu (cycles per tile, lone warp) this form takes 1.55 k; the inverse split over
 // the lanes (lane j solves L r = e_j, 45 instructions instead of 120) 1.56 k; [A | I] spread over the lanes with shuffles
 // 1.61 k; square-root-free elimination with the products formed under the reciprocal 2.45 k; a float-seeded Newton rsqrt
 // instead of the library's 2.5 k (the conversions are slow).  QR_C8_DIAG / QR_C8_RSQRT keep two of them buildable.

@@ -559,7 +559,7 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
         QR_TRACE_ROUND(round, nred, W);
 #if defined(QR_ON_DEVICE)
         // large systems of the long-horizon classes: 8x8 tiles, blocked Cholesky on the FP64 tensor cores (chol8.h)
-        const bool big = NT >= QR_CHOL8_MIN_NT && W.k8 && nbr >= QR_CHOL8_MIN_NB;
+        const bool big = NT >= QR_CHOL8_MIN_NT && W.k8 && nbr >= QR_CHOL8_MIN_NB && !(opt.flags & QR_QP_SCALAR_FACTOR);
         const int nt8 = qr_k8_nt(nred);
 #else
         const bool big = false;

@@ -1,5 +1,5 @@
-// tools/chol8_test.cu -- stand-alone check and timing of csrc/chol8.h against the 3x3-block LDL' of csrc/qp_solver.h.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o scratch/chol8_test tools/chol8_test.cu && scratch/chol8_test
+// tests/cpp/chol8_test.cu -- stand-alone check and timing of csrc/chol8.h against the 3x3-block LDL' of csrc/qp_solver.h.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tests/cpp/chol8_test tests/cpp/chol8_test.cu && tests/cpp/chol8_test
 // One 256-thread CTA per SM factorises a random SPD matrix of n = 3*nb variables held in shared memory and solves one
 // right-hand side; prints the residual of both paths and clock64 cycles per factorisation + solve.
 #include <cuda_runtime.h>
@@ -14,7 +14,7 @@ __device__ long long g_c8last;
 #ifdef C8PROF   // phase marks cost ~500 cycles each (global read-modify-write on the critical path): off for the totals
 #define QR_C8P(tag) do { if (threadIdx.x == 0 && blockIdx.x == 0) { long long n_ = clock64(); g_c8p[tag] += n_ - g_c8last; g_c8last = n_; } } while (0)
 #endif
-#include "../quadruped-robot_b200/csrc/qp_solver.h"
+#include "../../quadruped-robot_b200/csrc/qp_solver.h"
 
 constexpr int NT = 256;
 
