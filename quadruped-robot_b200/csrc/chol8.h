@@ -71,19 +71,27 @@ __device__ __forceinline__ void qr_dmma(double& c0, double& c1, double a, double
 // count: measured with tests/cpp/chol8_test.cu (cycles per tile, lone warp) this form takes 1.55 k; the inverse split over
 // the lanes (lane j solves L r = e_j, 45 instructions instead of 120) 1.56 k; [A | I] spread over the lanes with shuffles
 // 1.61 k; square-root-free elimination with the products formed under the reciprocal 2.45 k; a float-seeded Newton rsqrt
-// instead of the library's 2.5 k (the conversions are slow).  QR_C8_DIAG / QR_C8_RSQRT keep two of them buildable.
+// instead of the library's 2.5 k (the conversions are slow); rsqrt.approx.ftz.f64 + 2 / 3 Newton steps 1.38 / 1.56 k.
+// Warm, the routine is 1.3 k cycles = 8 x (89 for the library rsqrt + 85 for scale -> update -> clamp); the inverse and the
+// stores are free (hidden under the chain).  QR_C8_DIAG / QR_C8_RSQRT keep the variants buildable.
 // A non-positive pivot is clamped; the caller's verification and finiteness checks catch a breakdown, as in qr_inv3_sym.
-__device__ __forceinline__ double qr_rsqrt_pos(double p) {
-    if (p > 1e-30 && p < 1e30) {   // float seed (23 bits) + two Newton steps: shorter than the library's chain
-        double r = (double)rsqrtf((float)p);
-        const double hp = 0.5 * p;
-        double e = fma(-hp * r, r, 0.5);
+#ifndef QR_C8_NEWTON
+#define QR_C8_NEWTON 3
+#endif
+__device__ __forceinline__ double qr_rsqrt_pos(double p) {   // 1/sqrt(p) for a positive normal p: hardware seed + Newton
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
+    const double hp = 0.5 * p;
+#pragma unroll
+    for (int it = 0; it < QR_C8_NEWTON; ++it) {
+        const double e = fma(-hp * r, r, 0.5);
         r = fma(r, e, r);
-        e = fma(-hp * r, r, 0.5);
-        return fma(r, e, r);
     }
-    return rsqrt(p);
+    return r;
 }
+#ifndef QR_C8_NEWTON
+#define QR_C8_NEWTON 3
+#endif
 #ifndef QR_C8_DIAG
 #define QR_C8_DIAG 0
 #endif
