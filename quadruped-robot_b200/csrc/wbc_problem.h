@@ -37,14 +37,14 @@ struct QrWbcArgs {
 
 struct QrWbcWork {
     double *st, *cmd;
-    double *Xup, *Xur, *Xa, *IC, *T1, *T2;       // 13 / 12 / 13 / 13 / 12 / 12 blocks of 36
+    double *Xup, *Xur, *Xa, *IC, *T1, *T2;       // 13 / 12 / 13 / 13 / 4 / 4 blocks of 36 (T1, T2: one per leg, reused level by level)
     double *v, *vr, *cj, *cr, *avp, *avr, *ag, *agr, *fvp, *fvr;   // 6-vectors per body
     double *sq, *cq;                              // sin / cos of the joint angles
     double *H, *Ainv, *G, *Cq, *rowbuf, *colbuf;
     double *Jc, *Jcd, *pF, *vF;                   // feet: 4 x (3x18), 4x3, 4x3, 4x3
     double *Jt, *xdd, *jdq, *perr, *dvel;         // tasks (up to 6)
     double *JC, *JCd, *fdes;                      // stacked contacts
-    double *N, *N2, *M1;                          // 18x18 temporaries
+    double *N, *M1;                            // 18x18 temporaries
     double *Jpre, *Jbar, *Lam, *LamInv, *tmpA;    // weighted-inverse temporaries
     double *svdB, *svdV, *svdS;                   // Jacobi workspace
     double *qdd, *dq, *qdot, *vec, *tot, *P6, *a0, *A6;
@@ -56,13 +56,13 @@ struct QrWbcWork {
 // inertias, body velocities...) are dead once H, C, G and the foot Jacobians exist; the task / projector / QP
 // workspace of the later phases is laid over them.  This is what sets the number of robots in flight per SM.
 QR_HD size_t qr_wbc_dyn_doubles() {
-    return 36 * (13 + 12 + 13 + 13 + 12 + 12) + 6 * (13 + 12 + 12 + 12 + 13 + 12 + 13 + 12 + 13 + 12) + 24;
+    return 36 * (13 + 12 + 13 + 13 + 4 + 4) + 6 * (13 + 12 + 12 + 12 + 13 + 12 + 13 + 12 + 13 + 12) + 24;
 }
 QR_HD size_t qr_wbc_late_doubles() {
     size_t d = 6 * 54 + 6 * 12;                       // tasks
     d += 12 * 18 + 12 + 12;                           // stacked contacts
-    d += 324 * 3;                                     // N, N2, M1
-    d += 216 + 216 + 144 + 144 + 216;                 // weighted-inverse temporaries
+    d += 324 * 2;                                     // N, M1
+    d += 54 + 216 + 144 + 144;                        // JtPre (3 x 18), weighted-inverse temporaries (tmpA lives in M1)
     d += 216 + 144 + 12;                              // Jacobi workspace
     d += 18 * 5 + 72 + 6 + 36;
     // QP workspace for up to 4 contact blocks (its interior-point fallback vectors reuse the Jacobi workspace)
@@ -86,7 +86,7 @@ QR_DEV void qr_wbc_carve(QrWbcWork& W, unsigned char* base) {
     W.Jc = take(4 * 54); W.Jcd = take(12); W.pF = take(12); W.vF = take(12);
     double* const overlay = d;
     // ---- dynamics phase
-    W.Xup = take(36 * 13); W.Xur = take(36 * 12); W.Xa = take(36 * 13); W.IC = take(36 * 13); W.T1 = take(36 * 12); W.T2 = take(36 * 12);
+    W.Xup = take(36 * 13); W.Xur = take(36 * 12); W.Xa = take(36 * 13); W.IC = take(36 * 13); W.T1 = take(36 * 4); W.T2 = take(36 * 4);
     W.v = take(6 * 13); W.vr = take(6 * 12); W.cj = take(6 * 12); W.cr = take(6 * 12); W.avp = take(6 * 13); W.avr = take(6 * 12);
     W.ag = take(6 * 13); W.agr = take(6 * 12); W.fvp = take(6 * 13); W.fvr = take(6 * 12);
     W.sq = take(12); W.cq = take(12);
@@ -94,9 +94,11 @@ QR_DEV void qr_wbc_carve(QrWbcWork& W, unsigned char* base) {
     d = overlay;
     W.Jt = take(6 * 54); W.xdd = take(18); W.jdq = take(18); W.perr = take(18); W.dvel = take(18);
     W.JC = take(216); W.JCd = take(12); W.fdes = take(12);
-    W.N = take(324); W.N2 = take(324); W.M1 = take(324);
-    W.Jpre = take(216); W.Jbar = take(216); W.Lam = take(144); W.LamInv = take(144); W.tmpA = take(216);
+    W.N = take(324); W.M1 = take(324);
+    W.Jpre = take(54); W.Jbar = take(216); W.Lam = take(144); W.LamInv = take(144);
     W.svdB = take(216); W.svdV = take(144); W.svdS = take(12);
+    W.tmpA = W.M1;   // tm_weighted_inverse holds A^-1 J' across its tm_pinv call (which owns the Jacobi workspace); M1 is
+                     // only the scratch of tm_project_out / of the mass-matrix inverse, before and after it
     W.qdd = take(18); W.dq = take(18); W.qdot = take(18); W.vec = take(18); W.tot = take(18); W.P6 = take(72); W.a0 = take(6); W.A6 = take(36);
     QrQpWork& Q = W.Q;
     Q.k8 = 0;
@@ -458,7 +460,7 @@ QR_DEV void qr_wbc_dynamics(const QrWbcModelDev& M, QrWbcWork& W) {
             const double* X = which == 0 ? W.Xup + 36 * (1 + j) : W.Xur + 36 * j;
             double s = 0.0;
             for (int l = 0; l < 6; ++l) s += I[6 * r + l] * X[6 * l + c];
-            (which == 0 ? W.T1 : W.T2)[36 * j + e] = s;
+            (which == 0 ? W.T1 : W.T2)[36 * leg + e] = s;   // per level: one 6x6 per leg
         }
         QR_SYNC();
         if (lvl > 0) {
@@ -466,7 +468,7 @@ QR_DEV void qr_wbc_dynamics(const QrWbcModelDev& M, QrWbcWork& W) {
                 const int leg = idx / 36, e = idx - 36 * leg, r = e / 6, c = e - 6 * r;
                 const int j = 3 * leg + lvl;
                 double s = 0.0;
-                for (int l = 0; l < 6; ++l) s += W.Xup[36 * (1 + j) + 6 * l + r] * W.T1[36 * j + 6 * l + c] + W.Xur[36 * j + 6 * l + r] * W.T2[36 * j + 6 * l + c];
+                for (int l = 0; l < 6; ++l) s += W.Xup[36 * (1 + j) + 6 * l + r] * W.T1[36 * leg + 6 * l + c] + W.Xur[36 * j + 6 * l + r] * W.T2[36 * leg + 6 * l + c];
                 W.IC[36 * j + e] += s;   // parent body of joint j is body j (= 1 + (j - 1))
             }
         } else {
@@ -475,7 +477,7 @@ QR_DEV void qr_wbc_dynamics(const QrWbcModelDev& M, QrWbcWork& W) {
                 double s = 0.0;
                 for (int leg = 0; leg < 4; ++leg) {
                     const int j = 3 * leg;
-                    for (int l = 0; l < 6; ++l) s += W.Xup[36 * (1 + j) + 6 * l + r] * W.T1[36 * j + 6 * l + c] + W.Xur[36 * j + 6 * l + r] * W.T2[36 * j + 6 * l + c];
+                    for (int l = 0; l < 6; ++l) s += W.Xup[36 * (1 + j) + 6 * l + r] * W.T1[36 * leg + 6 * l + c] + W.Xur[36 * j + 6 * l + r] * W.T2[36 * leg + 6 * l + c];
                 }
                 W.IC[e] += s;
             }
