@@ -598,7 +598,7 @@ int mpc_enqueue(Ctx& cx, const qr_mpc_params* P, const qr_qp_options* opt, int b
         rc = ensure_scratch_doubles(*lane, pl.scratch_doubles(cap));
         if (rc) return rc;
         A.nfcap = cap;
-        A.coarse_rounds = QR_COARSE_MAX_ROUNDS_LAT;
+        A.coarse_rounds = two_levels ? 0 : QR_COARSE_MAX_ROUNDS_LAT;   // two-level classes: their own per-level caps
         bind_scratch(A, pl, cap, *lane);
         if (two_levels) qr_mpc_fused_latency_kernel<true><<<pl.grid, QR_LAT_NT, pl.smem, st>>>(A);
         else qr_mpc_fused_latency_kernel<false><<<pl.grid, QR_LAT_NT, pl.smem, st>>>(A);
