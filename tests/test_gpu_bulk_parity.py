@@ -33,6 +33,9 @@ CONFIGS = [
     ("lite3_h5_trot", "lite3", 5, 0.06, "trot", False, 2048, True),      # the shipped Lite3 default
     ("lite3_h10_trot", "lite3", 10, 0.03, "trot", False, 2048, True),    # configs[1]
     ("a1_h16_trot", "a1", 16, 0.03, "trot", False, 2048, True),          # the reference's largest horizon
+    # all four legs in stance at the reference's largest horizon: 64 stance foot-steps, i.e. the size class whose reduced
+    # systems are factorised on the FP64 tensor cores (csrc/chol8.h) -- that path against the reference's own build
+    ("a1_h16_stand", "a1", 16, 0.03, "stand", False, 512, True),
 ]
 
 
