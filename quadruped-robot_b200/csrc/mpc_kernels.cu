@@ -1008,13 +1008,19 @@ namespace {
 #endif
 constexpr int QR_WBC_NT = QR_WBC_NT_DEF;
 
-__global__ void __launch_bounds__(QR_WBC_NT) qr_wbc_kernel(const QrWbcArgs A) {
+// QR_WBC_TEAMS robots per CTA, each with its own team of QR_WBC_NT threads, workspace and named barrier (qr_team.h).
+#ifndef QR_WBC_TEAMS
+#define QR_WBC_TEAMS 2
+#endif
+static_assert(QR_WBC_TEAMS == 1 || QR_WBC_NT == QR_MULTI_TEAM_NT, "several teams per CTA need the multi-team thread index");
+__global__ void __launch_bounds__(QR_WBC_NT * QR_WBC_TEAMS) qr_wbc_kernel(const QrWbcArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NT = QR_WBC_NT;
+    const int team = threadIdx.x / NT;
     QrWbcWork W;
-    qr_wbc_carve(W, smem);
+    qr_wbc_carve(W, smem + (size_t)team * qr_wbc_smem_bytes());
     qr_wbc_init_tables<NT>(W);
-    for (int prob = blockIdx.x; prob < A.batch; prob += gridDim.x) qr_wbc_problem<NT>(A, prob, W);
+    for (int prob = blockIdx.x * QR_WBC_TEAMS + team; prob < A.batch; prob += gridDim.x * QR_WBC_TEAMS) qr_wbc_problem<NT>(A, prob, W);
 }
 
 __global__ void qr_swing_parabola_kernel(int batch, const float* start, const float* end, const float* height,
@@ -1072,22 +1078,22 @@ int wbc_launch(Ctx& cx, const qr_wbc_model* model, int batch, const float* state
     const QrWbcModelDev* dev_model = nullptr;
     int rc = wbc_model_on_device(cx, model, &dev_model);
     if (rc) return rc;
-    const size_t smem = qr_wbc_smem_bytes();
+    const size_t smem = qr_wbc_smem_bytes() * QR_WBC_TEAMS;
     if (!cx.wbc_occ) {
         cudaError_t e = cudaFuncSetAttribute(qr_wbc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(QR_ECUDA, "cudaFuncSetAttribute(wbc)", e);
         int occ = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qr_wbc_kernel, QR_WBC_NT, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qr_wbc_kernel, QR_WBC_NT * QR_WBC_TEAMS, smem);
         if (e != cudaSuccess) return fail(QR_ECUDA, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(wbc)", e);
         cx.wbc_occ = occ < 1 ? 1 : occ;
     }
     int grid = cx.sm_count * cx.wbc_occ;
-    if (grid > batch) grid = batch;
+    if (grid > (batch + QR_WBC_TEAMS - 1) / QR_WBC_TEAMS) grid = (batch + QR_WBC_TEAMS - 1) / QR_WBC_TEAMS;
     A.model = dev_model;
     A.opt = default_options();
     A.batch = batch;
     A.state = state; A.cmd = cmd; A.contact = contact;
-    qr_wbc_kernel<<<grid, QR_WBC_NT, smem, st>>>(A);
+    qr_wbc_kernel<<<grid, QR_WBC_NT * QR_WBC_TEAMS, smem, st>>>(A);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(QR_ECUDA, "launch qr_wbc_kernel", e);
     return QR_OK;

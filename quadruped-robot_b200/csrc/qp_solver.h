@@ -391,8 +391,8 @@ QR_DEV void qr_ldl_backward(QrQpWork& W, int nb, double* out QR_PROF_ARG) {
     double* y = W.wv;
 #ifdef QR_ON_DEVICE
     if (NT >= 32 && nb <= 32) {
-        if (threadIdx.x < 32) {
-            const int lane = threadIdx.x;
+        if (qr_tid<NT>() < 32) {
+            const int lane = qr_tid<NT>();
             const int me = lane < nb ? lane : 0;
             double y0 = y[3 * me], y1 = y[3 * me + 1], y2 = y[3 * me + 2];
             const double* Di = W.Dinv + 9 * me;

@@ -22,25 +22,47 @@
 #define QR_HD inline
 #endif
 
+#ifndef QR_MULTI_TEAM_NT
+#define QR_MULTI_TEAM_NT 64   // team size that may share a CTA with other teams (device: see qr_tid below)
+#endif
+
 #if defined(__CUDA_ARCH__)
 // ---- device ------------------------------------------------------------------------------
 #define QR_ON_DEVICE 1
+// Teams of QR_MULTI_TEAM_NT threads (the WBC team size; no MPC size class uses it) may share a CTA: thread t belongs to
+// team t / NT, its index in the team is t % NT, and the team's barrier is the named barrier 1 + team.  Several robots per
+// CTA run the same code at nearly the same time, so the CTA fetches an instruction line once for all of them -- the WBC
+// kernel's body is 20 k instructions executed once per robot, and the instruction caches are what bounds it.
+template <int NT>
+__device__ __forceinline__ int qr_tid() {
+    return NT == QR_MULTI_TEAM_NT ? (int)(threadIdx.x % NT) : (int)threadIdx.x;
+}
 template <int NT>
 __device__ __forceinline__ void qr_team_sync() {
-    if (NT <= 32) __syncwarp(); else __syncthreads();
+    if (NT <= 32) __syncwarp();
+    else if (NT == QR_MULTI_TEAM_NT) asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x / NT)), "n"(NT) : "memory");
+    // (immediate barrier numbers behind a switch on the team were measured: 6.8 -> 4.6 M robots/s, the four copies of
+    // every barrier site inflate a kernel that is bound by instruction fetch)
+    else __syncthreads();
 }
-#define QR_FOR(i, n) for (int i = threadIdx.x; i < (n); i += NT)
+#define QR_FOR(i, n) for (int i = qr_tid<NT>(); i < (n); i += NT)
 // strided loop over the entries (i, j) of an m x n row-major array: the row / column of an entry follow from the previous
 // one by additions (one integer division per loop instead of one per entry)
 #define QR_FOR_2D(idx, i, j, m, n)                                                                                    \
-    for (int idx = threadIdx.x, _qn = (n), _qdi = NT / _qn, _qdj = NT - _qdi * _qn, i = idx / _qn, j = idx - i * _qn; \
+    for (int idx = qr_tid<NT>(), _qn = (n), _qdi = NT / _qn, _qdj = NT - _qdi * _qn, i = idx / _qn, j = idx - i * _qn; \
          idx < (m) * _qn; idx += NT, i += _qdi, j += _qdj, i += (j >= _qn), j -= (j >= _qn) ? _qn : 0)
-#define QR_THREADS(t) for (int t = threadIdx.x, _qr_once = 1; _qr_once; _qr_once = 0)
+#define QR_THREADS(t) for (int t = qr_tid<NT>(), _qr_once = 1; _qr_once; _qr_once = 0)
 #define QR_SYNC() qr_team_sync<NT>()
 // barrier + "does any thread of the team hold a non-zero flag"
 template <int NT>
 __device__ __forceinline__ int qr_team_any(int v) {
     if (NT <= 32) { int r = __any_sync(0xffffffffu, v); __syncwarp(); return r; }
+    if (NT == QR_MULTI_TEAM_NT) {
+        int r;
+        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %1, 0;\n\tbar.red.or.pred p, %2, %3, q;\n\tselp.s32 %0, 1, 0, p;\n\t}"
+                     : "=r"(r) : "r"(v), "r"(1 + (int)(threadIdx.x / NT)), "n"(NT) : "memory");
+        return r;
+    }
     return __syncthreads_or(v);
 }
 #define QR_ANY(v) qr_team_any<NT>(v)

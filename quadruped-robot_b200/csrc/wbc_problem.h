@@ -76,7 +76,9 @@ QR_HD size_t qr_wbc_smem_doubles() {
     const size_t a = qr_wbc_dyn_doubles(), b = qr_wbc_late_doubles();
     return d + (a > b ? a : b) + 8;
 }
-QR_HD size_t qr_wbc_smem_bytes() { return qr_wbc_smem_doubles() * sizeof(double) + (16 + 4 * 3 + 5 + 12 + 16) * sizeof(int) + 32; }
+QR_HD size_t qr_wbc_smem_bytes() {   // per robot, a multiple of 16 (several robots' workspaces sit back to back in one CTA)
+    return (qr_wbc_smem_doubles() * sizeof(double) + (16 + 4 * 3 + 5 + 12 + 16) * sizeof(int) + 32 + 15) & ~(size_t)15;
+}
 
 QR_DEV void qr_wbc_carve(QrWbcWork& W, unsigned char* base) {
     double* d = reinterpret_cast<double*>(base);
