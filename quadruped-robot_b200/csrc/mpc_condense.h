@@ -24,6 +24,11 @@
 // MINI_EIGEN_EXP_NILPOTENT3); against the scaling-and-squaring Pade evaluation of Eigen's MatrixFunctions the
 // entries agree to 3e-7 relative (float32 rounding of the Pade steps), not bitwise.
 #pragma once
+// Loops of the once-per-instance phases are kept rolled: the throughput kernels are bound by instruction fetch, and an
+// unrolled copy of a loop body is code that evicts the active-set round loop of the other CTAs on the SM.
+#ifndef QR_UNROLL_SMALL
+#define QR_UNROLL_SMALL _Pragma("unroll 1")
+#endif
 
 #include "qr_team.h"
 #include "../../include/qr_gpu.h"
@@ -235,6 +240,7 @@ QR_DEV void qr_condense_h_pair(const QrCondenseTables& T, int h, int i, int la, 
     const QrF4* gga = &T.Gx[r0 - i][ca];
     const QrF4* tgb = &T.TGx[r0 - j][cb];
     const QrF4* ggb = &T.Gx[r0 - j][cb];
+    QR_UNROLL_SMALL
     for (int r = r0; r < h; ++r, tga += 12, gga += 12, tgb += 12, ggb += 12) {
         const QrF4 a = *tga, b = *ggb;     // entry (s, t): TGx[r - i][ca] . Gx[r - j][cb]
         const QrF4 c = *tgb, d = *gga;     // entry (t, s): TGx[r - j][cb] . Gx[r - i][ca]
@@ -262,6 +268,7 @@ QR_DEV void qr_condense_h_pair(const QrCondenseTables& T, int h, int i, int la, 
 QR_DEV float qr_condense_g_entry(const QrCondenseTables& T, int h, int i, int la, int aa) {
     const int ca = 3 * la + aa;
     float s = 0.f;
+    QR_UNROLL_SMALL
     for (int j = i; j < h; ++j) {
         const QrF4 a = T.TGx[j - i][ca];
         s = QR_FADD(s, QR_FMUL(a.x, T.e[j][0]));

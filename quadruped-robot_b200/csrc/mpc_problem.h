@@ -206,6 +206,7 @@ QR_DEV void qr_mpc_stage(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
             const float mu = A.mu_i ? A.mu_i[prob] : A.P.mu;
             S.scal[0] = (double)QR_FDIV(1.f, mu);        // mu_ = 1.f / frictionCoeff (qr_mpc_interface.cpp:230)
             int nf = 0, st = 0;
+            QR_UNROLL_SMALL
             for (int k = 0; k < 4 * h; ++k) {
                 const float ub = QR_FMUL(S.gait[k], fmax);   // U_b(5k+4) = gait * fMax (:387)
                 if (ub > 0.f && nf < A.nfcap) {
@@ -217,6 +218,7 @@ QR_DEV void qr_mpc_stage(const QrMpcArgs& A, int prob, QrMpcSmem& S) {
                     if (ub > 0.f) st = 3;  // over capacity: the size classification makes this unreachable
                 }
             }
+            QR_UNROLL_SMALL
             for (int i = 0; i < 28; ++i) if (!(fabsf(S.state[i]) < 3.0e38f)) st = 3;
             if (!(mu > 0.f)) st = 3;
             S.misc[0] = st;

@@ -45,11 +45,16 @@ __device__ __forceinline__ void qr_team_sync() {
     // every barrier site inflate a kernel that is bound by instruction fetch)
     else __syncthreads();
 }
-#define QR_FOR(i, n) for (int i = qr_tid<NT>(); i < (n); i += NT)
+// (rolled: a team loop runs one to three iterations per thread, and an unrolled copy of its body is only more code for
+// kernels that are bound by instruction fetch)
+#ifndef QR_FOR_UNROLL
+#define QR_FOR_UNROLL _Pragma("unroll 1")
+#endif
+#define QR_FOR(i, n) QR_FOR_UNROLL for (int i = qr_tid<NT>(); i < (n); i += NT)
 // strided loop over the entries (i, j) of an m x n row-major array: the row / column of an entry follow from the previous
 // one by additions (one integer division per loop instead of one per entry)
 #define QR_FOR_2D(idx, i, j, m, n)                                                                                    \
-    for (int idx = qr_tid<NT>(), _qn = (n), _qdi = NT / _qn, _qdj = NT - _qdi * _qn, i = idx / _qn, j = idx - i * _qn; \
+    QR_FOR_UNROLL for (int idx = qr_tid<NT>(), _qn = (n), _qdi = NT / _qn, _qdj = NT - _qdi * _qn, i = idx / _qn, j = idx - i * _qn; \
          idx < (m) * _qn; idx += NT, i += _qdi, j += _qdj, i += (j >= _qn), j -= (j >= _qn) ? _qn : 0)
 #define QR_THREADS(t) for (int t = qr_tid<NT>(), _qr_once = 1; _qr_once; _qr_once = 0)
 #define QR_SYNC() qr_team_sync<NT>()
