@@ -101,16 +101,21 @@ QR_DEV double qr_rsqrt(double v) {
 
 // Row i of (Hs * v), Hs symmetric block-packed.  Three independent accumulators keep the FMA
 // dependency chain a third as long.
-QR_DEV double qr_sym_matvec_row(const double* Hs, const double* v, int nf, int i) {
+// SMALL (the WBC force QP: at most four blocks, Hessian in shared memory): loops kept rolled -- the default fourfold
+// unrolling is only code there, and that kernel is bound by instruction fetch.
+template <bool SMALL>
+QR_DEV double qr_sym_matvec_row_t(const double* Hs, const double* v, int nf, int i) {
     const int S = i / 3, a = i - 3 * S;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
     const double* row = Hs + qr_blk(S, 0) + 3 * a;
+#pragma unroll(SMALL ? 1 : 4)
     for (int T = 0; T <= S; ++T, row += 9) {
         a0 += row[0] * v[3 * T];
         a1 += row[1] * v[3 * T + 1];
         a2 += row[2] * v[3 * T + 2];
     }
     const double* col = Hs + qr_blk(S + 1, S) + a;
+#pragma unroll(SMALL ? 1 : 4)
     for (int T = S + 1; T < nf; ++T) {
         a0 += col[0] * v[3 * T];
         a1 += col[3] * v[3 * T + 1];
@@ -119,6 +124,7 @@ QR_DEV double qr_sym_matvec_row(const double* Hs, const double* v, int nf, int i
     }
     return (a0 + a1) + a2;
 }
+QR_DEV double qr_sym_matvec_row(const double* Hs, const double* v, int nf, int i) { return qr_sym_matvec_row_t<false>(Hs, v, nf, i); }
 
 #if defined(QR_ON_DEVICE)
 // q = Hs v + g on the rows of the foot-steps with act != 0 (all rows when act is null), four lanes per row: lane `part`
@@ -718,7 +724,7 @@ QR_DEV int qr_active_set(QrQpWork& W, const qr_qp_options& opt, int* ok, int col
         } else
 #endif
         QR_FOR(i, n) {
-            if (W.act[i / 3]) W.q[i] = qr_sym_matvec_row(W.Hs, W.xn, nf, i) + W.g[i];
+            if (W.act[i / 3]) W.q[i] = qr_sym_matvec_row_t<(NT <= 64)>(W.Hs, W.xn, nf, i) + W.g[i];
         }
         QR_SYNC();
         QR_PROF(6);
