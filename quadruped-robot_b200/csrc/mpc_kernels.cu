@@ -1000,15 +1000,17 @@ extern "C" int qr_gpu_debug_profile(unsigned long long* out64) {
 
 namespace {
 
-// Threads per robot.  Shared memory (36.8 KB per robot) fixes six robots in flight per SM whatever the team size, so the
-// team size sets the number of warps that hide each other's latency: measured on B200 (Lite3, 65536 robots, outputs
-// bit-identical) 32 / 64 / 96 / 128 threads -> 4.63 / 5.90 / 5.23 / 5.06 M robots/s (batch 1024: 4.47 / 5.63 / 6.29 / 6.01).
+// Threads per robot, measured on B200 with one robot per CTA and six robots per SM (Lite3, 65536 robots, outputs
+// bit-identical): 32 / 64 / 96 / 128 threads -> 4.63 / 5.90 / 5.23 / 5.06 M robots/s (batch 1024: 4.47 / 5.63 / 6.29 / 6.01).
+// (The workspace is 32.2 KB per robot now; the kernel turned out to be bound by instruction fetch, not by residency.)
 #ifndef QR_WBC_NT_DEF
 #define QR_WBC_NT_DEF 64
 #endif
 constexpr int QR_WBC_NT = QR_WBC_NT_DEF;
 
-// QR_WBC_TEAMS robots per CTA, each with its own team of QR_WBC_NT threads, workspace and named barrier (qr_team.h).
+// QR_WBC_TEAMS robots per CTA, each with its own team of QR_WBC_NT threads, workspace and named barrier (qr_team.h): the
+// teams run the same code at nearly the same time, so an instruction line is fetched once for all of them.  Measured
+// (65536 robots): 1 / 2 / 3 / 4 robots per CTA -> 7.2 (5.4 on the named barrier) / 8.55 / 8.33 / 7.16 M robots/s.
 #ifndef QR_WBC_TEAMS
 #define QR_WBC_TEAMS 2
 #endif
