@@ -1010,7 +1010,7 @@ constexpr int QR_WBC_NT = QR_WBC_NT_DEF;
 
 // QR_WBC_TEAMS robots per CTA, each with its own team of QR_WBC_NT threads, workspace and named barrier (qr_team.h): the
 // teams run the same code at nearly the same time, so an instruction line is fetched once for all of them.  Measured
-// (65536 robots): 1 / 2 / 3 / 4 robots per CTA -> 7.2 (5.4 on the named barrier) / 8.55 / 8.33 / 7.16 M robots/s.
+// (65536 robots, every variant on the named barrier): 1 / 2 / 3 / 4 robots per CTA -> 6.76 / 8.55 / 8.33 / 7.16 M robots/s.
 #ifndef QR_WBC_TEAMS
 #define QR_WBC_TEAMS 2
 #endif
